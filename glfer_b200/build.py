@@ -1,0 +1,93 @@
+"""Build recipe for libglfer_b200.so (CUDA kernels for sm_100a + C host layer), in-tree.
+
+`python -m glfer_b200.build` or glfer_b200.build.build().  nvcc cross-compiles without a
+GPU; the resulting .so travels to the GPU box with the repository snapshot."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "libglfer_b200.so")
+OBJ = os.path.join(HERE, "_build")
+
+CU_SOURCES = ["csrc/gram_kernels.cu"]
+C_SOURCES = ["host/window.c", "host/dpss.c", "host/gram.c", "host/dropin.c", "host/wav.c"]
+HEADERS = ["csrc/fft_core.cuh", "csrc/tables.hpp", "host/glb_host.h", "../include/glb_shim.h", "../include/fft.h",
+           "../include/mtm.h", "../include/avg.h", "../include/glfer_b200.h"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# no -march=native / -ffast-math: the window tables must round exactly like the reference's
+C_FLAGS = ["-O2", "-fPIC", "-std=gnu11", "-Wall", "-Wno-unused-function", "-pthread"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(cmd: list[str], log: str | None = None) -> None:
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log:
+        with open(log, "w") as fh:
+            fh.write(" ".join(cmd) + "\n" + res.stdout)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    nvcc = _nvcc()
+    for src in CU_SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(OBJ, os.path.basename(src) + ".o")
+        if force or _stale(o, [s] + hdrs):
+            if verbose:
+                print("nvcc", src)
+            _run([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o], log=o + ".log")
+        objs.append(o)
+    for src in C_SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(OBJ, os.path.basename(src) + ".o")
+        if force or _stale(o, [s] + hdrs):
+            if verbose:
+                print("gcc", src)
+            _run(["gcc"] + C_FLAGS + ["-c", s, "-o", o])
+        objs.append(o)
+    if force or _stale(LIB, objs):
+        if verbose:
+            print("link", LIB)
+        # nvcc links the static CUDA runtime: the .so depends on libcuda only at run time
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-pthread", "-lm", "-lpthread"])
+    return LIB
+
+
+def build_tools(force: bool = False) -> str:
+    """The headless harness (tools/glfer_headless.c) against the product library."""
+    build(force=False)
+    out = os.path.join(ROOT, "tools", "glfer_headless")
+    src = os.path.join(ROOT, "tools", "glfer_headless.c")
+    if os.path.exists(src) and (force or _stale(out, [src, LIB])):
+        _run(["gcc", "-O2", "-std=gnu11", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+              "-L", HERE, "-lglfer_b200", "-Wl,-rpath," + HERE, "-lm"])
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

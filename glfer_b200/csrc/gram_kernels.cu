@@ -1,0 +1,791 @@
+// gram_kernels.cu -- sm_100a kernels of the spectrogram hot path + the C-ABI shim.
+//
+// Kernels (all hand-written, no library FFT):
+//   gram_kernel<M>        overlapped-frame gather -> [block-mean removal] -> [RA9MB] ->
+//                         taper multiply -> [limiter] -> real FFT (N = 2M, in registers +
+//                         swizzled shared memory) -> |X|^2 -> [sum over K' tapers with the
+//                         1/lambda weights folded into the tapers] -> [10 log10] -> one PSD
+//                         row per frame straight to HBM.  Replaces prepare_audio + fft_do +
+//                         fft_psd (fft.c:66-226) and the taper loop of mtm_do (mtm.c:189-220).
+//   block_means_kernel    mean of every hop block (prepare_audio, fft.c:86-96).
+//   avg_kernel            sliding per-bin frame averaging, three normalisations
+//                         (update_avg_*, avg.c:108-298).
+//   peak_carry_kernel     the carried *peakbin of avg.c:129-133.
+//   pcm*_to_float_kernel  WAV sample conversion (wav_fmt.c:105-116).
+//
+// No tensor cores: the path is an FFT at ~9 flop/B executed, bound by HBM and the
+// FP32/shared-memory pipes, not a dense contraction.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <vector>
+#include <algorithm>
+
+#include "fft_core.cuh"
+#include "tables.hpp"
+#include "../../include/glb_shim.h"
+
+using namespace glb;
+
+// ------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+extern "C" const char *glb_last_error(void) { return g_err; }
+extern "C" void glb_set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
+extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load(); }
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+               __FILE__, __LINE__);                                                           \
+      return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? GLB_ENODEV      \
+             : (e_ == cudaErrorMemoryAllocation ? GLB_ENOMEM : GLB_ECUDA);                    \
+    }                                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------- plumbing
+extern "C" int glb_device_count(int *count) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    *count = 0;
+    return GLB_ENODEV;
+  }
+  *count = c;
+  return GLB_OK;
+}
+extern "C" int glb_set_device(int dev) { CU(cudaSetDevice(dev)); return GLB_OK; }
+extern "C" int glb_sm_count(int dev, int *sms) {
+  CU(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return GLB_OK;
+}
+extern "C" int glb_malloc(void **p, size_t bytes) { CU(cudaMalloc(p, bytes ? bytes : 1)); return GLB_OK; }
+extern "C" int glb_free(void *p) { if (p) CU(cudaFree(p)); return GLB_OK; }
+extern "C" int glb_memset(void *p, int v, size_t bytes, void *s) {
+  CU(cudaMemsetAsync(p, v, bytes, (cudaStream_t) s));
+  return GLB_OK;
+}
+extern "C" int glb_host_alloc(void **p, size_t bytes) { CU(cudaMallocHost(p, bytes ? bytes : 1)); return GLB_OK; }
+extern "C" int glb_host_free(void *p) { if (p) CU(cudaFreeHost(p)); return GLB_OK; }
+static int copy_(void *d, const void *s, size_t n, cudaMemcpyKind k, void *stream) {
+  if (n == 0) return GLB_OK;
+  if (stream) CU(cudaMemcpyAsync(d, s, n, k, (cudaStream_t) stream));
+  else CU(cudaMemcpy(d, s, n, k));
+  return GLB_OK;
+}
+extern "C" int glb_memcpy_h2d(void *d, const void *s, size_t n, void *st) { return copy_(d, s, n, cudaMemcpyHostToDevice, st); }
+extern "C" int glb_memcpy_d2h(void *d, const void *s, size_t n, void *st) { return copy_(d, s, n, cudaMemcpyDeviceToHost, st); }
+extern "C" int glb_memcpy_d2d(void *d, const void *s, size_t n, void *st) { return copy_(d, s, n, cudaMemcpyDeviceToDevice, st); }
+extern "C" int glb_stream_create(void **s) {
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *s = st;
+  return GLB_OK;
+}
+extern "C" int glb_stream_destroy(void *s) { if (s) CU(cudaStreamDestroy((cudaStream_t) s)); return GLB_OK; }
+extern "C" int glb_stream_sync(void *s) { CU(cudaStreamSynchronize((cudaStream_t) s)); return GLB_OK; }
+extern "C" int glb_stream_wait_event(void *s, void *e) { CU(cudaStreamWaitEvent((cudaStream_t) s, (cudaEvent_t) e, 0)); return GLB_OK; }
+extern "C" int glb_device_sync(void) { CU(cudaDeviceSynchronize()); return GLB_OK; }
+extern "C" int glb_event_create(void **e) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); *e = ev; return GLB_OK; }
+extern "C" int glb_event_destroy(void *e) { if (e) CU(cudaEventDestroy((cudaEvent_t) e)); return GLB_OK; }
+extern "C" int glb_event_record(void *e, void *s) { CU(cudaEventRecord((cudaEvent_t) e, (cudaStream_t) s)); return GLB_OK; }
+extern "C" int glb_event_sync(void *e) { CU(cudaEventSynchronize((cudaEvent_t) e)); return GLB_OK; }
+extern "C" int glb_event_elapsed_ms(void *a, void *b, float *ms) {
+  CU(cudaEventElapsedTime(ms, (cudaEvent_t) a, (cudaEvent_t) b));
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------- tables
+struct GramTables {
+  int n;
+  float2 *tw;
+  float2 *vtab;
+};
+
+template <int M> static std::vector<float2> tw_for() { return build_twiddles<M>(); }
+
+static bool host_twiddles(int m, std::vector<float2> &tw) {
+  switch (m) {
+    case 16: tw = tw_for<16>(); return true;
+    case 32: tw = tw_for<32>(); return true;
+    case 64: tw = tw_for<64>(); return true;
+    case 128: tw = tw_for<128>(); return true;
+    case 256: tw = tw_for<256>(); return true;
+    case 512: tw = tw_for<512>(); return true;
+    case 1024: tw = tw_for<1024>(); return true;
+    case 2048: tw = tw_for<2048>(); return true;
+    case 4096: tw = tw_for<4096>(); return true;
+    case 8192: tw = tw_for<8192>(); return true;
+    case 16384: tw = tw_for<16384>(); return true;
+    default: return false;
+  }
+}
+
+extern "C" int glb_fft_supported(int n) {
+  return n >= 32 && n <= 32768 && (n & (n - 1)) == 0;
+}
+
+extern "C" int glb_tables_create(int n, void **out) {
+  if (!glb_fft_supported(n)) {
+    snprintf(g_err, sizeof g_err, "FFT size %d unsupported (power of two, 32..32768)", n);
+    return GLB_EINVAL;
+  }
+  std::vector<float2> tw;
+  host_twiddles(n / 2, tw);
+  std::vector<float2> vt = build_vtab(n / 2);
+  GramTables *t = new GramTables();
+  t->n = n;
+  t->tw = nullptr;
+  t->vtab = nullptr;
+  CU(cudaMalloc(&t->tw, tw.size() * sizeof(float2)));
+  CU(cudaMalloc(&t->vtab, vt.size() * sizeof(float2)));
+  CU(cudaMemcpy(t->tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t->vtab, vt.data(), vt.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  *out = t;
+  return GLB_OK;
+}
+
+extern "C" int glb_tables_destroy(void *tp) {
+  GramTables *t = (GramTables *) tp;
+  if (!t) return GLB_OK;
+  cudaFree(t->tw);
+  cudaFree(t->vtab);
+  delete t;
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------- gram kernel
+struct KParams {
+  const float *samples;
+  long long origin, count;
+  const float *tapers;
+  int ntapers;
+  const float *means;
+  long long means_first_block;
+  int hop, n_ov, cblk;        // cblk = ceil(n_ov / hop)
+  float inv_hop;
+  float ra9mb_a;
+  int limiter;
+  float lim_scale;            // taper_scale^0.9
+  float spec_scale;           // 1 / (2 taper_scale)
+  long long first_frame, nframes;
+  int frames_per_group;
+  float *rows;
+  long long row_stride;
+  int rows_db;
+  float2 *spectrum;
+  const float2 *tw, *vtab;
+};
+
+#ifndef GLB_REG_TARGET
+#define GLB_REG_TARGET 80
+#endif
+template <int M> struct Geo {
+  static constexpr int T = M / kPoints;
+  static constexpr int G = (T >= 128) ? 1 : 128 / T;   // frame groups per CTA
+  static constexpr int THREADS = G * T;
+  static constexpr size_t SMEM = (size_t) G * M * sizeof(float2);
+  // CTAs per SM the register allocation is tuned for (~GLB_REG_TARGET registers per thread)
+  static constexpr int MINB_ = 65536 / (THREADS * GLB_REG_TARGET);
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
+};
+
+__device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
+
+// Gather + pre-ops + taper for one frame: v[q] = z[t + T q], z[m] = y[2m] + i y[2m+1].
+template <int M>
+__device__ __forceinline__ void load_frame(float2 (&v)[kPoints], int t, const KParams &p, long long f, int j) {
+  constexpr int T = M / kPoints, N = 2 * M;
+  const long long s0 = f * (long long) p.hop - p.n_ov;   // stream index of frame sample 0
+  const long long rel = s0 - p.origin;
+  const float *tap = p.tapers + (size_t) j * N;
+  const bool interior = (s0 >= 0) && (rel >= 0) && (rel + N <= p.count) && ((rel & 1) == 0);
+  const bool plain = (p.ra9mb_a <= 0.f) && (p.limiter == 0);
+  if (interior && plain) {
+    const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
+    const float2 *w2 = reinterpret_cast<const float2 *>(tap);
+    if (p.means == nullptr) {
+#pragma unroll
+      for (int q = 0; q < kPoints; q++) {
+        const float2 x = ldg2(src + t + T * q);
+        const float2 w = ldg2(w2 + t + T * q);
+        v[q] = make_float2(x.x * w.x, x.y * w.y);
+      }
+    } else {
+      // block of frame sample i (all >= 0 here): f - cblk + floor((i + cblk*hop - n_ov) / hop)
+      const float *mu = p.means + (f - p.cblk - p.means_first_block);
+      const float off = (float) (p.cblk * p.hop - p.n_ov) + 0.5f;
+#pragma unroll
+      for (int q = 0; q < kPoints; q++) {
+        const int i = 2 * (t + T * q);
+        const float2 x = ldg2(src + t + T * q);
+        const float2 w = ldg2(w2 + t + T * q);
+        const int b0 = (int) (((float) i + off) * p.inv_hop);
+        const int b1 = (int) (((float) (i + 1) + off) * p.inv_hop);
+        const float m0 = __ldg(mu + b0);
+        const float m1 = (b1 == b0) ? m0 : __ldg(mu + b1);
+        v[q] = make_float2((x.x - m0) * w.x, (x.y - m1) * w.y);
+      }
+    }
+    return;
+  }
+  // general path: stream edges, odd alignment, pre-ops
+  const float off = (float) (p.cblk * p.hop - p.n_ov) + 0.5f;
+#pragma unroll
+  for (int q = 0; q < kPoints; q++) {
+    float y[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int i = 2 * (t + T * q) + e;
+      const long long s = s0 + i;
+      const long long r = s - p.origin;
+      float x = 0.f;
+      if (s >= 0 && r >= 0 && r < p.count) {
+        x = __ldg(p.samples + r);
+        if (p.means != nullptr) {
+          const int b = (int) (((float) i + off) * p.inv_hop);
+          x -= __ldg(p.means + (f - p.cblk - p.means_first_block) + b);
+        }
+      }
+      if (p.ra9mb_a > 0.f) x = x / (p.ra9mb_a + x * x);
+      x *= __ldg(tap + i);
+      if (p.limiter == 1) {
+        const float m = p.lim_scale * powf(fabsf(x), 0.1f);
+        x = (x > 0.f) ? m : -m;
+      }
+      y[e] = x;
+    }
+    v[q] = make_float2(y[0], y[1]);
+  }
+}
+
+template <int M, int P> struct MidPasses {
+  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw) {
+    if constexpr (P < Plan<M>::NP - 1) {
+      pass_load<M>(v, t, buf);
+      __syncthreads();                 // every thread has read before anyone overwrites
+      pass_store<M, P>(v, t, buf, tw);
+      __syncthreads();
+      MidPasses<M, P + 1>::run(v, t, buf, tw);
+    }
+  }
+};
+
+template <int M, bool MULTI>
+__global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(const KParams p) {
+  constexpr int T = Geo<M>::T, G = Geo<M>::G;
+  extern __shared__ __align__(16) float2 smem[];
+  const int g = threadIdx.x / T;
+  const int t = threadIdx.x % T;
+  float2 *buf = smem + (size_t) g * M;
+  const long long gid = (long long) blockIdx.x * G + g;
+  const long long fb = gid * p.frames_per_group;
+
+  for (int it = 0; it < p.frames_per_group; ++it) {
+    const long long fl = fb + it;
+    const bool active = fl < p.nframes;
+    const long long f = p.first_frame + fl;
+    float acc[17];
+    if (MULTI) {
+#pragma unroll
+      for (int i = 0; i < 17; i++) acc[i] = 0.f;
+    }
+    const int ntap = MULTI ? p.ntapers : 1;
+    for (int j = 0; j < ntap; ++j) {
+      float2 v[kPoints];
+      if (active) {
+        load_frame<M>(v, t, p, f, j);
+      } else {
+#pragma unroll
+        for (int q = 0; q < kPoints; q++) v[q] = make_float2(0.f, 0.f);
+      }
+      pass_store<M, 0>(v, t, buf, p.tw);
+      __syncthreads();
+      MidPasses<M, 1>::run(v, t, buf, p.tw);
+      last_pass<M>(v, t, buf, p.tw);
+      if (MULTI) {
+        emit_bins<M>(v, t, p.vtab, [&](int slot, float2 a, bool) { acc[slot] += norm2(a); });
+      } else if (active) {
+        float *row = p.rows ? p.rows + fl * p.row_stride : nullptr;
+        float2 *sp = p.spectrum ? p.spectrum + fl * (long long) (M + 1) : nullptr;
+        const bool db = p.rows_db != 0;
+        const float ss = p.spec_scale;
+        emit_bins<M>(v, t, p.vtab, [&](int slot, float2 a, bool cj) {
+          const int bin = slot_bin<M>(t, slot);
+          if (row) {
+            float y = norm2(a);
+            if (db) y = 10.f * log10f(y);
+            row[bin] = y;
+          }
+          if (sp) sp[bin] = make_float2(a.x * ss, cj ? -a.y * ss : a.y * ss);
+        });
+      }
+      __syncthreads();                 // buffer is reused by the next taper / frame
+    }
+    if (MULTI && active && p.rows) {
+      float *row = p.rows + fl * p.row_stride;
+      const bool db = p.rows_db != 0;
+#pragma unroll
+      for (int slot = 0; slot < 17; slot++) {
+        if (slot < 16 || t == 0) {
+          float y = acc[slot];
+          if (db) y = 10.f * log10f(y);
+          row[slot_bin<M>(t, slot)] = y;
+        }
+      }
+    }
+  }
+}
+
+template <int M>
+static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
+  using GeoM = Geo<M>;
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  auto kern = multi ? gram_kernel<M, true> : gram_kernel<M, false>;
+  // per (device, variant): opt in to the dynamic shared memory once, cache the occupancy
+  static thread_local int occ_cache[2][64];
+  int &occ = occ_cache[multi ? 1 : 0][dev & 63];
+  if (occ == 0) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GeoM::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GeoM::THREADS, GeoM::SMEM));
+    if (occ < 1) occ = 1;
+  }
+  // resident grid: every CTA slot of the chip holds G frame groups, each walking a
+  // contiguous run of frames (keeps the overlapped samples of consecutive frames in L1/L2)
+  long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
+  if (groups > kp.nframes) groups = kp.nframes;
+  if (groups < 1) groups = 1;
+  KParams k = kp;
+  k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
+  long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
+  int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
+  kern<<<ctas, GeoM::THREADS, GeoM::SMEM, st>>>(k);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
+  if (!a || !a->tables || !glb_fft_supported(a->n) || a->hop < 1 || a->hop > a->n || a->ntapers < 1) {
+    glb_set_error("glb_launch_gram: invalid arguments");
+    return GLB_EINVAL;
+  }
+  if (a->nframes <= 0) return GLB_OK;
+  const GramTables *tb = (const GramTables *) a->tables;
+  if (tb->n != a->n) {
+    glb_set_error("glb_launch_gram: tables were built for another FFT size");
+    return GLB_EINVAL;
+  }
+  KParams k;
+  memset(&k, 0, sizeof k);
+  k.samples = a->samples;
+  k.origin = a->origin;
+  k.count = a->count;
+  k.tapers = a->tapers;
+  k.ntapers = a->ntapers;
+  k.means = a->block_means;
+  k.means_first_block = a->means_first_block;
+  k.hop = a->hop;
+  k.n_ov = a->n - a->hop;
+  k.cblk = (k.n_ov + a->hop - 1) / a->hop;
+  k.inv_hop = (float) (1.0 / (double) a->hop);
+  k.ra9mb_a = a->ra9mb_a;
+  k.limiter = a->limiter;
+  k.lim_scale = (float) pow((double) a->taper_scale, 0.9);
+  k.spec_scale = (float) (1.0 / (2.0 * (double) a->taper_scale));
+  k.first_frame = a->first_frame;
+  k.nframes = a->nframes;
+  k.rows = a->rows;
+  k.row_stride = a->row_stride;
+  k.rows_db = a->rows_db;
+  k.spectrum = (float2 *) a->spectrum;
+  k.tw = tb->tw;
+  k.vtab = tb->vtab;
+  const bool multi = a->ntapers > 1;
+  if (multi && a->spectrum) {
+    glb_set_error("glb_launch_gram: spectrum output is only defined for one taper");
+    return GLB_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t) stream;
+  switch (a->n / 2) {
+    case 16: return launch_gram_m<16>(k, multi, a->groups_hint, st);
+    case 32: return launch_gram_m<32>(k, multi, a->groups_hint, st);
+    case 64: return launch_gram_m<64>(k, multi, a->groups_hint, st);
+    case 128: return launch_gram_m<128>(k, multi, a->groups_hint, st);
+    case 256: return launch_gram_m<256>(k, multi, a->groups_hint, st);
+    case 512: return launch_gram_m<512>(k, multi, a->groups_hint, st);
+    case 1024: return launch_gram_m<1024>(k, multi, a->groups_hint, st);
+    case 2048: return launch_gram_m<2048>(k, multi, a->groups_hint, st);
+    case 4096: return launch_gram_m<4096>(k, multi, a->groups_hint, st);
+    case 8192: return launch_gram_m<8192>(k, multi, a->groups_hint, st);
+    case 16384: return launch_gram_m<16384>(k, multi, a->groups_hint, st);
+  }
+  return GLB_EINVAL;
+}
+
+// ------------------------------------------------------------------------- block means
+// One warp per hop block; lanes stride the block, float partial sums, shuffle tree.
+__global__ void block_means_kernel(const float *__restrict__ samples, long long origin, long long count,
+                                   int hop, long long first_block, long long nblocks, float *__restrict__ means) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  for (long long b = warp; b < nblocks; b += nwarps) {
+    const long long base = (first_block + b) * hop - origin;
+    float s = 0.f;
+    for (int i = lane; i < hop; i += 32) {
+      const long long r = base + i;
+      s += (r >= 0 && r < count) ? __ldg(samples + r) : 0.f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) means[b] = s / (float) hop;
+  }
+}
+
+extern "C" int glb_launch_block_means(const float *samples, long long origin, long long count, int hop,
+                                      long long first_block, long long nblocks, float *means, void *stream) {
+  if (nblocks <= 0) return GLB_OK;
+  if (hop < 1) { glb_set_error("block_means: hop < 1"); return GLB_EINVAL; }
+  const int threads = 256;
+  long long ctas = (nblocks * 32 + threads - 1) / threads;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  block_means_kernel<<<(int) ctas, threads, 0, (cudaStream_t) stream>>>(samples, origin, count, hop, first_block, nblocks, means);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------- PCM ingest
+__global__ void pcm16_to_float_kernel(const short *__restrict__ in, float *__restrict__ out, long long n) {
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (float) in[i] / 32768.f;
+}
+__global__ void pcm8_to_float_kernel(const unsigned char *__restrict__ in, float *__restrict__ out, long long n) {
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = ((float) in[i] - 128.f) / 128.f;
+}
+extern "C" int glb_launch_pcm16_to_float(const short *pcm, float *out, long long count, void *stream) {
+  if (count <= 0) return GLB_OK;
+  long long ctas = std::min<long long>((count + 255) / 256, 148 * 32);
+  pcm16_to_float_kernel<<<(int) ctas, 256, 0, (cudaStream_t) stream>>>(pcm, out, count);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+extern "C" int glb_launch_pcm8_to_float(const unsigned char *pcm, float *out, long long count, void *stream) {
+  if (count <= 0) return GLB_OK;
+  long long ctas = std::min<long long>((count + 255) / 256, 148 * 32);
+  pcm8_to_float_kernel<<<(int) ctas, 256, 0, (cudaStream_t) stream>>>(pcm, out, count);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------- averaging
+// One CTA walks a chunk of consecutive frames; threads stride the band
+// [minbin, maxbin).  Per bin the window sum cum = sum of the last min(f+1, depth) PSD
+// values is held in double in shared memory (the reference keeps double cum[],
+// avg.c:119,123) and slid frame to frame; the chunk's first frame sums its window
+// directly from the rows, so chunks are independent.
+struct AvgRed {
+  double mx; int arg; double sum; double mn;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) avg_kernel(const glb_avg_args a, int chunk) {
+  extern __shared__ double cum[];                    // band doubles
+  __shared__ double s_mx[8], s_sum[8], s_mn[8], s_var[8];
+  __shared__ int s_arg[8], s_cnt[8];
+  __shared__ double b_mx, b_sum, b_mn, b_var;
+  __shared__ int b_arg, b_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int band = a.maxbin - a.minbin;
+  const long long c0 = (long long) blockIdx.x * chunk;
+  const long long c1 = (c0 + chunk < a.nframes) ? c0 + chunk : a.nframes;
+  OutT *out_base = (OutT *) a.avg_rows;
+  auto psd_row = [&](long long g2) -> const float * {
+    const long long r = a.psd_ring_rows > 0 ? g2 % a.psd_ring_rows : g2 - a.psd_first_frame;
+    return a.psd + r * a.psd_stride;
+  };
+  int carried = a.peakbin_init;
+  bool carry_known = (blockIdx.x == 0);
+
+  for (long long fl = c0; fl < c1; ++fl) {
+    const long long f = a.first_frame + fl;          // frames since alloc_avg
+    const float *row = psd_row(f);
+    const long long eff = (f + 1 < a.depth) ? f + 1 : a.depth;   // effdepth after this update
+    double mx = -1.0, sum = 0.0, mn = 1.0;
+    int arg = -1;
+    for (int i = tid; i < band; i += 256) {
+      const int b = a.minbin + i;
+      double c;
+      if (fl == c0) {
+        c = 0.0;
+        for (long long g2 = f - eff + 1; g2 <= f; ++g2) c += (double) psd_row(g2)[b];
+      } else {
+        c = cum[i] + (double) row[b];
+        if (f - a.depth >= 0) c -= (double) psd_row(f - a.depth)[b];
+      }
+      cum[i] = c;
+      if (arg < 0 || c > mx) { mx = c; arg = b; }     // first maximum within this thread's bins
+      sum += c;
+      if (c < mn) mn = c;
+    }
+    // block reduction: max with the lowest bin on ties, sum, min
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (oarg >= 0 && (arg < 0 || omx > mx || (omx == mx && oarg < arg))) { mx = omx; arg = oarg; }
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const double omn = __shfl_xor_sync(0xffffffffu, mn, o);
+      if (omn < mn) mn = omn;
+    }
+    if (lane == 0) { s_mx[wid] = mx; s_arg[wid] = arg; s_sum[wid] = sum; s_mn[wid] = mn; }
+    __syncthreads();
+    if (tid == 0) {
+      double m = s_mx[0], sm = s_sum[0], mi = s_mn[0];
+      int ar = s_arg[0];
+      for (int w = 1; w < 8; w++) {
+        if (s_arg[w] >= 0 && (ar < 0 || s_mx[w] > m || (s_mx[w] == m && s_arg[w] < ar))) { m = s_mx[w]; ar = s_arg[w]; }
+        sm += s_sum[w];
+        if (s_mn[w] < mi) mi = s_mn[w];
+      }
+      // `double max = psd[minbin]; if (cum > max) { max = cum; *peakbin = index; }` avg.c:111,129-133
+      const double m0 = (double) row[a.minbin];
+      if (ar >= 0 && m > m0) { b_mx = m; b_arg = ar; } else { b_mx = m0; b_arg = -1; }
+      b_sum = sm;
+      b_mn = mi;
+    }
+    __syncthreads();
+    const double vmax = b_mx, vsum = b_sum, vmin = b_mn;
+    const int cand = b_arg;
+    if (cand >= 0) { carried = cand; carry_known = true; }
+    const int pk = carried;
+    double avgspec = 0.0, retv = 0.0;
+    if (a.mode == 2) {
+      retv = (vsum - vmax) / ((double) (band - 1) * (double) (eff + 1));
+    } else {
+      avgspec = (vsum - vmax) / (double) (band - 1);
+      retv = vmax / avgspec;
+    }
+    // output row
+    OutT *orow = out_base + fl * a.out_stride;
+    double var = 0.0;
+    int cnt = 0;
+    for (int b = tid; b < a.nbins; b += 256) {
+      double y = 1e-15;
+      if (b >= a.minbin && b < a.maxbin) {
+        const double c = cum[b - a.minbin];
+        if (a.mode == 2) {
+          y = c / (double) (eff + 1);
+        } else if (a.mode == 3) {
+          y = a.max0 ? (c - vmin) / (vmax - vmin) : c / avgspec;
+        } else {
+          if (c - avgspec > 0) {
+            y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
+            if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
+          } else {
+            y = 1e-15;
+          }
+        }
+      }
+      if (sizeof(OutT) == 4 && a.rows_db) y = 10.0 * log10(y);
+      orow[b] = (OutT) y;
+    }
+    if (a.mode == 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        var += __shfl_xor_sync(0xffffffffu, var, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      if (lane == 0) { s_var[wid] = var; s_cnt[wid] = cnt; }
+      __syncthreads();
+      if (tid == 0) {
+        double v = 0; int c = 0;
+        for (int w = 0; w < 8; w++) { v += s_var[w]; c += s_cnt[w]; }
+        b_var = v; b_cnt = c;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (a.ret) a.ret[fl] = retv;
+      if (a.peak_cand) a.peak_cand[fl] = cand;
+      if (a.variance) a.variance[fl] = (a.mode == 1) ? b_var / (double) b_cnt : 0.0;
+      if (a.mode == 1 && !carry_known && a.unresolved) atomicAdd(a.unresolved, 1);
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int glb_launch_avg(const glb_avg_args *a, void *stream) {
+  if (!a || a->mode < 1 || a->mode > 3 || a->depth < 1 || a->minbin < 0 || a->maxbin < a->minbin) {
+    glb_set_error("glb_launch_avg: invalid arguments");
+    return GLB_EINVAL;
+  }
+  if (a->nframes <= 0) return GLB_OK;
+  const int band = a->maxbin - a->minbin;
+  const size_t smem = (size_t) (band > 0 ? band : 1) * sizeof(double);
+  if (smem > 200 * 1024) { glb_set_error("glb_launch_avg: band too wide"); return GLB_EINVAL; }
+  int chunk;
+  if (a->sequential) {
+    chunk = (int) std::min<long long>(a->nframes, 0x7fffffff);
+  } else {
+    // amortise the direct window sum of a chunk's first frame over >= 8*depth frames
+    long long want = std::max<long long>(8LL * a->depth, 16);
+    long long by_grid = (a->nframes + 148 * 8 - 1) / (148 * 8);
+    chunk = (int) std::max(want, by_grid);
+  }
+  long long ctas = (a->nframes + chunk - 1) / chunk;
+  cudaStream_t st = (cudaStream_t) stream;
+  if (a->out_double) {
+    CU(cudaFuncSetAttribute(avg_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    avg_kernel<double><<<(int) ctas, 256, smem, st>>>(*a, chunk);
+  } else {
+    CU(cudaFuncSetAttribute(avg_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    avg_kernel<float><<<(int) ctas, 256, smem, st>>>(*a, chunk);
+  }
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+// carried peak bin: last written candidate at or before each frame
+__global__ void __launch_bounds__(1024) peak_carry_kernel(const int *__restrict__ cand, int *__restrict__ out,
+                                                          long long n, int init) {
+  __shared__ int last[1024];
+  const int tid = threadIdx.x;
+  const long long per = (n + 1023) / 1024;
+  const long long b = tid * per, e = (b + per < n) ? b + per : n;
+  int l = -1;
+  for (long long i = b; i < e; i++) if (cand[i] >= 0) l = cand[i];
+  last[tid] = l;
+  __syncthreads();
+  int carry = init;
+  for (int w = 0; w < tid; w++) if (last[w] >= 0) carry = last[w];
+  for (long long i = b; i < e; i++) {
+    if (cand[i] >= 0) carry = cand[i];
+    out[i] = carry;
+  }
+}
+
+extern "C" int glb_launch_peak_carry(const int *cand, int *peakbin, long long nframes, int init, void *stream) {
+  if (nframes <= 0) return GLB_OK;
+  peak_carry_kernel<<<1, 1024, 0, (cudaStream_t) stream>>>(cand, peakbin, nframes, init);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------- half-complex PSD
+// fft_psd (fft.c:203-226) for a spectrum that did not come from gram_kernel (callers that
+// fill outbuf themselves).  phase = atan2(Re, Im), the reference's argument order.
+__global__ void halfcomplex_psd_kernel(const float *__restrict__ hc, int n, float *__restrict__ psd,
+                                       float *__restrict__ phase) {
+  const int half = (n + 1) / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n / 2; i += gridDim.x * blockDim.x) {
+    const bool edge = (i == 0) || (n % 2 == 0 && i == n / 2);
+    if (!edge && i >= half) continue;
+    const float re = hc[i];
+    const float im = edge ? 0.f : hc[n - i];
+    if (psd) psd[i] = (re * re + im * im) / (float) n;
+    if (phase) phase[i] = edge ? 0.f : atan2f(re, im);
+  }
+}
+
+extern "C" int glb_launch_halfcomplex_psd(const float *hc, int n, float *psd, float *phase, void *stream) {
+  if (n < 1) { glb_set_error("halfcomplex_psd: n < 1"); return GLB_EINVAL; }
+  const int ctas = (n / 2 + 1 + 255) / 256;
+  halfcomplex_psd_kernel<<<ctas, 256, 0, (cudaStream_t) stream>>>(hc, n, psd, phase);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+// ------------------------------------------------------------------------- floor statistics
+// compute_floor (fft.c:240-294) per PSD row: one CTA sorts the row descending in shared
+// memory (bitonic network over the next power of two, padded with -inf), then takes the
+// head (sig), sums the tail from index (int)(n * 0.95) (floor) and scans for the first
+// maximum (peak value and bin; peak stays (0, 0) when no bin is > 0, fft.c:284-291).
+__global__ void __launch_bounds__(512) floor_stats_kernel(const float *__restrict__ rows, long long stride, int nbins,
+                                                          int npow2, float *__restrict__ stats) {
+  extern __shared__ float srt[];
+  __shared__ float red_v[16];
+  __shared__ int red_i[16];
+  const float *row = rows + (long long) blockIdx.x * stride;
+  const int tid = threadIdx.x;
+  float best = 0.f;
+  int best_i = 0x7fffffff;
+  for (int i = tid; i < npow2; i += 512) {
+    const float v = (i < nbins) ? row[i] : -INFINITY;
+    srt[i] = v;
+    if (i < nbins && v > best) { best = v; best_i = i; }   // thread's bins ascend: first max
+  }
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow2; i += 512) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float a = srt[i], b = srt[l];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < b) : (a > b)) { srt[i] = b; srt[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // tail sum (lowest 5 %): partial sums, then one thread adds the partials
+  const int start = (int) (nbins * 0.95);
+  float part = 0.f;
+  for (int i = start + tid; i < nbins; i += 512) part += srt[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  __shared__ float red_s[16];
+  if ((tid & 31) == 0) { red_s[tid >> 5] = part; red_v[tid >> 5] = best; red_i[tid >> 5] = best_i; }
+  __syncthreads();
+  if (tid == 0) {
+    float fsum = 0.f, pv = 0.f;
+    int pi = 0x7fffffff;
+    for (int w = 0; w < 16; w++) {
+      fsum += red_s[w];
+      if (red_v[w] > pv || (red_v[w] == pv && red_i[w] < pi)) { pv = red_v[w]; pi = red_i[w]; }
+    }
+    float fl = fsum / 0.05f;
+    fl = fl / (float) nbins;
+    float *o = stats + (long long) blockIdx.x * 4;
+    o[0] = srt[0];
+    o[1] = fl;
+    o[2] = (pv > 0.f) ? pv : 0.f;
+    o[3] = (pv > 0.f) ? (float) pi : 0.f;
+  }
+}
+
+extern "C" int glb_launch_floor_stats(const float *rows, long long stride, int nbins, long long nrows, float *stats,
+                                      void *stream) {
+  if (nrows <= 0) return GLB_OK;
+  if (nbins < 1 || nbins > 32768) { glb_set_error("floor_stats: row too wide"); return GLB_EINVAL; }
+  int np2 = 1;
+  while (np2 < nbins) np2 <<= 1;
+  const size_t smem = (size_t) np2 * sizeof(float);
+  CU(cudaFuncSetAttribute(floor_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  floor_stats_kernel<<<(unsigned) nrows, 512, smem, (cudaStream_t) stream>>>(rows, stride, nbins, np2, stats);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}

@@ -1,0 +1,507 @@
+/* dropin.c -- the reference's per-call estimator interface (fft.h:77-83, mtm.h:47-49,
+ * avg.h:38-43) on top of the GPU engine: one hop block per call, exactly the sequence
+ * audio_available() drives (source.c:130-165).
+ *
+ * Host side of a call = what the caller can observe in the public structs: the hop-block
+ * mean removal done in place in the caller's buffer (fft.c:86-96), the overlap history in
+ * params->inbuf_audio (fft.c:98-113), the windowed frame in inbuf_fft (read by
+ * g_scope.c:186-197) and the half-complex spectrum in outbuf.  The spectrum estimate
+ * itself (window/taper multiply, FFT, |X|^2, taper sum, averaging) runs on the GPU as a
+ * batch of one frame through the same kernels as the batched path.
+ *
+ * Engines are kept in a registry keyed by the params pointer because the reference's
+ * structs have no spare field for a handle.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "glb_host.h"
+
+/* ------------------------------------------------------------------ hidden globals
+ * Layout mirrors of the two globals fft.c reads (glfer.h:62-139); GTK pointers are plain
+ * pointers here.  They are weak: when the host program defines `opt` and `glfer`
+ * (glfer.c:56-62) the library reads them, otherwise the setters below provide the values. */
+typedef struct {
+  char *program_name; int mode; int scale_type;
+  int data_block_size; float data_blocks_overlap; float display_update_time; float limiter_a; int enable_limiter;
+  float mtm_w; int mtm_k;
+  int hparma_t; int hparma_p_e;
+  int lmp_av;
+  int window_type;
+  char *audio_device; int sample_rate;
+  float dot_time; float dfcw_gap_time; int tx_mode; float dash_dot_ratio; float ptt_delay; float sidetone_freq;
+  int sidetone; float dfcw_dot_freq; float dfcw_dash_freq; int beacon_mode; float beacon_pause; int beacon_tx_pause;
+  char *ctrl_device; int device_type;
+  float offset_freq; float thr_level; int autoscale; float max_level_db; float min_level_db;
+  int averaging; int avgsamples; float min_avgband; float max_avgband; int palette;
+} glb_opt_mirror;
+
+typedef struct {
+  void *tt; void *qso_menu_item; void *test_menu_item;
+  int init_done; int first_buffer; int input_source; float cpu_usage; int current_mode;
+  void *scope_window;
+  float avgmax; double avgvar; int avgfill; float peakfreq; float peakval; float avgtime;
+} glb_glfer_mirror;
+
+extern glb_opt_mirror opt __attribute__((weak));
+extern glb_glfer_mirror glfer __attribute__((weak));
+
+static int g_autoscale = 1;        /* glfer.c default: opt.autoscale = 1 */
+static int g_first_buffer = 1;
+
+void glfer_b200_set_autoscale(int v) { g_autoscale = v; }
+void glfer_b200_set_first_buffer(int v) { g_first_buffer = v; }
+int glb_autoscale(void) { return (&opt != NULL) ? opt.autoscale : g_autoscale; }
+int glb_first_buffer(void) { return (&glfer != NULL) ? glfer.first_buffer : g_first_buffer; }
+
+void glb_fatal(const char *where)
+{
+  fprintf(stderr, "libglfer_b200: %s: %s\n", where, glfer_b200_last_error());
+  exit(-1);
+}
+
+/* fft.c:48-60 */
+fft_window_t fft_windows[] = {
+  {"/Hanning", HANNING_WINDOW}, {"/Blackman", BLACKMAN_WINDOW}, {"/Gaussian", GAUSSIAN_WINDOW},
+  {"/Welch", WELCH_WINDOW}, {"/Bartlett", BARTLETT_WINDOW}, {"/Rectangular", RECTANGULAR_WINDOW},
+  {"/Hamming", HAMMING_WINDOW}, {"/Kaiser", KAISER_WINDOW}
+};
+int num_fft_windows = sizeof(fft_windows) / sizeof(fft_windows[0]);
+
+/* ------------------------------------------------------------------ engine registry */
+typedef struct engine {
+  const void *key;
+  struct engine *next;
+  int n, ntapers;
+  float taper_scale;
+  void *tables, *stream;
+  float *d_frame, *d_tapers, *d_psd, *d_spec, *d_hc, *d_phase;
+  float *h_psd, *h_spec;     /* pinned */
+  int fresh;                 /* h_psd holds the PSD of the last *_do on this key */
+  /* averaging engines */
+  int width, depth;
+  long long frames;          /* frames since alloc_avg */
+  float *d_ring;             /* [depth][width] last PSD rows */
+  double *d_avg, *d_ret, *d_var;
+  int *d_cand;
+} engine;
+
+static engine *g_engines;
+
+static engine *find_engine(const void *key)
+{
+  for (engine *e = g_engines; e; e = e->next)
+    if (e->key == key) return e;
+  return NULL;
+}
+
+static engine *new_engine(const void *key)
+{
+  engine *e = calloc(1, sizeof *e);
+  if (!e) { glb_set_error("out of memory"); glb_fatal("engine"); }
+  e->key = key;
+  e->next = g_engines;
+  g_engines = e;
+  return e;
+}
+
+static void drop_engine(const void *key)
+{
+  for (engine **pp = &g_engines; *pp; pp = &(*pp)->next) {
+    engine *e = *pp;
+    if (e->key != key) continue;
+    *pp = e->next;
+    if (e->stream) glb_stream_sync(e->stream);
+    glb_free(e->d_frame); glb_free(e->d_tapers); glb_free(e->d_psd); glb_free(e->d_spec);
+    glb_free(e->d_hc); glb_free(e->d_phase); glb_free(e->d_ring); glb_free(e->d_avg);
+    glb_free(e->d_ret); glb_free(e->d_var); glb_free(e->d_cand);
+    glb_host_free(e->h_psd); glb_host_free(e->h_spec);
+    glb_tables_destroy(e->tables);
+    glb_stream_destroy(e->stream);
+    free(e);
+    return;
+  }
+}
+
+#define MUST(x, where) do { if ((x) != GLB_OK) glb_fatal(where); } while (0)
+
+static void need_device(const char *where)
+{
+  int c = 0;
+  if (glb_device_count(&c) != GLB_OK || c < 1) {
+    glb_set_error("no CUDA device (libglfer_b200 has no CPU fallback)");
+    glb_fatal(where);
+  }
+}
+
+/* device side of an estimator: tables, scaled tapers, one-frame buffers */
+static engine *make_estimator(const void *key, int n, int ntapers, const float *scaled_tapers, float scale)
+{
+  need_device("init");
+  if (!glb_fft_supported(n)) {
+    fprintf(stderr, "libglfer_b200: n = %d is not a power of 2 in 32..32768\n", n);   /* cf. fft_radix2.c:89-93 */
+    exit(-1);
+  }
+  drop_engine(key);
+  engine *e = new_engine(key);
+  e->n = n;
+  e->ntapers = ntapers;
+  e->taper_scale = scale;
+  MUST(glb_stream_create(&e->stream), "stream");
+  MUST(glb_tables_create(n, &e->tables), "tables");
+  MUST(glb_malloc((void **) &e->d_frame, sizeof(float) * n), "malloc");
+  MUST(glb_malloc((void **) &e->d_tapers, sizeof(float) * (size_t) ntapers * n), "malloc");
+  MUST(glb_malloc((void **) &e->d_psd, sizeof(float) * (n / 2 + 1)), "malloc");
+  MUST(glb_malloc((void **) &e->d_spec, sizeof(float) * 2 * (n / 2 + 1)), "malloc");
+  MUST(glb_host_alloc((void **) &e->h_psd, sizeof(float) * (n / 2 + 1)), "host_alloc");
+  MUST(glb_host_alloc((void **) &e->h_spec, sizeof(float) * 2 * (n / 2 + 1)), "host_alloc");
+  MUST(glb_memcpy_h2d(e->d_tapers, scaled_tapers, sizeof(float) * (size_t) ntapers * n, NULL), "h2d");
+  return e;
+}
+
+/* one frame through gram_kernel: inbuf_audio -> PSD row (+ spectrum for one taper) */
+static void run_frame(engine *e, const float *frame, float a, int limiter, int want_spec)
+{
+  glb_gram_args g;
+  memset(&g, 0, sizeof g);
+  MUST(glb_memcpy_h2d(e->d_frame, frame, sizeof(float) * e->n, e->stream), "h2d");
+  g.n = e->n;
+  g.hop = e->n;                      /* the frame is complete: no gather, no history */
+  g.samples = e->d_frame;
+  g.origin = 0;
+  g.count = e->n;
+  g.tapers = e->d_tapers;
+  g.ntapers = e->ntapers;
+  g.ra9mb_a = a;
+  g.limiter = limiter;
+  g.taper_scale = e->taper_scale;
+  g.first_frame = 0;
+  g.nframes = 1;
+  g.rows = e->d_psd;
+  g.row_stride = e->n / 2 + 1;
+  g.spectrum = want_spec ? e->d_spec : NULL;
+  g.tables = e->tables;
+  MUST(glb_launch_gram(&g, e->stream), "launch");
+  MUST(glb_memcpy_d2h(e->h_psd, e->d_psd, sizeof(float) * (e->n / 2 + 1), e->stream), "d2h");
+  if (want_spec) MUST(glb_memcpy_d2h(e->h_spec, e->d_spec, sizeof(float) * 2 * (e->n / 2 + 1), e->stream), "d2h");
+  MUST(glb_stream_sync(e->stream), "sync");
+  e->fresh = 1;
+}
+
+/* ------------------------------------------------------------------ fft.h */
+void compute_window(fft_params_t *params)
+{
+  glb_window_table(params->n, params->window_type, params->window);
+}
+
+/* fft.c:66-165, host-visible part: mean removal in the caller's block, history shift,
+ * append, and the windowed copy in inbuf_fft */
+void prepare_audio(float *audio_buf, fft_params_t *params)
+{
+  const int N = params->n;
+  const int n_eff = glb_hop(N, params->overlap);
+  const int n_overlap = N - n_eff;
+  if (params->sub_mean) {
+    float sig_mean = 0.0f;
+    for (int i = 0; i < n_eff; i++) sig_mean += audio_buf[i];
+    sig_mean /= n_eff;
+    for (int i = 0; i < n_eff; i++) audio_buf[i] -= sig_mean;
+  }
+  if (!glb_first_buffer())
+    memmove(params->inbuf_audio, params->inbuf_audio + (N - n_overlap), sizeof(float) * n_overlap);
+  else
+    memset(params->inbuf_audio, 0, sizeof(float) * n_overlap);
+  memcpy(params->inbuf_audio + n_overlap, audio_buf, sizeof(float) * n_eff);
+  const int windowed = params->window_type != RECTANGULAR_WINDOW;
+  for (int i = 0; i < N; i++) {
+    float x = params->inbuf_audio[i];
+    if (params->a > 0.0) x = x / (params->a + x * x);
+    if (windowed) x = params->window[i] * x;
+    if (params->limiter == 1) {
+      const float l = log(fabs(x));
+      x = (x > 0 ? exp(l * 0.1) : -exp(l * 0.1));
+    }
+    params->inbuf_fft[i] = x;
+  }
+}
+
+void fft_init(fft_params_t *params)
+{
+  const int n = params->n;
+  params->inbuf_audio = calloc(n, sizeof(float));
+  params->inbuf_fft = calloc(n, sizeof(float));
+  params->outbuf = params->inbuf_fft;            /* fft.c:180 */
+  params->window = malloc(n * sizeof(float));
+  if (!params->inbuf_audio || !params->inbuf_fft || !params->window) { glb_set_error("out of memory"); glb_fatal("fft_init"); }
+  compute_window(params);
+  params->sub_mean = glb_autoscale();            /* fft.c:186 */
+  const float scale = (float) (1.0 / (2.0 * sqrt((double) n)));
+  float *scaled = malloc(sizeof(float) * n);
+  for (int i = 0; i < n; i++) {
+    const double w = (params->window_type == RECTANGULAR_WINDOW) ? 1.0 : (double) params->window[i];
+    scaled[i] = (float) (w * (double) scale);
+  }
+  make_estimator(params, n, 1, scaled, scale);
+  free(scaled);
+}
+
+/* half-complex layout of fft_real_radix2_transform / rfftw_one: out[k] = Re, out[n-k] = Im */
+static void spectrum_to_halfcomplex(const float *spec, int n, float *hc)
+{
+  hc[0] = spec[0];
+  for (int k = 1; k < (n + 1) / 2; k++) {
+    hc[k] = spec[2 * k];
+    hc[n - k] = spec[2 * k + 1];
+  }
+  if (n % 2 == 0) hc[n / 2] = spec[2 * (n / 2)];
+}
+
+void fft_do(float *audio_buf, fft_params_t *params)
+{
+  engine *e = find_engine(params);
+  if (!e) { glb_set_error("fft_do on parameters that did not go through fft_init"); glb_fatal("fft_do"); }
+  prepare_audio(audio_buf, params);
+  run_frame(e, params->inbuf_audio, params->a, params->limiter, 1);
+  spectrum_to_halfcomplex(e->h_spec, params->n, params->outbuf);   /* overwrites inbuf_fft, as in-place FFT does */
+}
+
+void fft_psd(float *psd_buf, float *phase_buf, fft_params_t *params)
+{
+  const int n = params->n, bins = n / 2 + 1;
+  engine *e = find_engine(params);
+  if (e && e->fresh && !phase_buf) {
+    if (psd_buf) memcpy(psd_buf, e->h_psd, sizeof(float) * bins);
+    return;
+  }
+  /* spectrum that was not produced by fft_do on these params (callers that fill outbuf
+     themselves), or phase wanted: run fft_psd's formula on the device from outbuf */
+  need_device("fft_psd");
+  void *d_hc = NULL, *d_psd = NULL, *d_ph = NULL;
+  MUST(glb_malloc(&d_hc, sizeof(float) * n), "malloc");
+  MUST(glb_malloc(&d_psd, sizeof(float) * bins), "malloc");
+  MUST(glb_malloc(&d_ph, sizeof(float) * bins), "malloc");
+  MUST(glb_memcpy_h2d(d_hc, params->outbuf, sizeof(float) * n, NULL), "h2d");
+  MUST(glb_launch_halfcomplex_psd(d_hc, n, psd_buf ? d_psd : NULL, phase_buf ? d_ph : NULL, NULL), "launch");
+  if (psd_buf) {
+    if (e && e->fresh) memcpy(psd_buf, e->h_psd, sizeof(float) * bins);
+    else MUST(glb_memcpy_d2h(psd_buf, d_psd, sizeof(float) * bins, NULL), "d2h");
+  }
+  if (phase_buf) MUST(glb_memcpy_d2h(phase_buf, d_ph, sizeof(float) * bins, NULL), "d2h");
+  glb_free(d_hc); glb_free(d_psd); glb_free(d_ph);
+}
+
+void fft_close(fft_params_t *params)
+{
+  drop_engine(params);
+  free(params->inbuf_audio); params->inbuf_audio = NULL;
+  free(params->inbuf_fft); params->inbuf_fft = NULL;
+  params->outbuf = NULL;
+  free(params->window); params->window = NULL;
+}
+
+void compute_floor(float *psd_buf, int n, float *sig_pwr_p, float *floor_pwr_p, float *peak_pwr_p,
+                   unsigned int *peak_bin_p)
+{
+  need_device("compute_floor");
+  void *d_row = NULL, *d_st = NULL;
+  float st[4];
+  MUST(glb_malloc(&d_row, sizeof(float) * n), "malloc");
+  MUST(glb_malloc(&d_st, sizeof st), "malloc");
+  MUST(glb_memcpy_h2d(d_row, psd_buf, sizeof(float) * n, NULL), "h2d");
+  MUST(glb_launch_floor_stats(d_row, n, n, 1, d_st, NULL), "launch");
+  MUST(glb_memcpy_d2h(st, d_st, sizeof st, NULL), "d2h");
+  glb_free(d_row); glb_free(d_st);
+  *sig_pwr_p = st[0];
+  *floor_pwr_p = st[1];
+  *peak_pwr_p = st[2];
+  *peak_bin_p = (unsigned int) st[3];
+}
+
+/* ------------------------------------------------------------------ mtm.h */
+static double **nr_dmatrix(long nrl, long nrh, long ncl, long nch)
+{
+  /* 1-offset row pointers over one contiguous block, as the caller of mtm.c:118 expects */
+  const long nrow = nrh - nrl + 1, ncol = nch - ncl + 1;
+  double **m = malloc(sizeof(double *) * (nrow + 1));
+  double *blk = malloc(sizeof(double) * (nrow * ncol + 1));
+  if (!m || !blk) { glb_set_error("out of memory"); glb_fatal("mtm_init"); }
+  m += 1;
+  m -= nrl;
+  m[nrl] = blk + 1 - ncl;
+  for (long i = nrl + 1; i <= nrh; i++) m[i] = m[i - 1] + ncol;
+  return m;
+}
+
+static void nr_free_dmatrix(double **m, long nrl, long ncl)
+{
+  free(m[nrl] + ncl - 1);
+  free(m + nrl - 1);
+}
+
+void mtm_init(mtm_params_t *params)
+{
+  const int n = params->fft.n, kmax = params->kmax;
+  if (kmax < 0 || kmax > 31) { fprintf(stderr, "libglfer_b200: mtm kmax %d outside 0..31\n", kmax); exit(-1); }
+  params->fft.inbuf_audio = calloc(n, sizeof(float));
+  params->fft.inbuf_fft = calloc(n, sizeof(float));
+  params->fft.outbuf = params->fft.inbuf_fft;    /* mtm.c:106 */
+  params->fft.sub_mean = glb_autoscale();        /* mtm.c:111 */
+  params->window = nr_dmatrix(1, n, 0, kmax);    /* mtm.c:118 */
+  params->sig = malloc(sizeof(double) * (kmax + 1));
+  double *tap = malloc(sizeof(double) * (size_t) (kmax + 1) * n);
+  double *lam = malloc(sizeof(double) * (kmax + 1));
+  if (!params->fft.inbuf_audio || !params->fft.inbuf_fft || !params->sig || !tap || !lam) {
+    glb_set_error("out of memory");
+    glb_fatal("mtm_init");
+  }
+  if (glb_dpss(n, (double) params->w, kmax, tap, lam) != 0) fprintf(stderr, "Error: DPSS computation failed\n");
+  const float scale = (float) (1.0 / (2.0 * sqrt((double) n)));
+  float *scaled = malloc(sizeof(float) * (size_t) (kmax + 1) * n);
+  for (int k = 0; k <= kmax; k++) {
+    params->sig[k] = lam[k] - 1.0;
+    const double g = (double) scale / sqrt(fabs(lam[k]));
+    for (int i = 0; i < n; i++) {
+      params->window[i + 1][k] = tap[(size_t) k * n + i];
+      scaled[(size_t) k * n + i] = (float) (tap[(size_t) k * n + i] * g);
+    }
+  }
+  make_estimator(params, n, kmax + 1, scaled, scale);
+  free(scaled); free(tap); free(lam);
+}
+
+void mtm_do(float *audio_buf, float *psd_buf, float *phase_buf, mtm_params_t *params)
+{
+  (void) phase_buf;                              /* never written by the reference either */
+  engine *e = find_engine(params);
+  if (!e) { glb_set_error("mtm_do on parameters that did not go through mtm_init"); glb_fatal("mtm_do"); }
+  prepare_audio(audio_buf, &params->fft);
+  run_frame(e, params->fft.inbuf_audio, 0.0f, 0, 0);
+  memcpy(psd_buf, e->h_psd, sizeof(float) * (params->fft.n / 2 + 1));
+}
+
+void mtm_close(mtm_params_t *params)
+{
+  drop_engine(params);
+  free(params->fft.inbuf_audio); params->fft.inbuf_audio = NULL;
+  free(params->fft.inbuf_fft); params->fft.inbuf_fft = NULL;
+  params->fft.outbuf = NULL;
+  if (params->window) nr_free_dmatrix(params->window, 1, 0);
+  params->window = NULL;
+  free(params->sig); params->sig = NULL;
+}
+
+/* ------------------------------------------------------------------ avg.h */
+void init_avg(avg_data_t *avgdata)
+{
+  avgdata->avgwidth = 0;
+  avgdata->avgdepth = 0;
+  avgdata->effdepth = 0;
+}
+
+void alloc_avg(avg_data_t *avgdata, int width, int depth)
+{
+  avgdata->avgwidth = width;
+  avgdata->avgdepth = depth;
+  avgdata->avgarray = malloc(width * sizeof(double *));
+  for (int i = 0; i < width; i++) avgdata->avgarray[i] = calloc(depth > 0 ? depth : 1, sizeof(double));
+  avgdata->avg = calloc(width > 0 ? width : 1, sizeof(double));
+  avgdata->cum = calloc(width > 0 ? width : 1, sizeof(double));
+  avgdata->effdepth = 0;
+  need_device("alloc_avg");
+  drop_engine(avgdata);
+  engine *e = new_engine(avgdata);
+  e->width = width;
+  e->depth = depth;
+  e->frames = 0;
+  MUST(glb_stream_create(&e->stream), "stream");
+  MUST(glb_malloc((void **) &e->d_ring, sizeof(float) * (size_t) (depth > 0 ? depth : 1) * width), "malloc");
+  MUST(glb_malloc((void **) &e->d_avg, sizeof(double) * width), "malloc");
+  MUST(glb_malloc((void **) &e->d_ret, sizeof(double)), "malloc");
+  MUST(glb_malloc((void **) &e->d_var, sizeof(double)), "malloc");
+  MUST(glb_malloc((void **) &e->d_cand, sizeof(int)), "malloc");
+}
+
+void delete_avg(avg_data_t *avgdata)
+{
+  if (avgdata->avgwidth != 0) {
+    for (int i = 0; i < avgdata->avgwidth; i++) free(avgdata->avgarray[i]);
+    free(avgdata->avgarray);
+    free(avgdata->avg);
+    free(avgdata->cum);
+    drop_engine(avgdata);
+  }
+  avgdata->avgwidth = 0;
+  avgdata->avgdepth = 0;
+  avgdata->effdepth = 0;
+}
+
+static double update_avg_common(int mode, avg_data_t *ad, int N, float *psd, int max0, int minbin, int maxbin,
+                                int *peakbin, double *variance)
+{
+  engine *e = find_engine(ad);
+  if (!e) { glb_set_error("update_avg on data that did not go through alloc_avg"); glb_fatal("update_avg"); }
+  const int width = e->width;
+  if (minbin < 0 || maxbin > width || maxbin < minbin || N > width) {
+    glb_set_error("update_avg: band or N outside the allocated width");
+    glb_fatal("update_avg");
+  }
+  /* the reference reads psd[minbin .. maxbin) of the caller's row: upload that span into
+     the ring row of this frame */
+  float *ring_row = e->d_ring + (size_t) (e->frames % e->depth) * width;
+  if (maxbin > minbin)
+    MUST(glb_memcpy_h2d(ring_row + minbin, psd + minbin, sizeof(float) * (maxbin - minbin), e->stream), "h2d");
+  else
+    MUST(glb_memcpy_h2d(ring_row + minbin, psd + minbin, sizeof(float), e->stream), "h2d");
+  glb_avg_args a;
+  memset(&a, 0, sizeof a);
+  a.mode = mode;
+  a.depth = e->depth;
+  a.minbin = minbin;
+  a.maxbin = maxbin;
+  a.max0 = max0;
+  a.nbins = N;
+  a.psd = e->d_ring;
+  a.psd_first_frame = 0;
+  a.psd_stride = width;
+  a.psd_ring_rows = e->depth;
+  a.first_frame = e->frames;
+  a.nframes = 1;
+  a.out_double = 1;
+  a.avg_rows = e->d_avg;
+  a.out_stride = width;
+  a.ret = e->d_ret;
+  a.peak_cand = e->d_cand;
+  a.variance = e->d_var;
+  a.peakbin_init = *peakbin;
+  a.sequential = 1;
+  MUST(glb_launch_avg(&a, e->stream), "launch");
+  double ret = 0.0, var = 0.0;
+  int cand = -1;
+  MUST(glb_memcpy_d2h(ad->avg, e->d_avg, sizeof(double) * N, e->stream), "d2h");
+  MUST(glb_memcpy_d2h(&ret, e->d_ret, sizeof(double), e->stream), "d2h");
+  MUST(glb_memcpy_d2h(&var, e->d_var, sizeof(double), e->stream), "d2h");
+  MUST(glb_memcpy_d2h(&cand, e->d_cand, sizeof(int), e->stream), "d2h");
+  MUST(glb_stream_sync(e->stream), "sync");
+  if (cand >= 0) *peakbin = cand;
+  if (variance) *variance = var;
+  e->frames++;
+  if (ad->effdepth < ad->avgdepth) ad->effdepth++;
+  return ret;
+}
+
+double update_avg_plain(avg_data_t *avgdata, int N, float *psd, int minbin, int maxbin, int *peakbin)
+{
+  return update_avg_common(GLFER_AVG_PLAIN, avgdata, N, psd, 0, minbin, maxbin, peakbin, NULL);
+}
+
+double update_avg_sumextreme(avg_data_t *avgdata, int N, float *psd, int max0, int minbin, int maxbin, int *peakbin)
+{
+  return update_avg_common(GLFER_AVG_SUMEXTREME, avgdata, N, psd, max0, minbin, maxbin, peakbin, NULL);
+}
+
+double update_avg_sumavg(avg_data_t *avgdata, int N, float *psd, int max0, int minbin, int maxbin, int *peakbin,
+                         double *variance)
+{
+  return update_avg_common(GLFER_AVG_SUMAVG, avgdata, N, psd, max0, minbin, maxbin, peakbin, variance);
+}

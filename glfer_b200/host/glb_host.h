@@ -1,0 +1,23 @@
+/* glb_host.h -- internals shared by the C host layer (not installed). */
+#ifndef GLB_HOST_H
+#define GLB_HOST_H
+
+#include "../../include/fft.h"
+#include "../../include/mtm.h"
+#include "../../include/avg.h"
+#include "../../include/glfer_b200.h"
+#include "../../include/glb_shim.h"
+
+double glb_bessel_i0(double x);
+void glb_window_table(int n, int window_type, float *w);
+int glb_dpss(int n, double nw, int kmax, double *tapers, double *lambda);
+int glb_hop(int n, float overlap);
+
+/* values of the hidden globals (weak `opt` / `glfer` when the host program has them) */
+int glb_autoscale(void);
+int glb_first_buffer(void);
+
+/* abort the way the reference does on allocation failure (fft.c:249-252) */
+void glb_fatal(const char *where);
+
+#endif

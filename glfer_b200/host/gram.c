@@ -1,0 +1,652 @@
+/* gram.c -- batched spectrogram plans: the C host layer over the CUDA shim.
+ *
+ * A plan is the batch counterpart of fft_init()/mtm_init() + alloc_avg(): it owns the
+ * window / DPSS taper tables (built on the host in double, uploaded once as floats with the
+ * PSD normalisation folded in), the FFT constant tables and two "slots" of device
+ * buffers with their own streams, so that glfer_gram_run() can overlap the upload of one
+ * chunk of the recording with the kernels and the download of the previous one.
+ *
+ * Folded scaling.  fft_psd divides |X|^2 by N (fft.c:212-216) and mtm_do divides each
+ * eigen-spectrum by lambda_k (mtm.c:215).  The real-FFT split in the kernel produces
+ * 2 X[k]; multiplying the taper by s = 1 / (2 sqrt(N)) (and by 1 / sqrt(lambda_k) for
+ * multitaper) makes |2 s X|^2 the PSD sample itself, so the kernel epilogue is a bare
+ * re^2 + im^2.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "glb_host.h"
+
+#define NSLOT 2
+
+typedef struct {
+  void *stream;
+  void *ev0, *ev1;
+  float *d_samples;     /* staged stream span */
+  size_t samples_cap;   /* floats */
+  long long s_origin, s_count;
+  short *d_pcm;
+  size_t pcm_cap;       /* shorts */
+  float *d_means;
+  size_t means_cap;
+  float *d_psd;         /* [halo + nframes][bins] */
+  size_t psd_cap;       /* floats */
+  float *d_avg;
+  size_t avg_cap;
+  double *d_ret, *d_var;
+  int *d_cand, *d_peak, *d_unres;
+  size_t scal_cap;      /* frames */
+  long long out_first, out_nframes, out_halo;
+} slot_t;
+
+struct glfer_gram_plan {
+  glfer_gram_config cfg;
+  int hop, bins, ntapers;
+  float taper_scale;
+  float *h_window;      /* unit-energy window as compute_window leaves it */
+  double *h_tapers;     /* MTM: [ntapers][n] */
+  double *h_lambda;
+  float *d_tapers;
+  void *tables;
+  slot_t slot[NSLOT];
+  int *d_cand_all, *d_peak_all;   /* whole-run *peakbin candidates / carried values */
+  size_t cand_all_cap;
+};
+
+static __thread char g_msg[512];
+
+const char *glfer_b200_last_error(void)
+{
+  return g_msg[0] ? g_msg : glb_last_error();
+}
+
+static int fail(int code, const char *msg)
+{
+  snprintf(g_msg, sizeof g_msg, "%s", msg);
+  return code;
+}
+
+static int shim(int rc)
+{
+  if (rc != GLB_OK) snprintf(g_msg, sizeof g_msg, "%s", glb_last_error());
+  return rc;   /* GLB_E* and GLFER_E* share values */
+}
+
+#define TRY(x) do { int rc_ = shim(x); if (rc_ != 0) return rc_; } while (0)
+
+int glfer_b200_device_count(void)
+{
+  int c = 0;
+  if (glb_device_count(&c) != GLB_OK) return 0;
+  return c;
+}
+
+void *glfer_b200_host_alloc(size_t bytes)
+{
+  void *p = NULL;
+  if (shim(glb_host_alloc(&p, bytes)) != 0) return NULL;
+  return p;
+}
+
+void glfer_b200_host_free(void *p) { glb_host_free(p); }
+
+unsigned long long glfer_b200_kernel_launches(void) { return glb_kernel_launches(); }
+
+/* hop exactly as prepare_audio computes it (fft.c:70): double product, truncated */
+int glb_hop(int n, float overlap)
+{
+  int n_eff = n * (1.0 - overlap);
+  return n_eff;
+}
+
+void glfer_gram_config_default(glfer_gram_config *c)
+{
+  memset(c, 0, sizeof *c);
+  c->mode = GLFER_MODE_FFT;
+  c->n = 1024;                 /* glfer.c:238-279 */
+  c->window_type = KAISER_WINDOW;
+  c->overlap = 0.0f;
+  c->a = 0.0f;
+  c->limiter = 0;
+  c->sub_mean = 1;             /* opt.autoscale = 1 */
+  c->mtm_w = 4.0f;
+  c->mtm_kmax = 7;
+  c->avg_mode = GLFER_NO_AVG;
+  c->avg_depth = 4;
+  c->avg_minbin = 0;
+  c->avg_maxbin = 0;
+  c->device = 0;
+}
+
+int glfer_gram_hop(const glfer_gram_plan *p) { return p->hop; }
+int glfer_gram_bins(const glfer_gram_plan *p) { return p->bins; }
+long long glfer_gram_num_frames(const glfer_gram_plan *p, long long nsamples) { return nsamples / p->hop; }
+
+static long long halo_frames(const glfer_gram_plan *p, long long first_frame)
+{
+  if (p->cfg.avg_mode == GLFER_NO_AVG) return 0;
+  long long h = p->cfg.avg_depth - 1;
+  return h < first_frame ? h : first_frame;
+}
+
+void glfer_gram_required_span(const glfer_gram_plan *p, long long first_frame, long long nframes,
+                              long long *lo, long long *hi)
+{
+  const long long f0 = first_frame - halo_frames(p, first_frame);
+  long long l = f0 * p->hop - (p->cfg.n - p->hop);
+  if (p->cfg.sub_mean && l > 0) l = (l / p->hop) * p->hop;   /* whole blocks for the block means */
+  *lo = l;
+  *hi = (first_frame + nframes) * (long long) p->hop;
+}
+
+int glfer_gram_window(const glfer_gram_plan *p, float *w)
+{
+  memcpy(w, p->h_window, sizeof(float) * p->cfg.n);
+  return 0;
+}
+
+int glfer_gram_tapers(const glfer_gram_plan *p, double *tapers, double *lambda)
+{
+  if (p->cfg.mode != GLFER_MODE_MTM) return fail(GLFER_EINVAL, "plan is not a multitaper plan");
+  memcpy(tapers, p->h_tapers, sizeof(double) * (size_t) p->ntapers * p->cfg.n);
+  memcpy(lambda, p->h_lambda, sizeof(double) * p->ntapers);
+  return 0;
+}
+
+void glfer_gram_plan_destroy(glfer_gram_plan *p)
+{
+  if (!p) return;
+  glb_set_device(p->cfg.device);
+  for (int i = 0; i < NSLOT; i++) {
+    slot_t *s = &p->slot[i];
+    if (s->stream) glb_stream_sync(s->stream);
+    glb_free(s->d_samples); glb_free(s->d_pcm); glb_free(s->d_means); glb_free(s->d_psd); glb_free(s->d_avg);
+    glb_free(s->d_ret); glb_free(s->d_var); glb_free(s->d_cand); glb_free(s->d_peak); glb_free(s->d_unres);
+    glb_event_destroy(s->ev0); glb_event_destroy(s->ev1);
+    glb_stream_destroy(s->stream);
+  }
+  glb_free(p->d_tapers);
+  glb_free(p->d_cand_all);
+  glb_free(p->d_peak_all);
+  glb_tables_destroy(p->tables);
+  free(p->h_window); free(p->h_tapers); free(p->h_lambda);
+  free(p);
+}
+
+int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
+{
+  g_msg[0] = 0;
+  if (!cfg || !out) return fail(GLFER_EINVAL, "null argument");
+  *out = NULL;
+  if (!glb_fft_supported(cfg->n)) return fail(GLFER_EINVAL, "FFT size must be a power of two in 32..32768");
+  if (cfg->mode != GLFER_MODE_FFT && cfg->mode != GLFER_MODE_MTM) return fail(GLFER_EINVAL, "unknown mode");
+  const int hop = glb_hop(cfg->n, cfg->overlap);
+  if (hop < 1 || hop > cfg->n) return fail(GLFER_EINVAL, "overlap leaves no new samples per block");
+  if (cfg->mode == GLFER_MODE_MTM && (cfg->mtm_kmax < 0 || cfg->mtm_kmax > 31))
+    return fail(GLFER_EINVAL, "mtm_kmax must be in 0..31 (32 eigenvectors exist)");
+  if (cfg->avg_mode != GLFER_NO_AVG) {
+    if (cfg->avg_mode < 1 || cfg->avg_mode > 3) return fail(GLFER_EINVAL, "unknown avg_mode");
+    if (cfg->avg_depth < 1) return fail(GLFER_EINVAL, "avg_depth < 1");
+    if (cfg->avg_minbin < 0 || cfg->avg_maxbin < cfg->avg_minbin || cfg->avg_maxbin > cfg->n / 2 + 1)
+      return fail(GLFER_EINVAL, "averaging band outside [0, n/2+1]");
+  }
+  int ndev = 0;
+  if (glb_device_count(&ndev) != GLB_OK || ndev < 1)
+    return fail(GLFER_ENODEV, "no CUDA device (libglfer_b200 has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(GLFER_EINVAL, "device ordinal out of range");
+  TRY(glb_set_device(cfg->device));
+
+  glfer_gram_plan *p = calloc(1, sizeof *p);
+  if (!p) return fail(GLFER_ENOMEM, "out of memory");
+  p->cfg = *cfg;
+  p->hop = hop;
+  p->bins = cfg->n / 2 + 1;
+  const int n = cfg->n;
+  p->taper_scale = (float) (1.0 / (2.0 * sqrt((double) n)));
+  p->h_window = malloc(sizeof(float) * n);
+  float *scaled = NULL;
+  int rc = 0;
+  if (cfg->mode == GLFER_MODE_FFT) {
+    p->ntapers = 1;
+    glb_window_table(n, cfg->window_type, p->h_window);
+    scaled = malloc(sizeof(float) * n);
+    for (int i = 0; i < n; i++) {
+      /* a rectangular window is NOT applied by the reference (fft.c:146-148): weight 1 */
+      const double w = (cfg->window_type == RECTANGULAR_WINDOW) ? 1.0 : (double) p->h_window[i];
+      scaled[i] = (float) (w * (double) p->taper_scale);
+    }
+  } else {
+    p->ntapers = cfg->mtm_kmax + 1;
+    glb_window_table(n, RECTANGULAR_WINDOW, p->h_window);
+    p->h_tapers = malloc(sizeof(double) * (size_t) p->ntapers * n);
+    p->h_lambda = malloc(sizeof(double) * p->ntapers);
+    /* mtm_params_t.w is a float (mtm.h:42) promoted to double (mtm.c:68) */
+    if (glb_dpss(n, (double) cfg->mtm_w, cfg->mtm_kmax, p->h_tapers, p->h_lambda) != 0) {
+      glfer_gram_plan_destroy(p);
+      return fail(GLFER_EINVAL, "DPSS computation failed");
+    }
+    scaled = malloc(sizeof(float) * (size_t) p->ntapers * n);
+    for (int k = 0; k < p->ntapers; k++) {
+      if (!(p->h_lambda[k] > 0.0)) {
+        free(scaled);
+        glfer_gram_plan_destroy(p);
+        return fail(GLFER_EINVAL, "DPSS eigenvalue not positive: reduce mtm_kmax or raise mtm_w");
+      }
+      const double g = (double) p->taper_scale / sqrt(p->h_lambda[k]);
+      for (int i = 0; i < n; i++) scaled[(size_t) k * n + i] = (float) (p->h_tapers[(size_t) k * n + i] * g);
+    }
+  }
+  rc = shim(glb_malloc((void **) &p->d_tapers, sizeof(float) * (size_t) p->ntapers * n));
+  if (rc == 0) rc = shim(glb_memcpy_h2d(p->d_tapers, scaled, sizeof(float) * (size_t) p->ntapers * n, NULL));
+  free(scaled);
+  if (rc == 0) rc = shim(glb_tables_create(n, &p->tables));
+  for (int i = 0; i < NSLOT && rc == 0; i++) {
+    rc = shim(glb_stream_create(&p->slot[i].stream));
+    if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev0));
+    if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev1));
+    if (rc == 0) rc = shim(glb_malloc((void **) &p->slot[i].d_unres, sizeof(int)));
+  }
+  if (rc != 0) {
+    char keep[512];
+    snprintf(keep, sizeof keep, "%s", g_msg);
+    glfer_gram_plan_destroy(p);
+    snprintf(g_msg, sizeof g_msg, "%s", keep);
+    return rc;
+  }
+  *out = p;
+  return GLFER_OK;
+}
+
+/* grow-only device buffers */
+static int ensure(void **ptr, size_t *cap, size_t want, size_t elem)
+{
+  if (want <= *cap) return 0;
+  if (*ptr) TRY(glb_free(*ptr));
+  *ptr = NULL;
+  *cap = 0;
+  TRY(glb_malloc(ptr, want * elem));
+  *cap = want;
+  return 0;
+}
+
+static int stage_slot(glfer_gram_plan *p, slot_t *s, const float *samples, const short *pcm, long long origin,
+                      long long count)
+{
+  if (count < 0) return fail(GLFER_EINVAL, "negative sample count");
+  TRY(ensure((void **) &s->d_samples, &s->samples_cap, (size_t) count + 2, sizeof(float)));
+  if (pcm) {
+    TRY(ensure((void **) &s->d_pcm, &s->pcm_cap, (size_t) count, sizeof(short)));
+    TRY(glb_memcpy_h2d(s->d_pcm, pcm, sizeof(short) * (size_t) count, s->stream));
+    TRY(glb_launch_pcm16_to_float(s->d_pcm, s->d_samples, count, s->stream));
+  } else {
+    TRY(glb_memcpy_h2d(s->d_samples, samples, sizeof(float) * (size_t) count, s->stream));
+  }
+  s->s_origin = origin;
+  s->s_count = count;
+  (void) p;
+  return 0;
+}
+
+/* queue the kernels of frames [first, first + nframes) on a slot */
+static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long nframes, int *cand_out)
+{
+  const glfer_gram_config *c = &p->cfg;
+  const long long halo = halo_frames(p, first);
+  const long long f0 = first - halo, nf = nframes + halo;
+  long long lo, hi;
+  glfer_gram_required_span(p, first, nframes, &lo, &hi);
+  if (lo < 0) lo = 0;
+  if (lo < s->s_origin || hi > s->s_origin + s->s_count)
+    return fail(GLFER_EINVAL, "staged samples do not cover the requested frames (see glfer_gram_required_span)");
+  TRY(ensure((void **) &s->d_psd, &s->psd_cap, (size_t) nf * p->bins, sizeof(float)));
+
+  const float *d_means = NULL;
+  long long means_first = 0;
+  if (c->sub_mean) {
+    const long long b_lo = lo / p->hop, b_hi = first + nframes;      /* blocks [b_lo, b_hi) */
+    TRY(ensure((void **) &s->d_means, &s->means_cap, (size_t) (b_hi - b_lo), sizeof(float)));
+    TRY(glb_launch_block_means(s->d_samples, s->s_origin, s->s_count, p->hop, b_lo, b_hi - b_lo, s->d_means, s->stream));
+    d_means = s->d_means;
+    means_first = b_lo;
+  }
+  glb_gram_args g;
+  memset(&g, 0, sizeof g);
+  g.n = c->n;
+  g.hop = p->hop;
+  g.samples = s->d_samples;
+  g.origin = s->s_origin;
+  g.count = s->s_count;
+  g.tapers = p->d_tapers;
+  g.ntapers = p->ntapers;
+  g.block_means = d_means;
+  g.means_first_block = means_first;
+  /* RA9MB and the limiter never reach the spectrum in multitaper mode: mtm_do rebuilds
+     inbuf_fft from inbuf_audio (mtm.c:190-192) */
+  g.ra9mb_a = (c->mode == GLFER_MODE_FFT) ? c->a : 0.0f;
+  g.limiter = (c->mode == GLFER_MODE_FFT) ? c->limiter : 0;
+  g.taper_scale = p->taper_scale;
+  g.first_frame = f0;
+  g.nframes = nf;
+  g.rows = s->d_psd;
+  g.row_stride = p->bins;
+  g.rows_db = (c->avg_mode == GLFER_NO_AVG) ? c->scale_db : 0;   /* averaging needs linear PSD */
+  g.spectrum = NULL;
+  g.tables = p->tables;
+  TRY(glb_launch_gram(&g, s->stream));
+
+  if (c->avg_mode != GLFER_NO_AVG) {
+    TRY(ensure((void **) &s->d_avg, &s->avg_cap, (size_t) nframes * p->bins, sizeof(float)));
+    if ((size_t) nframes > s->scal_cap) {
+      glb_free(s->d_ret); glb_free(s->d_var); glb_free(s->d_cand); glb_free(s->d_peak);
+      s->d_ret = s->d_var = NULL; s->d_cand = s->d_peak = NULL; s->scal_cap = 0;
+      TRY(glb_malloc((void **) &s->d_ret, sizeof(double) * (size_t) nframes));
+      TRY(glb_malloc((void **) &s->d_var, sizeof(double) * (size_t) nframes));
+      TRY(glb_malloc((void **) &s->d_cand, sizeof(int) * (size_t) nframes));
+      TRY(glb_malloc((void **) &s->d_peak, sizeof(int) * (size_t) nframes));
+      s->scal_cap = (size_t) nframes;
+    }
+    glb_avg_args a;
+    memset(&a, 0, sizeof a);
+    a.mode = c->avg_mode;
+    a.depth = c->avg_depth;
+    a.minbin = c->avg_minbin;
+    a.maxbin = c->avg_maxbin;
+    a.max0 = c->avg_max0;
+    a.nbins = p->bins;
+    a.psd = s->d_psd;
+    a.psd_first_frame = f0;
+    a.psd_stride = p->bins;
+    a.first_frame = first;
+    a.nframes = nframes;
+    a.out_double = 0;
+    a.avg_rows = s->d_avg;
+    a.out_stride = p->bins;
+    a.rows_db = c->scale_db;
+    a.ret = s->d_ret;
+    a.peak_cand = cand_out ? cand_out : s->d_cand;
+    a.variance = s->d_var;
+    a.peakbin_init = c->avg_peakbin_init;
+    a.unresolved = s->d_unres;
+    a.sequential = 0;
+    if (c->avg_mode == GLFER_AVG_SUMAVG) {
+      TRY(glb_memset(s->d_unres, 0, sizeof(int), s->stream));
+      TRY(glb_launch_avg(&a, s->stream));
+      int unres = 0;
+      TRY(glb_memcpy_d2h(&unres, s->d_unres, sizeof(int), s->stream));
+      TRY(glb_stream_sync(s->stream));
+      if (unres > 0) {             /* a chunk began before any *peakbin write: walk in order */
+        a.sequential = 1;
+        TRY(glb_launch_avg(&a, s->stream));
+      }
+    } else {
+      TRY(glb_launch_avg(&a, s->stream));
+    }
+    /* with cand_out the caller resolves the carried *peakbin once over the whole run */
+    if (!cand_out) TRY(glb_launch_peak_carry(s->d_cand, s->d_peak, nframes, c->avg_peakbin_init, s->stream));
+  }
+  s->out_first = first;
+  s->out_nframes = nframes;
+  s->out_halo = halo;
+  return 0;
+}
+
+static int fetch_slot(glfer_gram_plan *p, slot_t *s, float *psd_rows, float *avg_rows, double *avg_ret,
+                      int *avg_peakbin, double *avg_variance)
+{
+  const size_t nf = (size_t) s->out_nframes;
+  if (psd_rows)
+    TRY(glb_memcpy_d2h(psd_rows, s->d_psd + (size_t) s->out_halo * p->bins, sizeof(float) * nf * p->bins, s->stream));
+  if (p->cfg.avg_mode != GLFER_NO_AVG) {
+    if (avg_rows) TRY(glb_memcpy_d2h(avg_rows, s->d_avg, sizeof(float) * nf * p->bins, s->stream));
+    if (avg_ret) TRY(glb_memcpy_d2h(avg_ret, s->d_ret, sizeof(double) * nf, s->stream));
+    if (avg_peakbin) TRY(glb_memcpy_d2h(avg_peakbin, s->d_peak, sizeof(int) * nf, s->stream));
+    if (avg_variance) TRY(glb_memcpy_d2h(avg_variance, s->d_var, sizeof(double) * nf, s->stream));
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- device-resident API */
+int glfer_gram_stage(glfer_gram_plan *p, const float *samples, long long origin, long long count)
+{
+  g_msg[0] = 0;
+  TRY(glb_set_device(p->cfg.device));
+  return stage_slot(p, &p->slot[0], samples, NULL, origin, count);
+}
+
+int glfer_gram_stage_pcm16(glfer_gram_plan *p, const short *pcm, long long origin, long long count)
+{
+  g_msg[0] = 0;
+  TRY(glb_set_device(p->cfg.device));
+  return stage_slot(p, &p->slot[0], NULL, pcm, origin, count);
+}
+
+int glfer_gram_exec(glfer_gram_plan *p, long long first_frame, long long nframes, float *kernel_ms)
+{
+  g_msg[0] = 0;
+  if (nframes < 0 || first_frame < 0) return fail(GLFER_EINVAL, "negative frame range");
+  TRY(glb_set_device(p->cfg.device));
+  slot_t *s = &p->slot[0];
+  if (kernel_ms) TRY(glb_event_record(s->ev0, s->stream));
+  int rc = exec_slot(p, s, first_frame, nframes, NULL);
+  if (rc != 0) return rc;
+  if (kernel_ms) {
+    TRY(glb_event_record(s->ev1, s->stream));
+    TRY(glb_event_sync(s->ev1));
+    TRY(glb_event_elapsed_ms(s->ev0, s->ev1, kernel_ms));
+  }
+  return 0;
+}
+
+int glfer_gram_sync(glfer_gram_plan *p)
+{
+  TRY(glb_set_device(p->cfg.device));
+  for (int i = 0; i < NSLOT; i++) TRY(glb_stream_sync(p->slot[i].stream));
+  return 0;
+}
+
+int glfer_gram_fetch(glfer_gram_plan *p, float *psd_rows, float *avg_rows, double *avg_ret, int *avg_peakbin,
+                     double *avg_variance)
+{
+  g_msg[0] = 0;
+  TRY(glb_set_device(p->cfg.device));
+  int rc = fetch_slot(p, &p->slot[0], psd_rows, avg_rows, avg_ret, avg_peakbin, avg_variance);
+  if (rc != 0) return rc;
+  return shim(glb_stream_sync(p->slot[0].stream));
+}
+
+/* ---------------------------------------------------------------- host-buffer API */
+static long long chunk_frames(const glfer_gram_plan *p)
+{
+  /* ~32 MiB of new samples per chunk: large enough to run the copy engines and the
+     kernel at full rate, small enough that two slots overlap well */
+  long long f = (32LL << 20) / ((long long) p->hop * 4);
+  if (f < 64) f = 64;
+  const long long min_avg = 16LL * p->cfg.avg_depth;
+  if (p->cfg.avg_mode != GLFER_NO_AVG && f < min_avg) f = min_avg;
+  return f;
+}
+
+static int run_impl(glfer_gram_plan *p, const float *samples, const short *pcm, long long origin, long long count,
+                    long long first_frame, long long nframes, float *psd_rows, float *avg_rows, double *avg_ret,
+                    int *avg_peakbin, double *avg_variance)
+{
+  g_msg[0] = 0;
+  if (nframes < 0 || first_frame < 0) return fail(GLFER_EINVAL, "negative frame range");
+  if (nframes == 0) return 0;
+  TRY(glb_set_device(p->cfg.device));
+  long long lo, hi;
+  glfer_gram_required_span(p, first_frame, nframes, &lo, &hi);
+  if (lo < 0) lo = 0;
+  if (lo < origin || hi > origin + count)
+    return fail(GLFER_EINVAL, "samples do not cover the requested frames (see glfer_gram_required_span)");
+  const long long cf = chunk_frames(p);
+  const int avg_on = p->cfg.avg_mode != GLFER_NO_AVG;
+  /* *peakbin is carried from frame to frame (avg.c:129-133).  SUMAVG needs the carried
+     value inside the kernel (variance excludes it, avg.c:279), so its chunks hand the
+     value over serially; the other modes collect per-frame candidates for the whole run
+     and resolve the carry once at the end, keeping the two slots fully overlapped. */
+  const int serial_carry = avg_on && p->cfg.avg_mode == GLFER_AVG_SUMAVG;
+  const int defer_carry = avg_on && !serial_carry;
+  if (defer_carry) {
+    if ((size_t) nframes > p->cand_all_cap) {
+      glb_free(p->d_cand_all); glb_free(p->d_peak_all);
+      p->d_cand_all = p->d_peak_all = NULL; p->cand_all_cap = 0;
+      TRY(glb_malloc((void **) &p->d_cand_all, sizeof(int) * (size_t) nframes));
+      TRY(glb_malloc((void **) &p->d_peak_all, sizeof(int) * (size_t) nframes));
+      p->cand_all_cap = (size_t) nframes;
+    }
+  }
+  int carried_peak = p->cfg.avg_peakbin_init;
+  const int saved_init = p->cfg.avg_peakbin_init;
+  int *h_last_peak = NULL;
+  int rc = 0;
+  long long done = 0;
+  int ci = 0;
+  /* chunk c runs on slot c % 2; before reusing a slot wait for its previous chunk */
+  while (done < nframes && rc == 0) {
+    slot_t *s = &p->slot[ci % NSLOT];
+    const long long c0 = first_frame + done;
+    const long long cn = (nframes - done < cf) ? nframes - done : cf;
+    rc = shim(glb_stream_sync(s->stream));
+    if (rc) break;
+    if (serial_carry && ci > 0) {
+      slot_t *prev = &p->slot[(ci - 1) % NSLOT];
+      int last = 0;
+      rc = shim(glb_memcpy_d2h(&last, prev->d_peak + (prev->out_nframes - 1), sizeof(int), prev->stream));
+      if (rc == 0) rc = shim(glb_stream_sync(prev->stream));
+      if (rc) break;
+      carried_peak = last;
+    }
+    p->cfg.avg_peakbin_init = carried_peak;
+    long long clo, chi;
+    glfer_gram_required_span(p, c0, cn, &clo, &chi);
+    if (clo < 0) clo = 0;
+    rc = stage_slot(p, s, samples ? samples + (clo - origin) : NULL, pcm ? pcm + (clo - origin) : NULL, clo, chi - clo);
+    if (rc) break;
+    rc = exec_slot(p, s, c0, cn, defer_carry ? p->d_cand_all + done : NULL);
+    if (rc) break;
+    rc = fetch_slot(p, s, psd_rows ? psd_rows + (size_t) done * p->bins : NULL,
+                    avg_rows ? avg_rows + (size_t) done * p->bins : NULL, avg_ret ? avg_ret + done : NULL,
+                    (avg_peakbin && !defer_carry) ? avg_peakbin + done : NULL,
+                    avg_variance ? avg_variance + done : NULL);
+    done += cn;
+    ci++;
+  }
+  (void) h_last_peak;
+  for (int i = 0; i < NSLOT; i++) {
+    int r2 = shim(glb_stream_sync(p->slot[i].stream));
+    if (rc == 0) rc = r2;
+  }
+  p->cfg.avg_peakbin_init = saved_init;
+  if (rc == 0 && defer_carry && avg_peakbin) {
+    void *st = p->slot[0].stream;
+    rc = shim(glb_launch_peak_carry(p->d_cand_all, p->d_peak_all, nframes, saved_init, st));
+    if (rc == 0) rc = shim(glb_memcpy_d2h(avg_peakbin, p->d_peak_all, sizeof(int) * (size_t) nframes, st));
+    if (rc == 0) rc = shim(glb_stream_sync(st));
+  }
+  return rc;
+}
+
+int glfer_gram_run(glfer_gram_plan *p, const float *samples, long long origin, long long count,
+                   long long first_frame, long long nframes, float *psd_rows, float *avg_rows, double *avg_ret,
+                   int *avg_peakbin, double *avg_variance)
+{
+  if (!p || !samples) return fail(GLFER_EINVAL, "null argument");
+  return run_impl(p, samples, NULL, origin, count, first_frame, nframes, psd_rows, avg_rows, avg_ret, avg_peakbin,
+                  avg_variance);
+}
+
+int glfer_gram_run_pcm16(glfer_gram_plan *p, const short *pcm, long long origin, long long count,
+                         long long first_frame, long long nframes, float *psd_rows, float *avg_rows,
+                         double *avg_ret, int *avg_peakbin, double *avg_variance)
+{
+  if (!p || !pcm) return fail(GLFER_EINVAL, "null argument");
+  return run_impl(p, NULL, pcm, origin, count, first_frame, nframes, psd_rows, avg_rows, avg_ret, avg_peakbin,
+                  avg_variance);
+}
+
+/* ---------------------------------------------------------------- time sharding */
+void glfer_gram_shard_range(long long nframes, int ndev, int g, long long *first, long long *count)
+{
+  /* contiguous, as even as possible: the first (nframes % ndev) shards get one extra frame */
+  const long long base = nframes / ndev, extra = nframes % ndev;
+  *first = g * base + (g < extra ? g : extra);
+  *count = base + (g < extra ? 1 : 0);
+}
+
+typedef struct {
+  glfer_gram_config cfg;
+  const float *samples;
+  long long nsamples, first, count;
+  float *psd_rows, *avg_rows;
+  double *avg_ret, *avg_variance;
+  int *avg_peakbin;
+  int bins;
+  int rc;
+  char msg[512];
+} shard_job;
+
+static void *shard_main(void *arg)
+{
+  shard_job *j = arg;
+  glfer_gram_plan *p = NULL;
+  j->rc = glfer_gram_plan_create(&j->cfg, &p);
+  if (j->rc == 0) {
+    const size_t off = (size_t) j->first * j->bins;
+    j->rc = glfer_gram_run(p, j->samples, 0, j->nsamples, j->first, j->count, j->psd_rows ? j->psd_rows + off : NULL,
+                           j->avg_rows ? j->avg_rows + off : NULL, j->avg_ret ? j->avg_ret + j->first : NULL,
+                           j->avg_peakbin ? j->avg_peakbin + j->first : NULL,
+                           j->avg_variance ? j->avg_variance + j->first : NULL);
+  }
+  if (j->rc != 0) snprintf(j->msg, sizeof j->msg, "%s", glfer_b200_last_error());
+  glfer_gram_plan_destroy(p);
+  return NULL;
+}
+
+int glfer_gram_run_sharded(const glfer_gram_config *cfg, int ndev, const int *devices, const float *samples,
+                           long long nsamples, float *psd_rows, float *avg_rows, double *avg_ret, int *avg_peakbin,
+                           double *avg_variance)
+{
+  g_msg[0] = 0;
+  if (!cfg || !samples || ndev < 1 || ndev > 64) return fail(GLFER_EINVAL, "bad arguments");
+  const int hop = glb_hop(cfg->n, cfg->overlap);
+  if (hop < 1) return fail(GLFER_EINVAL, "overlap leaves no new samples per block");
+  const long long nframes = nsamples / hop;
+  shard_job jobs[64];
+  pthread_t th[64];
+  for (int g = 0; g < ndev; g++) {
+    shard_job *j = &jobs[g];
+    memset(j, 0, sizeof *j);
+    j->cfg = *cfg;
+    j->cfg.device = devices ? devices[g] : g;
+    if (g > 0) j->cfg.avg_peakbin_init = -1;
+    j->samples = samples;
+    j->nsamples = nsamples;
+    glfer_gram_shard_range(nframes, ndev, g, &j->first, &j->count);
+    j->psd_rows = psd_rows; j->avg_rows = avg_rows; j->avg_ret = avg_ret;
+    j->avg_peakbin = avg_peakbin; j->avg_variance = avg_variance;
+    j->bins = cfg->n / 2 + 1;
+    pthread_create(&th[g], NULL, shard_main, j);
+  }
+  int rc = 0;
+  for (int g = 0; g < ndev; g++) {
+    pthread_join(th[g], NULL);
+    if (jobs[g].rc != 0 && rc == 0) {
+      rc = jobs[g].rc;
+      snprintf(g_msg, sizeof g_msg, "shard %d: %s", g, jobs[g].msg);
+    }
+  }
+  /* the carried *peakbin (avg.c:129-133) is the one sequential dependency between shards:
+     shards g > 0 ran with the sentinel -1 as their initial value, so leading frames that
+     never wrote *peakbin are recognisable and inherit the previous shard's last value */
+  if (rc == 0 && avg_peakbin && cfg->avg_mode != GLFER_NO_AVG) {
+    for (int g = 1; g < ndev; g++) {
+      const long long f0 = jobs[g].first, f1 = f0 + jobs[g].count;
+      for (long long f = f0; f < f1 && avg_peakbin[f] < 0; f++)
+        avg_peakbin[f] = (f > 0) ? avg_peakbin[f - 1] : cfg->avg_peakbin_init;
+    }
+  }
+  return rc;
+}

@@ -1,0 +1,66 @@
+/* fft.h -- periodogram estimator interface of libglfer_b200 (drop-in for the reference).
+ *
+ * Same type, field and function names, argument meaning and ownership rules as the
+ * reference's fft.h so that source.c:141-146,320-325, glfer.c:143, g_main.c:1109 and
+ * g_scope.c:186-197 compile and link unchanged against this library instead of
+ * fft.c + fft_radix2.c.  Layout is the reference's no-FFTW variant (fft.h:51-63: float
+ * buffers, outbuf aliasing inbuf_fft, fft.c:178-180); build glfer without
+ * HAVE_LIBRFFTW when linking against this library.
+ *
+ * What changes underneath: fft_do() runs window multiply + real FFT + |X|^2 on the
+ * GPU (one frame per call here; the batched path is glfer_b200.h).  There is no CPU
+ * implementation: with no CUDA device the calls print an error and abort the way the
+ * reference does on allocation failure (fft.c:249-252).
+ */
+#ifndef GLFER_B200_FFT_H
+#define GLFER_B200_FFT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* replaces fft.h:51-63 */
+typedef struct {
+  float *inbuf_audio;   /* N samples: (N - hop) of history + hop new ones (fft.c:98-113) */
+  float *inbuf_fft;     /* windowed frame as handed to the FFT (fft.c:127-156) */
+  float *outbuf;        /* half-complex spectrum, aliases inbuf_fft (fft.c:180) */
+  int n;                /* FFT size */
+  float *window;        /* unit-energy window, N floats (fft.c:309-360) */
+  int window_type;      /* enum below */
+  float overlap;        /* fraction of overlap between blocks */
+  float a;              /* RA9MB non-linear processing parameter (fft.c:127) */
+  int limiter;          /* fft.c:151 */
+  int sub_mean;         /* set by fft_init from opt.autoscale (fft.c:186) */
+} fft_params_t;
+
+/* replaces fft.h:67 */
+enum { HANNING_WINDOW = 0, BLACKMAN_WINDOW, GAUSSIAN_WINDOW, WELCH_WINDOW, BARTLETT_WINDOW,
+       RECTANGULAR_WINDOW, HAMMING_WINDOW, KAISER_WINDOW };
+
+/* replaces fft.h:69-75; table and count exported as fft.c:48-60 does */
+typedef struct _fft_window_t fft_window_t;
+struct _fft_window_t {
+  char *name;
+  int type;
+};
+extern fft_window_t fft_windows[];
+extern int num_fft_windows;
+
+/* replaces fft.h:77-81 */
+void prepare_audio(float *audio_buf, fft_params_t *params);
+void fft_init(fft_params_t *params);
+void fft_do(float *audio_buf, fft_params_t *params);
+void fft_psd(float *psd_buf, float *phase_buf, fft_params_t *params);
+void fft_close(fft_params_t *params);
+
+/* replaces fft.h:83 (display/AGC statistics of one PSD row) */
+void compute_floor(float *psd_buf, int n, float *sig_pwr_p, float *floor_pwr_p, float *peak_pwr_p,
+                   unsigned int *peak_bin_p);
+
+/* window table generator (fft.c:63, non-static in the reference) */
+void compute_window(fft_params_t *params);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

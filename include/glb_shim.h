@@ -1,0 +1,137 @@
+/* glb_shim.h -- the thin C-ABI CUDA shim under the C host layer.
+ *
+ * Internal boundary of libglfer_b200.so: plain pointers and sizes only, no C++ or
+ * framework types.  The C host layer (glfer_b200/host/ *.c) never includes CUDA headers; every
+ * device operation goes through these entry points, implemented in
+ * glfer_b200/csrc/gram_kernels.cu.  All functions return 0 on success, a negative
+ * GLB_E* code otherwise, and record a message retrievable with glb_last_error().
+ */
+#ifndef GLB_SHIM_H
+#define GLB_SHIM_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLB_OK 0
+#define GLB_ECUDA (-1)     /* a CUDA runtime call failed */
+#define GLB_EINVAL (-2)    /* invalid argument (e.g. unsupported FFT size) */
+#define GLB_ENOMEM (-3)
+#define GLB_ENODEV (-4)    /* no CUDA device: the library has no CPU fallback */
+
+const char *glb_last_error(void);
+void glb_set_error(const char *msg);
+
+/* devices, memory, streams, events */
+int glb_device_count(int *count);
+int glb_set_device(int dev);
+int glb_sm_count(int dev, int *sms);
+int glb_malloc(void **dptr, size_t bytes);
+int glb_free(void *dptr);
+int glb_memset(void *dptr, int value, size_t bytes, void *stream);
+int glb_host_alloc(void **hptr, size_t bytes);      /* pinned */
+int glb_host_free(void *hptr);
+int glb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);  /* async when stream != NULL */
+int glb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int glb_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int glb_stream_create(void **stream);
+int glb_stream_destroy(void *stream);
+int glb_stream_sync(void *stream);
+int glb_stream_wait_event(void *stream, void *event);
+int glb_device_sync(void);
+int glb_event_create(void **event);
+int glb_event_destroy(void *event);
+int glb_event_record(void *event, void *stream);
+int glb_event_sync(void *event);
+int glb_event_elapsed_ms(void *start, void *stop, float *ms);
+
+/* FFT constant tables (twiddles + real-FFT split factors) for frame length n, on
+ * the current device.  n must be a power of two, 32 <= n <= 32768. */
+int glb_fft_supported(int n);
+int glb_tables_create(int n, void **tables);
+int glb_tables_destroy(void *tables);
+
+/* One launch of the fused spectrogram kernel: frames [first_frame, first_frame +
+ * nframes) of the stream, frame f = stream samples [f*hop - n_ov, f*hop + hop). */
+typedef struct {
+  int n;                       /* frame length N */
+  int hop;                     /* new samples per frame */
+  const float *samples;        /* device: stream samples [origin, origin + count) */
+  long long origin;            /* stream index of samples[0] (may be negative-free: >= 0) */
+  long long count;             /* samples resident; stream indices outside [0,..) and outside the buffer read as 0 */
+  const float *tapers;         /* device: [ntapers][n] floats, pre-scaled (see host layer) */
+  int ntapers;                 /* 1 = periodogram, K' = kmax+1 for multitaper */
+  const float *block_means;    /* device: mean of hop block b at [b - means_first_block], or NULL */
+  long long means_first_block;
+  float ra9mb_a;               /* > 0: x / (a + x^2) before the taper (fft.c:127-136) */
+  int limiter;                 /* 1: sign(v) |v|^0.1 after the taper (fft.c:151-156) */
+  float taper_scale;           /* the scale folded into tapers (needed by limiter / spectrum output) */
+  long long first_frame;
+  long long nframes;
+  float *rows;                 /* device out: [nframes][row_stride] PSD, or NULL */
+  long long row_stride;
+  int rows_db;                 /* 1: write 10*log10(psd) */
+  float *spectrum;             /* device out: [nframes][n/2+1] (re,im) pairs, or NULL (periodogram only) */
+  const void *tables;          /* from glb_tables_create(n) */
+  int groups_hint;             /* 0 = auto: resident frame-groups per launch */
+} glb_gram_args;
+
+int glb_launch_gram(const glb_gram_args *a, void *stream);
+
+/* mean of every complete hop block: means[b - first_block] = mean(stream[b*hop, (b+1)*hop)) */
+int glb_launch_block_means(const float *samples, long long origin, long long count, int hop,
+                           long long first_block, long long nblocks, float *means, void *stream);
+
+/* int16 PCM -> float exactly as wav_fmt.c:113 ((float) s / 32768) */
+int glb_launch_pcm16_to_float(const short *pcm, float *out, long long count, void *stream);
+/* uint8 PCM -> float as wav_fmt.c:108 (((float) b - 128) / 128) */
+int glb_launch_pcm8_to_float(const unsigned char *pcm, float *out, long long count, void *stream);
+
+/* Sliding per-bin frame averaging (avg.c:108-298) over PSD rows resident on the device. */
+typedef struct {
+  int mode;                    /* avgmode_t: 1 sumavg, 2 plain, 3 sumextreme */
+  int depth;
+  int minbin, maxbin;
+  int max0;
+  int nbins;                   /* bins written per output row (N/2+1) */
+  const float *psd;            /* device: row of frame g at psd + (g - psd_first_frame) * psd_stride */
+  long long psd_first_frame;
+  long long psd_stride;
+  int psd_ring_rows;           /* > 0: psd is a ring, frame g lives in row g % psd_ring_rows */
+  long long first_frame;       /* global (since alloc_avg) index of the first output frame */
+  long long nframes;
+  int out_double;              /* 0: float rows, 1: double rows */
+  void *avg_rows;              /* device out [nframes][out_stride] */
+  long long out_stride;
+  int rows_db;                 /* 1: 10*log10 of the averaged row (float rows only) */
+  double *ret;                 /* device out [nframes]: the function's return value */
+  int *peak_cand;              /* device out [nframes]: bin written to *peakbin, or -1 if not written */
+  double *variance;            /* device out [nframes] (sumavg) or NULL */
+  int peakbin_init;            /* caller's *peakbin before the first frame */
+  int *unresolved;             /* device counter: frames whose variance needed an unknown carried peakbin */
+  int sequential;              /* 1: one CTA walks all frames in order (exact carry; slow) */
+} glb_avg_args;
+
+int glb_launch_avg(const glb_avg_args *a, void *stream);
+/* peakbin[f] = peak_cand[f] >= 0 ? peak_cand[f] : peakbin[f-1], peakbin[-1] = init */
+int glb_launch_peak_carry(const int *peak_cand, int *peakbin, long long nframes, int init, void *stream);
+
+/* PSD and phase of one half-complex spectrum (fft_psd, fft.c:203-226): hc[k] = Re X[k],
+ * hc[n-k] = Im X[k]; psd / phase may be NULL; all device pointers. */
+int glb_launch_halfcomplex_psd(const float *hc, int n, float *psd, float *phase, void *stream);
+
+/* Per-row statistics of compute_floor (fft.c:240-294): stats[row] = { sig = largest bin,
+ * floor = (sum of the lowest n - (int)(0.95 n) bins) / 0.05 / n, peak value, peak bin (as
+ * float) }.  nbins <= 16385.  stats: [nrows][4] floats. */
+int glb_launch_floor_stats(const float *rows, long long stride, int nbins, long long nrows, float *stats,
+                           void *stream);
+
+/* counters */
+unsigned long long glb_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,150 @@
+/* glfer_b200.h -- batched spectrogram extension of the estimator interface.
+ *
+ * The reference computes one frame per call (fft_do / mtm_do / update_avg_*, called from
+ * audio_available(), source.c:130-165).  A GPU launch per hop block is latency bound, so
+ * the library adds a batched entry point that a file source or a headless harness calls
+ * once per recording (or per time shard).  Its results equal the sequence of per-call
+ * results of the reference loop:
+ *     for each hop block f:  fft_do; fft_psd   (or mtm_do);   [update_avg_*]
+ * with glfer.first_buffer TRUE on block 0 only: frame f covers stream samples
+ * [f*hop - (N-hop), f*hop + hop) with zeros before the stream start (fft.c:98-113), block
+ * means removed per hop block when sub_mean (fft.c:86-96), averaging warm-up and the
+ * effdepth+1 divisor counted from frame 0 (avg.c:116-156).
+ *
+ * All functions return 0 on success or a negative GLFER_E* code; glfer_b200_last_error()
+ * returns the message.  There is no CPU fallback: without a CUDA device plan creation
+ * fails with GLFER_ENODEV.
+ */
+#ifndef GLFER_B200_H
+#define GLFER_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLFER_OK 0
+#define GLFER_ECUDA (-1)
+#define GLFER_EINVAL (-2)
+#define GLFER_ENOMEM (-3)
+#define GLFER_ENODEV (-4)
+
+/* estimator mode: values of the reference's mode enum (glfer.h:47) */
+#define GLFER_MODE_FFT 0
+#define GLFER_MODE_MTM 1
+/* averaging mode: values of avgmode_t (glfer.h:53-55) */
+#define GLFER_NO_AVG 0
+#define GLFER_AVG_SUMAVG 1
+#define GLFER_AVG_PLAIN 2
+#define GLFER_AVG_SUMEXTREME 3
+
+typedef struct {
+  int mode;            /* GLFER_MODE_FFT | GLFER_MODE_MTM */
+  int n;               /* FFT size (opt.data_block_size): power of two, 32..32768 */
+  int window_type;     /* fft.h window enum; ignored for MTM (forced rectangular, source.c:344) */
+  float overlap;       /* opt.data_blocks_overlap; hop = (int)(n * (1.0 - overlap)) (fft.c:70) */
+  float a;             /* opt.limiter_a, RA9MB parameter; <= 0 disables */
+  int limiter;         /* opt.enable_limiter */
+  int sub_mean;        /* opt.autoscale as latched by fft_init (fft.c:186) */
+  float mtm_w;         /* opt.mtm_w (N*W) */
+  int mtm_kmax;        /* opt.mtm_k: kmax + 1 tapers are used */
+  int avg_mode;        /* GLFER_NO_AVG ... */
+  int avg_depth;       /* opt.avgsamples */
+  int avg_minbin;      /* (int)(opt.min_avgband / binsize) (g_main.c:1145) */
+  int avg_maxbin;
+  int avg_max0;        /* scale_type is *_MAX0 (g_main.c:1148-1151) */
+  int avg_peakbin_init;/* the caller's peakbin before frame 0 */
+  int scale_db;        /* 1: rows are 10*log10(value) (g_main.c:1191-1199) */
+  int device;          /* CUDA device ordinal */
+} glfer_gram_config;
+
+typedef struct glfer_gram_plan glfer_gram_plan;
+
+const char *glfer_b200_last_error(void);
+int glfer_b200_device_count(void);
+/* pinned host memory for fast transfers (optional; any host pointer is accepted) */
+void *glfer_b200_host_alloc(size_t bytes);
+void glfer_b200_host_free(void *p);
+/* kernels launched by this process so far */
+unsigned long long glfer_b200_kernel_launches(void);
+
+void glfer_gram_config_default(glfer_gram_config *cfg);     /* the defaults of glfer.c:238-279 */
+int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **plan);
+void glfer_gram_plan_destroy(glfer_gram_plan *plan);
+
+int glfer_gram_hop(const glfer_gram_plan *plan);
+int glfer_gram_bins(const glfer_gram_plan *plan);                       /* n/2 + 1 */
+long long glfer_gram_num_frames(const glfer_gram_plan *plan, long long nsamples);  /* nsamples / hop */
+/* stream span [lo, hi) the frames [first_frame, first_frame + nframes) read (lo may be
+ * negative: indices < 0 are the zero history) */
+void glfer_gram_required_span(const glfer_gram_plan *plan, long long first_frame, long long nframes,
+                              long long *lo, long long *hi);
+/* window / taper tables as the estimator uses them (unit energy, before internal scaling) */
+int glfer_gram_window(const glfer_gram_plan *plan, float *window /* [n] */);
+int glfer_gram_tapers(const glfer_gram_plan *plan, double *tapers /* [kmax+1][n] */, double *lambda /* [kmax+1] */);
+
+/* ---- one call, host buffers in and out (transfers pipelined with the kernels) ----
+ * samples points at stream index `origin`, `count` samples long, and must cover
+ * glfer_gram_required_span() clipped to [0, inf).  Any output pointer may be NULL.
+ *   psd_rows [nframes][bins]   PSD (or dB when scale_db)
+ *   avg_rows [nframes][bins]   averaged rows (avg_mode != GLFER_NO_AVG)
+ *   avg_ret / avg_peakbin / avg_variance [nframes]: return value, *peakbin, *variance of
+ *   update_avg_* after each frame. */
+int glfer_gram_run(glfer_gram_plan *plan, const float *samples, long long origin, long long count,
+                   long long first_frame, long long nframes, float *psd_rows, float *avg_rows,
+                   double *avg_ret, int *avg_peakbin, double *avg_variance);
+/* same, 16-bit PCM input converted on the device as wav_fmt.c:113 does */
+int glfer_gram_run_pcm16(glfer_gram_plan *plan, const short *pcm, long long origin, long long count,
+                         long long first_frame, long long nframes, float *psd_rows, float *avg_rows,
+                         double *avg_ret, int *avg_peakbin, double *avg_variance);
+
+/* ---- device-resident path: stage once, execute many times, fetch when wanted ---- */
+int glfer_gram_stage(glfer_gram_plan *plan, const float *samples, long long origin, long long count);
+int glfer_gram_stage_pcm16(glfer_gram_plan *plan, const short *pcm, long long origin, long long count);
+/* frames [first_frame, first_frame + nframes) from the staged samples into device rows;
+ * returns after the work is queued.  kernel_ms (may be NULL) receives the device time of
+ * the launch sequence measured with CUDA events on the plan's stream (this call then
+ * waits for completion). */
+int glfer_gram_exec(glfer_gram_plan *plan, long long first_frame, long long nframes, float *kernel_ms);
+int glfer_gram_sync(glfer_gram_plan *plan);
+int glfer_gram_fetch(glfer_gram_plan *plan, float *psd_rows, float *avg_rows, double *avg_ret,
+                     int *avg_peakbin, double *avg_variance);
+
+/* ---- time-sharded multi-GPU run inside one process (one host thread per device) ----
+ * Frames [0, nframes) are split into ndev contiguous ranges; device g gets samples
+ * [F_g*hop - halo, F_{g+1}*hop) (halo = N - hop, plus (depth-1) frames when averaging);
+ * no inter-GPU communication.  devices == NULL means 0..ndev-1. */
+int glfer_gram_run_sharded(const glfer_gram_config *cfg, int ndev, const int *devices, const float *samples,
+                           long long nsamples, float *psd_rows, float *avg_rows, double *avg_ret,
+                           int *avg_peakbin, double *avg_variance);
+/* the shard arithmetic on its own: frame range of shard g of ndev */
+void glfer_gram_shard_range(long long nframes, int ndev, int g, long long *first, long long *count);
+
+/* ---- WAV source (wav_fmt.c:45-121 semantics, LP64-safe) ---- */
+typedef struct {
+  int sample_rate;
+  int bits;             /* 8 or 16 */
+  int channels;
+  long long nsamples;   /* samples in the data chunk (channels not de-interleaved, as the reference) */
+  void *data;           /* raw PCM as read */
+} glfer_wav;
+int glfer_wav_load(const char *path, glfer_wav *wav);
+void glfer_wav_free(glfer_wav *wav);
+/* spectrogram of a WAV exactly as `glfer -f file` would see it block by block, including
+ * the stale tail of a short final read (wav_fmt.c:102-119).  Returns frames via *nframes;
+ * psd_rows must hold glfer_wav_num_frames() rows. */
+long long glfer_wav_num_frames(const glfer_gram_plan *plan, const glfer_wav *wav);
+int glfer_gram_run_wav(glfer_gram_plan *plan, const glfer_wav *wav, float *psd_rows, float *avg_rows,
+                       double *avg_ret, int *avg_peakbin, double *avg_variance);
+
+/* ---- hidden inputs of the per-call interface (fft.c:99,186: globals `glfer`, `opt`) ----
+ * When the host program defines `opt` and `glfer` (as glfer.c:56-62 does) the per-call
+ * functions read them.  Otherwise these setters provide the two values. */
+void glfer_b200_set_autoscale(int autoscale);
+void glfer_b200_set_first_buffer(int first_buffer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,125 @@
+"""Pins the numpy restatement (oracle/glfer_oracle.py) against the reference: the committed
+fixtures generated from the unmodified reference sources, the known-answer values of
+SURVEY.md section 8c, and (when oracle/_ref is present) the reference library itself."""
+import os
+
+import numpy as np
+import pytest
+
+from glfer_b200 import synth
+from oracle import glfer_oracle as O
+from oracle import ref_lib as R
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "glfer_ref_f64.npz"))
+X = synth.pcm16_to_float(GOLD["pcm"])
+have_ref = pytest.mark.skipif(not R.available("f64"), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def test_windows_bit_exact_vs_fixture():
+    for t in range(8):
+        assert np.array_equal(O.compute_window(1024, t), GOLD["windows_1024"][t]), O.WINDOW_NAMES[t]
+
+
+def test_window_kat_values():
+    # w[512] and sum(w) of the unit-energy windows at N=1024
+    kat = {0: (5.105584487e-02, 26.11512763), 1: (5.664945394e-02, 24.34009806), 2: (4.042137787e-02, 30.89686565),
+           3: (4.281169921e-02, 29.19757857), 4: (5.410012975e-02, 27.69926637), 5: (3.125e-02, 32.0),
+           6: (4.959570244e-02, 27.40168354), 7: (5.162739381e-02, 26.40954478)}
+    for t, (mid, total) in kat.items():
+        w = O.compute_window(1024, t).astype(np.float64)
+        assert abs(w[512] - mid) < 2e-9
+        assert abs(w.sum() - total) < 2e-6
+
+
+def test_periodogram_fixtures_bit_exact():
+    assert np.array_equal(O.periodogram(X, 1024, 0, 0.5, True), GOLD["c1_rows"])
+    assert np.array_equal(O.periodogram(X, 1024, 0, 0.5, False), GOLD["c1_rows_nomean"])
+    assert np.array_equal(O.periodogram(X, 4096, 7, 0.75, True), GOLD["c2_rows"])
+    for t in range(8):
+        assert np.array_equal(O.periodogram(X[:8192], 512, t, 0.5, True), GOLD["win_rows"][t])
+    assert np.array_equal(O.periodogram(X[:20000], 1024, 1, 0.9, True), GOLD["odd_rows"])
+    assert np.array_equal(O.periodogram(X[:20000], 1024, 0, 0.5, True, a=0.01, limiter=1), GOLD["preop_rows"])
+
+
+def test_sine_known_answers():
+    i = np.arange(4096)
+    xs = np.sin(2 * np.pi * i / 8).astype(np.float32)
+    h = O.periodogram(xs, 1024, O.HANNING, 0.5)[:2, 128]
+    r = O.periodogram(xs, 1024, O.RECTANGULAR, 0.5)[:2, 128]
+    assert np.allclose(h, [4.146352410e-02, 1.665038764e-01], rtol=2e-7)
+    assert np.allclose(r, [64.0, 256.0], rtol=1e-6)          # rectangular is not normalised
+    assert np.array_equal(h, GOLD["kat_sine_hann"]) and np.array_equal(r, GOLD["kat_sine_rect"])
+
+
+def test_hop_truncation():
+    assert O.hop_size(4096, 0.9) == 409            # float overlap, double product, truncated
+    assert O.hop_size(1024, 0.5) == 512 and O.hop_size(4096, 0.75) == 1024 and O.hop_size(1024, 0.0) == 1024
+
+
+def test_dpss_and_multitaper_fixture():
+    tap, lam = O.gl_dpss(1024, 4.0, 7)
+    assert np.allclose(lam, GOLD["c3_lambda"], rtol=1e-12)
+    sgn = np.sign(np.sum(tap * GOLD["c3_tapers"], axis=1))
+    assert np.max(np.abs(tap * sgn[:, None] - GOLD["c3_tapers"])) < 1e-6
+    # SURVEY 8c (probe of the unmodified reference): 1 - lambda_0..3 and lambda_4..7
+    assert np.allclose(1.0 - lam[:4], [2.946e-10, 2.768e-08, 1.210e-06, 3.245e-05], rtol=2e-3)
+    assert np.allclose(lam[4:], [0.999410076, 0.992504500, 0.936652233, 0.698835614], rtol=0, atol=2e-9)
+    rows = O.multitaper(X, 1024, 0.5, 4.0, 7, True)
+    rel = np.abs(rows.astype(np.float64) - GOLD["c3_rows"]) / GOLD["c3_rows"]
+    assert rel.max() < 1e-6
+
+
+def test_avg_fixtures():
+    mn, mx = GOLD["c2_band"]
+    assert (mn, mx) == O.avg_bins(8000, 4096, 400.0, 1200.0)
+    for mode, name in ((O.AVG_PLAIN, "plain"), (O.AVG_SUMAVG, "sumavg"), (O.AVG_SUMEXTREME, "sumextreme")):
+        a, ret, pk, var = O.update_avg(mode, GOLD["c2_rows"], 4096, 4, int(mn), int(mx), 0)
+        assert np.allclose(a[:, :2049], GOLD[f"c2_avg_{name}"], rtol=1e-12, atol=0)
+        assert np.allclose(ret, GOLD[f"c2_ret_{name}"], rtol=1e-12)
+        assert np.array_equal(pk, GOLD[f"c2_pk_{name}"])
+        if mode == O.AVG_SUMAVG:
+            assert np.allclose(var, GOLD[f"c2_var_{name}"], rtol=1e-12)
+
+
+def test_avg_plain_known_answer():
+    # depth 3, band [2,7), psd[b] = (f+1)(b+1)
+    psd = np.array([[(f + 1) * (b + 1) for b in range(16)] for f in range(5)], dtype=np.float32)
+    a, ret, pk, _ = O.update_avg(O.AVG_PLAIN, psd, 16, 3, 2, 7)
+    assert np.allclose(a[:, 2], [1.5, 3.0, 4.5, 6.75, 9.0])
+    assert np.allclose(ret, [2.25, 4.5, 6.75, 10.125, 13.5])
+    assert (pk == 6).all() and a[0, 0] == 1e-15 and a[0, 7] == 1e-15
+
+
+def test_wav_reader_stale_tail(tmp_path):
+    pcm = GOLD["pcm"][:1000 + 300]
+    p = tmp_path / "t.wav"
+    synth.write_wav16(str(p), pcm, 8000)
+    stream, rate, bits = O.read_wav_blocks(str(p), 500)
+    assert rate == 8000 and bits == 16 and len(stream) == 1500
+    assert np.array_equal(stream[:1300], synth.pcm16_to_float(pcm))
+    assert np.array_equal(stream[1300:], stream[800:1000])        # stale tail of the previous block
+
+
+@have_ref
+def test_restatement_matches_reference_library():
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(30000) * 0.1).astype(np.float32)
+    for n, wt, ov, sm, a, lim in ((256, 2, 0.25, True, 0.0, 0), (2048, 4, 0.6, False, 0.0, 0), (1024, 6, 0.5, True, 0.05, 1),
+                                  (8192, 3, 0.5, True, 0.0, 0)):
+        assert np.array_equal(O.periodogram(x, n, wt, ov, sm, a, lim), R.periodogram(x, n, wt, ov, sm, a, lim))
+    for n in (64, 1024, 16384, 32768):
+        for t in range(8):
+            assert np.array_equal(O.compute_window(n, t), R.window(n, t))
+    q = R.mtm(x, 2048, 0.5, 3.0, 5, True)
+    p = O.multitaper(x, 2048, 0.5, 3.0, 5, True)
+    assert (np.abs(p.astype(np.float64) - q) / q).max() < 1e-6
+    rows = R.periodogram(x, 512, 0, 0.5, True)
+    for mode in (1, 2, 3):
+        for max0 in (0, 1):
+            a1 = O.update_avg(mode, rows, 512, 5, 10, 200, max0)
+            a2 = R.avg(mode, rows, 512, 5, 10, 200, max0)
+            assert np.allclose(a1[0], a2[0], rtol=1e-12) and np.allclose(a1[1], a2[1], rtol=1e-12)
+            assert np.array_equal(a1[2], a2[2])
+    s, f, p, b = R.floor_stats(rows[3])
+    s2, f2, p2, b2 = O.compute_floor(rows[3])
+    assert s == pytest.approx(s2) and f == pytest.approx(f2, rel=1e-5) and p == pytest.approx(p2) and b == b2
