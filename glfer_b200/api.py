@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
         l.glfer_gram_stage_pcm16.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]
         l.glfer_gram_exec.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_float)]
         l.glfer_gram_sync.argtypes = [C.c_void_p]
+        l.glfer_gram_last_gram_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         l.glfer_gram_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         l.glfer_gram_run_sharded.argtypes = [C.POINTER(GramConfig), C.c_int, C.POINTER(C.c_int), C.c_void_p,
                                              C.c_longlong] + [C.c_void_p] * 5
@@ -263,6 +264,11 @@ class GramPlan:
         ms = C.c_float(0.0)
         _check(lib().glfer_gram_exec(self._h, first_frame, nframes, C.byref(ms) if timed else None))
         return ms.value if timed else None
+
+    def last_gram_ms(self) -> float:
+        ms = C.c_float(0.0)
+        _check(lib().glfer_gram_last_gram_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def sync(self):
         _check(lib().glfer_gram_sync(self._h))

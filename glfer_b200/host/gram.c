@@ -23,7 +23,8 @@
 
 typedef struct {
   void *stream;
-  void *ev0, *ev1;
+  void *ev0, *ev1, *ev2, *ev3;
+  int time_gram;        /* record ev2/ev3 around the gram kernel */
   float *d_samples;     /* staged stream span */
   size_t samples_cap;   /* floats */
   long long s_origin, s_count;
@@ -164,7 +165,7 @@ void glfer_gram_plan_destroy(glfer_gram_plan *p)
     if (s->stream) glb_stream_sync(s->stream);
     glb_free(s->d_samples); glb_free(s->d_pcm); glb_free(s->d_means); glb_free(s->d_psd); glb_free(s->d_avg);
     glb_free(s->d_ret); glb_free(s->d_var); glb_free(s->d_cand); glb_free(s->d_peak); glb_free(s->d_unres);
-    glb_event_destroy(s->ev0); glb_event_destroy(s->ev1);
+    glb_event_destroy(s->ev0); glb_event_destroy(s->ev1); glb_event_destroy(s->ev2); glb_event_destroy(s->ev3);
     glb_stream_destroy(s->stream);
   }
   glb_free(p->d_tapers);
@@ -246,6 +247,8 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
     rc = shim(glb_stream_create(&p->slot[i].stream));
     if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev0));
     if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev1));
+    if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev2));
+    if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev3));
     if (rc == 0) rc = shim(glb_malloc((void **) &p->slot[i].d_unres, sizeof(int)));
   }
   if (rc != 0) {
@@ -334,7 +337,9 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   g.rows_db = (c->avg_mode == GLFER_NO_AVG) ? c->scale_db : 0;   /* averaging needs linear PSD */
   g.spectrum = NULL;
   g.tables = p->tables;
+  if (s->time_gram) TRY(glb_event_record(s->ev2, s->stream));
   TRY(glb_launch_gram(&g, s->stream));
+  if (s->time_gram) TRY(glb_event_record(s->ev3, s->stream));
 
   if (c->avg_mode != GLFER_NO_AVG) {
     TRY(ensure((void **) &s->d_avg, &s->avg_cap, (size_t) nframes * p->bins, sizeof(float)));
@@ -428,8 +433,10 @@ int glfer_gram_exec(glfer_gram_plan *p, long long first_frame, long long nframes
   if (nframes < 0 || first_frame < 0) return fail(GLFER_EINVAL, "negative frame range");
   TRY(glb_set_device(p->cfg.device));
   slot_t *s = &p->slot[0];
+  s->time_gram = kernel_ms != NULL;
   if (kernel_ms) TRY(glb_event_record(s->ev0, s->stream));
   int rc = exec_slot(p, s, first_frame, nframes, NULL);
+  s->time_gram = 0;
   if (rc != 0) return rc;
   if (kernel_ms) {
     TRY(glb_event_record(s->ev1, s->stream));
@@ -437,6 +444,12 @@ int glfer_gram_exec(glfer_gram_plan *p, long long first_frame, long long nframes
     TRY(glb_event_elapsed_ms(s->ev0, s->ev1, kernel_ms));
   }
   return 0;
+}
+
+int glfer_gram_last_gram_ms(glfer_gram_plan *p, float *ms)
+{
+  TRY(glb_set_device(p->cfg.device));
+  return shim(glb_event_elapsed_ms(p->slot[0].ev2, p->slot[0].ev3, ms));
 }
 
 int glfer_gram_sync(glfer_gram_plan *p)

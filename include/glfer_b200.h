@@ -107,6 +107,9 @@ int glfer_gram_stage_pcm16(glfer_gram_plan *plan, const short *pcm, long long or
  * the launch sequence measured with CUDA events on the plan's stream (this call then
  * waits for completion). */
 int glfer_gram_exec(glfer_gram_plan *plan, long long first_frame, long long nframes, float *kernel_ms);
+/* device time of the fused spectrogram kernel alone in the last glfer_gram_exec that was
+ * given a non-NULL kernel_ms (the other launches are block means / averaging) */
+int glfer_gram_last_gram_ms(glfer_gram_plan *plan, float *ms);
 int glfer_gram_sync(glfer_gram_plan *plan);
 int glfer_gram_fetch(glfer_gram_plan *plan, float *psd_rows, float *avg_rows, double *avg_ret,
                      int *avg_peakbin, double *avg_variance);
