@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libglfer_b200.so")
+LIB_PATH = os.environ.get("GLFER_B200_LIB") or os.path.join(HERE, "libglfer_b200.so")
 
 MODE_FFT, MODE_MTM = 0, 1
 NO_AVG, AVG_SUMAVG, AVG_PLAIN, AVG_SUMEXTREME = 0, 1, 2, 3

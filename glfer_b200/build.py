@@ -49,6 +49,22 @@ def _run(cmd: list[str], log: str | None = None) -> None:
         raise RuntimeError("build step failed: " + " ".join(cmd))
 
 
+def build_variant(tag: str, extra_nvcc: list[str]) -> str:
+    """Experiment helper: a second library with extra nvcc flags (e.g. another register
+    target), selected at run time with GLFER_B200_LIB=<path>."""
+    build()
+    nvcc = _nvcc()
+    objs = []
+    for src in CU_SOURCES:
+        o = os.path.join(OBJ, os.path.basename(src) + f".{tag}.o")
+        _run([nvcc] + NVCC_FLAGS + extra_nvcc + ["-c", os.path.join(HERE, src), "-o", o], log=o + ".log")
+        objs.append(o)
+    objs += [os.path.join(OBJ, os.path.basename(src) + ".o") for src in C_SOURCES]
+    out = os.path.join(HERE, f"libglfer_b200_{tag}.so")
+    _run([nvcc, "-shared", "-o", out] + objs + ["-Xcompiler", "-pthread", "-lm", "-lpthread"])
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]

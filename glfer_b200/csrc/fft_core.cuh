@@ -4,8 +4,9 @@
 // z[m] = x[2m] + i x[2m+1], followed by the even/odd split.  One frame is owned by
 // T = M/16 threads; every thread holds P = 16 complex points in registers and the
 // passes exchange data through one M-entry float2 buffer in shared memory
-// (Stockham auto-sort indexing, XOR-swizzled so both the strided first-pass stores
-// and the unit-stride loads are bank-conflict free).
+// (Stockham auto-sort indexing; the buffer is padded by 2 entries per 16 so that the
+// strided first-pass stores and the unit-stride loads are both bank-conflict free AND
+// every address is a per-thread base plus a compile-time immediate).
 //
 // Everything here is __host__ __device__ so tests/emu (g++) can run the exact index
 // arithmetic on the CPU, phase by phase, without a GPU.  This replaces (does not
@@ -19,7 +20,9 @@
 #define GLB_HD inline
 #include <cmath>
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #endif
 
 namespace glb {
@@ -70,8 +73,11 @@ GLB_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b
 GLB_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 GLB_HD float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
 
-// XOR swizzle of a float2 index: low 4 bits (the 8-byte bank pair) ^= next 4 bits.
-GLB_HD int swz(int p) { return p ^ ((p >> 4) & 15); }
+// Padded float2 index: 2 spare entries after every 16 (16 B alignment of even entries is
+// kept, so pairs can move as one 128-bit access).  pad(a + c) = pad(a) + c + c/8 whenever
+// c is a multiple of 16: strided accesses become base + immediate.
+GLB_HD int pad(int p) { return p + 2 * (p >> 4); }
+template <int M> struct BufSize { static constexpr int value = M + M / 8 + 2; };   // float2 entries
 
 // ------------------------------------------------------------------ in-register DFTs
 // Forward transforms (kernel e^{-2 pi i nk/R}) over v[0], v[S], ..., v[(R-1)S];
@@ -150,7 +156,12 @@ template <int S> struct Dft<16, S> { static GLB_HD void run(float2 *v) { dft16<S
 
 // ------------------------------------------------------------------ passes
 // Element q of thread t in every non-final pass is entry t + T*q of the buffer.
-//
+template <int M> GLB_HD int ld_index(int t, int q) {
+  constexpr int T = M / kPoints;
+  if constexpr (T % 16 == 0) return pad(t) + q * (T + T / 8);
+  else return pad(t + T * q);
+}
+
 // pass_store<M,P>: twiddle (P > 0), radix-R butterflies on the 16 register points
 // and Stockham store: butterfly j = t + u*T (u < 16/R), k = j mod Ns, output r' goes
 // to entry (j - k) * R + k + r' * Ns.
@@ -170,17 +181,27 @@ GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
       for (int r = 1; r < R; r++) v[u + r * S] = cmul(v[u + r * S], twp[(r - 1) * Ns]);
     }
     Dft<R, S>::run(v + u);
-    const int base = (j - k) * R + k;
+    if constexpr (P == 0 && R == 16) {
+      // 16 consecutive entries 16j..16j+15 -> padded 18j..18j+15, as eight 128-bit stores
+      float4 *dst = reinterpret_cast<float4 *>(buf + 18 * j);
 #pragma unroll
-    for (int r = 0; r < R; r++) buf[swz(base + r * Ns)] = v[u + r * S];
+      for (int r = 0; r < 16; r += 2) dst[r / 2] = make_float4(v[u + r * S].x, v[u + r * S].y, v[u + (r + 1) * S].x, v[u + (r + 1) * S].y);
+    } else if constexpr (Ns % 16 == 0) {
+      const int base = pad((j - k) * R + k);
+#pragma unroll
+      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 8)] = v[u + r * S];
+    } else {
+      const int base = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; r++) buf[pad(base + r * Ns)] = v[u + r * S];
+    }
   }
 }
 
 template <int M>
 GLB_HD void pass_load(float2 *v, int t, const float2 *buf) {
-  constexpr int T = M / kPoints;
 #pragma unroll
-  for (int q = 0; q < kPoints; q++) v[q] = buf[swz(t + T * q)];
+  for (int q = 0; q < kPoints; q++) v[q] = buf[ld_index<M>(t, q)];
 }
 
 // Final pass: radix 8, Ns = M/8 = 2T.  Thread t owns butterflies jA = t and
@@ -195,10 +216,19 @@ GLB_HD void last_pass(float2 *v, int t, const float2 *buf, const float2 *tw) {
   const int jB = (t == 0) ? T : 2 * T - t;
   const float2 *twA = tw + TwOffset<M, NP - 1>::value + jA;
   const float2 *twB = tw + TwOffset<M, NP - 1>::value + jB;
+  if constexpr (Ns % 16 == 0) {
+    const int bA = pad(jA), bB = pad(jB);
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
-    v[r] = buf[swz(jA + r * Ns)];
-    v[8 + r] = buf[swz(jB + r * Ns)];
+    for (int r = 0; r < 8; r++) {
+      v[r] = buf[bA + r * (Ns + Ns / 8)];
+      v[8 + r] = buf[bB + r * (Ns + Ns / 8)];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      v[r] = buf[pad(jA + r * Ns)];
+      v[8 + r] = buf[pad(jB + r * Ns)];
+    }
   }
 #pragma unroll
   for (int r = 1; r < 8; r++) {
@@ -221,6 +251,236 @@ GLB_HD void split_pair(float2 zk, float2 zm, float2 vk, float2 &a, float2 &b) {
 }
 
 GLB_HD float norm2(float2 a) { return a.x * a.x + a.y * a.y; }
+
+// ------------------------------------------------------------------ register-resident twiddles
+// The twiddles a thread needs do not depend on the frame, so a kernel that walks many
+// frames keeps a few base powers in registers and rebuilds the rest with one complex
+// multiply each (products of two correctly rounded roots: ~1.2e-7 relative, the same
+// order as the FFT's own rounding).  This removes every per-frame table load:
+//   mid pass, radix 16: w^1 w^2 w^3 w^4 w^8 w^12 kept, w^(4a+b) = w^(4a) w^b
+//   mid pass, radix 8 : w^1..w^4 kept, w^5 w^6 w^7 = w^4 w^(1..3)
+//   last pass (radix 8): butterfly A as radix 8; butterfly B = 2T - t uses
+//     W_M^(jB r) = W_8^r conj(W_M^(t r)): conjugate twiddles and a one-place cyclic shift
+//     of the DFT outputs (thread 0, whose B is butterfly T, multiplies by W_16^r instead)
+//   split factors: V_(t + r' 2T) = V_t W_16^r'
+template <int R> struct TwBases;
+template <> struct TwBases<16> { static constexpr int n = 6; };
+template <> struct TwBases<8> { static constexpr int n = 4; };
+template <> struct TwBases<4> { static constexpr int n = 3; };
+template <> struct TwBases<2> { static constexpr int n = 1; };
+template <> struct TwBases<1> { static constexpr int n = 0; };
+
+struct TwRegs {
+  float2 mid[2][12];   // passes 1 and 2 (when they are not the last): [u * nbases + i]
+  float2 last[4];      // w_a^1..w_a^4, w_a = W_M^t
+  float2 v0;           // V_t = -i exp(-2 pi i t / N)
+};
+
+template <int M, int P>
+GLB_HD void load_mid_bases(TwRegs &tr, int t, const float2 *tw) {
+  if constexpr (P >= 1 && P < Plan<M>::NP - 1) {
+    constexpr int T = M / kPoints;
+    constexpr int R = PlanRadix<M, P>::R, Ns = PlanRadix<M, P>::Ns, S = kPoints / R, NB = TwBases<R>::n;
+#pragma unroll
+    for (int u = 0; u < S; u++) {
+      const int k = (t + u * T) & (Ns - 1);
+      const float2 *twp = tw + TwOffset<M, P>::value + k;
+      if constexpr (R == 16) {
+        const int e[6] = {1, 2, 3, 4, 8, 12};
+#pragma unroll
+        for (int i = 0; i < 6; i++) tr.mid[P - 1][u * NB + i] = twp[(e[i] - 1) * Ns];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NB; i++) tr.mid[P - 1][u * NB + i] = twp[i * Ns];
+      }
+    }
+  }
+}
+
+template <int M>
+GLB_HD void load_tw_regs(TwRegs &tr, int t, const float2 *tw, const float2 *vtab) {
+  constexpr int T = M / kPoints, NP = Plan<M>::NP;
+  load_mid_bases<M, 1>(tr, t, tw);
+  load_mid_bases<M, 2>(tr, t, tw);
+  const float2 *twA = tw + TwOffset<M, NP - 1>::value + t;
+#pragma unroll
+  for (int i = 0; i < 4; i++) tr.last[i] = twA[i * 2 * T];
+  tr.v0 = vtab[t];
+}
+
+// v[u + r S] *= w^r for r = 1..R-1 from the kept bases
+template <int R, int S>
+GLB_HD void apply_tw_bases(float2 *v, const float2 *b) {
+  if constexpr (R == 16) {
+    const float2 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3], w8 = b[4], w12 = b[5];
+    v[1 * S] = cmul(v[1 * S], w1);
+    v[2 * S] = cmul(v[2 * S], w2);
+    v[3 * S] = cmul(v[3 * S], w3);
+    v[4 * S] = cmul(v[4 * S], w4);
+    v[5 * S] = cmul(v[5 * S], cmul(w4, w1));
+    v[6 * S] = cmul(v[6 * S], cmul(w4, w2));
+    v[7 * S] = cmul(v[7 * S], cmul(w4, w3));
+    v[8 * S] = cmul(v[8 * S], w8);
+    v[9 * S] = cmul(v[9 * S], cmul(w8, w1));
+    v[10 * S] = cmul(v[10 * S], cmul(w8, w2));
+    v[11 * S] = cmul(v[11 * S], cmul(w8, w3));
+    v[12 * S] = cmul(v[12 * S], w12);
+    v[13 * S] = cmul(v[13 * S], cmul(w12, w1));
+    v[14 * S] = cmul(v[14 * S], cmul(w12, w2));
+    v[15 * S] = cmul(v[15 * S], cmul(w12, w3));
+  } else if constexpr (R == 8) {
+    const float2 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3];
+    v[1 * S] = cmul(v[1 * S], w1);
+    v[2 * S] = cmul(v[2 * S], w2);
+    v[3 * S] = cmul(v[3 * S], w3);
+    v[4 * S] = cmul(v[4 * S], w4);
+    v[5 * S] = cmul(v[5 * S], cmul(w4, w1));
+    v[6 * S] = cmul(v[6 * S], cmul(w4, w2));
+    v[7 * S] = cmul(v[7 * S], cmul(w4, w3));
+  } else if constexpr (R == 4) {
+    v[1 * S] = cmul(v[1 * S], b[0]);
+    v[2 * S] = cmul(v[2 * S], b[1]);
+    v[3 * S] = cmul(v[3 * S], b[2]);
+  } else if constexpr (R == 2) {
+    v[1 * S] = cmul(v[1 * S], b[0]);
+  }
+}
+
+// mid pass with register twiddles, split in two so the block barrier can sit between the
+// arithmetic and the stores (warps then wait with their butterflies already done)
+template <int M, int P>
+GLB_HD void pass_compute_rt(float2 *v, const TwRegs &tr) {
+  constexpr int R = PlanRadix<M, P>::R, S = kPoints / R, NB = TwBases<R>::n;
+#pragma unroll
+  for (int u = 0; u < S; u++) {
+    if constexpr (P > 0) apply_tw_bases<R, S>(v + u, &tr.mid[P - 1][u * NB]);
+    Dft<R, S>::run(v + u);
+  }
+}
+
+template <int M, int P>
+GLB_HD void pass_scatter(const float2 *v, int t, float2 *buf) {
+  constexpr int T = M / kPoints;
+  constexpr int R = PlanRadix<M, P>::R, Ns = PlanRadix<M, P>::Ns, S = kPoints / R;
+#pragma unroll
+  for (int u = 0; u < S; u++) {
+    const int j = t + u * T;
+    const int k = j & (Ns - 1);
+    if constexpr (P == 0 && R == 16) {
+      float4 *dst = reinterpret_cast<float4 *>(buf + 18 * j);
+#pragma unroll
+      for (int r = 0; r < 16; r += 2) dst[r / 2] = make_float4(v[u + r * S].x, v[u + r * S].y, v[u + (r + 1) * S].x, v[u + (r + 1) * S].y);
+    } else if constexpr (Ns % 16 == 0) {
+      const int base = pad((j - k) * R + k);
+#pragma unroll
+      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 8)] = v[u + r * S];
+    } else {
+      const int base = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; r++) buf[pad(base + r * Ns)] = v[u + r * S];
+    }
+  }
+}
+
+// last pass with register twiddles; on return v[r'] = Z[jA + r' 2T], v[8 + r'] = Z[jB + r' 2T]
+template <int M>
+GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, const TwRegs &tr) {
+  constexpr int T = M / kPoints, NP = Plan<M>::NP, Ns = 2 * T;
+  const int jA = t;
+  const int jB = (t == 0) ? T : 2 * T - t;
+  if constexpr (Ns % 16 == 0) {
+    const int bA = pad(jA), bB = pad(jB);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      v[r] = buf[bA + r * (Ns + Ns / 8)];
+      v[8 + r] = buf[bB + r * (Ns + Ns / 8)];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      v[r] = buf[pad(jA + r * Ns)];
+      v[8 + r] = buf[pad(jB + r * Ns)];
+    }
+  }
+  const float2 w1 = tr.last[0], w2 = tr.last[1], w3 = tr.last[2], w4 = tr.last[3];
+  const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+  const float2 w[8] = {make_float2(1.f, 0.f), w1, w2, w3, w4, w5, w6, w7};
+#pragma unroll
+  for (int r = 1; r < 8; r++) v[r] = cmul(v[r], w[r]);
+  dft8<1>(v);
+  if (t != 0) {
+    // B: x_r conj(w_a^r), DFT8, outputs shifted by one place
+    float2 y[8];
+    y[0] = v[8];
+#pragma unroll
+    for (int r = 1; r < 8; r++) y[r] = cmulc(v[8 + r], w[r]);
+    dft8<1>(y);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[8 + r] = y[(r + 1) & 7];
+  } else {
+    // thread 0: butterfly T, twiddles W_M^(T r) = W_16^r from the table
+    const float2 *twB = tw + TwOffset<M, NP - 1>::value + T;
+#pragma unroll
+    for (int r = 1; r < 8; r++) v[8 + r] = cmul(v[8 + r], twB[(r - 1) * Ns]);
+    dft8<1>(v + 8);
+  }
+}
+
+GLB_HD float2 w16_mul(float2 q, int e) {
+  // q * exp(-2 pi i e / 16), e = 0..7, constants folded after unrolling
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  switch (e) {
+    case 0: return q;
+    case 1: return cmul(q, make_float2(c1, -s1));
+    case 2: return make_float2((q.x + q.y) * h, (q.y - q.x) * h);
+    case 3: return cmul(q, make_float2(s1, -c1));
+    case 4: return mul_mi(q);
+    case 5: return cmul(q, make_float2(-s1, -c1));
+    case 6: return make_float2((q.y - q.x) * h, -(q.x + q.y) * h);
+    default: return cmul(q, make_float2(-c1, -s1));
+  }
+}
+
+// split with V_k = V_t W_16^rp rebuilt from the kept V_t
+GLB_HD void split_pair_rt(float2 zk, float2 zm, float2 v0, int rp, float2 &a, float2 &b) {
+  float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
+  float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
+  float2 vq = cmul(v0, w16_mul(q, rp));
+  a = cadd(p, vq);
+  b = csub(p, vq);
+}
+
+template <int M, class F>
+GLB_HD void emit_bins_rt(const float2 *v, int t, const float2 *vtab, const TwRegs &tr, F &&f) {
+  constexpr int T = M / kPoints;
+  float2 a, b;
+  if (t != 0) {
+#pragma unroll
+    for (int rp = 0; rp < 8; rp++) {
+      split_pair_rt(v[rp], v[8 + 7 - rp], tr.v0, rp, a, b);
+      f(2 * rp, a, false);
+      f(2 * rp + 1, b, true);
+    }
+  } else {
+    split_pair(v[0], v[0], vtab[0], a, b);
+    f(0, a, false);
+    f(1, b, true);
+#pragma unroll
+    for (int rp = 1; rp < 4; rp++) {
+      split_pair(v[rp], v[8 - rp], vtab[rp * 2 * T], a, b);
+      f(2 * rp, a, false);
+      f(2 * rp + 1, b, true);
+    }
+    split_pair(v[4], v[4], vtab[M / 2], a, b);
+    f(8, a, false);
+#pragma unroll
+    for (int rp = 0; rp < 4; rp++) {
+      split_pair(v[8 + rp], v[8 + 7 - rp], vtab[T + rp * 2 * T], a, b);
+      f(9 + 2 * rp, a, false);
+      f(10 + 2 * rp, b, true);
+    }
+  }
+}
 
 // Bin bookkeeping of the final pass.  For thread t >= 1 pair r' (0..7) is
 // (Z[k], Z[M-k]) with k = t + r' 2T held in (v[r'], v[8 + 7 - r']).  Thread 0 pairs

@@ -165,8 +165,11 @@ struct KParams {
   long long origin, count;
   const float *tapers;
   int ntapers;
-  const float *means;
+  const float *means;         // pre-computed block means (general geometry), or nullptr
   long long means_first_block;
+  int fused_mean;             // 1: block means are computed inside the kernel (regular geometry)
+  int qs;                     // regular geometry: hop = 2T << qs
+  float inv_hop_mean;         // 1 / hop
   int hop, n_ov, cblk;        // cblk = ceil(n_ov / hop)
   float inv_hop;
   float ra9mb_a;
@@ -186,110 +189,267 @@ struct KParams {
 #define GLB_REG_TARGET 80
 #endif
 template <int M> struct Geo {
+  static constexpr int N = 2 * M;
   static constexpr int T = M / kPoints;
   static constexpr int G = (T >= 128) ? 1 : 128 / T;   // frame groups per CTA
   static constexpr int THREADS = G * T;
-  static constexpr size_t SMEM = (size_t) G * M * sizeof(float2);
+  static constexpr int NW = (T + 31) / 32;             // warps per group
+  // frames are staged in shared memory by TMA bulk copies, one frame ahead, when the
+  // staging buffer still leaves room for >= 2 CTAs per SM
+  static constexpr bool STAGE = (M <= 4096);           // (used by the multitaper variant only)
+  // twiddles kept in registers across frames instead of per-frame table loads
+  static constexpr bool RT = (M <= 2048);
+  static constexpr size_t BUF_BYTES = (size_t) BufSize<M>::value * sizeof(float2);      // multiple of 16
+  static constexpr size_t RED_BYTES = 16 * NW * sizeof(float) + 16 * sizeof(float);     // partial sums + means
+  // per frame group: FFT buffer | [staging buffer] | reduction scratch | mbarrier
+  static __host__ __device__ constexpr size_t stage_bytes(bool multi) { return (STAGE && multi) ? (size_t) N * sizeof(float) : 0; }
+  static __host__ __device__ constexpr size_t group_bytes(bool multi) { return ((BUF_BYTES + stage_bytes(multi) + RED_BYTES + 16 + 15) / 16) * 16; }
+  static __host__ __device__ constexpr size_t smem_bytes(bool multi) { return (size_t) G * group_bytes(multi); }
   // CTAs per SM the register allocation is tuned for (~GLB_REG_TARGET registers per thread)
   static constexpr int MINB_ = 65536 / (THREADS * GLB_REG_TARGET);
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
 };
 
+// ---- mbarrier / TMA bulk-copy helpers (1-D cp.async.bulk global -> shared) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
 
-// Gather + pre-ops + taper for one frame: v[q] = z[t + T q], z[m] = y[2m] + i y[2m+1].
-template <int M>
-__device__ __forceinline__ void load_frame(float2 (&v)[kPoints], int t, const KParams &p, long long f, int j) {
-  constexpr int T = M / kPoints, N = 2 * M;
-  const long long s0 = f * (long long) p.hop - p.n_ov;   // stream index of frame sample 0
+// frame f can be fetched by one bulk copy: entirely inside the staged samples, no zero
+// history, 16-byte aligned
+__device__ __forceinline__ bool frame_bulk_ok(const KParams &p, long long f, int n) {
+  const long long s0 = f * (long long) p.hop - p.n_ov;
   const long long rel = s0 - p.origin;
-  const float *tap = p.tapers + (size_t) j * N;
-  const bool interior = (s0 >= 0) && (rel >= 0) && (rel + N <= p.count) && ((rel & 1) == 0);
-  const bool plain = (p.ra9mb_a <= 0.f) && (p.limiter == 0);
-  if (interior && plain) {
-    const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
-    const float2 *w2 = reinterpret_cast<const float2 *>(tap);
-    if (p.means == nullptr) {
+  return (s0 >= 0) && (rel >= 0) && (rel + n <= p.count) && ((rel & 3) == 0);
+}
+
+// Raw samples of one frame: x[q] = (y[2m], y[2m+1]), m = t + T q; zeros before the stream.
+template <int M>
+__device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KParams &p, long long f, const float *stage,
+                                         bool staged) {
+  constexpr int T = M / kPoints, N = 2 * M;
+  if (staged) {
+    const float2 *s2 = reinterpret_cast<const float2 *>(stage);
 #pragma unroll
-      for (int q = 0; q < kPoints; q++) {
-        const float2 x = ldg2(src + t + T * q);
-        const float2 w = ldg2(w2 + t + T * q);
-        v[q] = make_float2(x.x * w.x, x.y * w.y);
-      }
-    } else {
-      // block of frame sample i (all >= 0 here): f - cblk + floor((i + cblk*hop - n_ov) / hop)
-      const float *mu = p.means + (f - p.cblk - p.means_first_block);
-      const float off = (float) (p.cblk * p.hop - p.n_ov) + 0.5f;
-#pragma unroll
-      for (int q = 0; q < kPoints; q++) {
-        const int i = 2 * (t + T * q);
-        const float2 x = ldg2(src + t + T * q);
-        const float2 w = ldg2(w2 + t + T * q);
-        const int b0 = (int) (((float) i + off) * p.inv_hop);
-        const int b1 = (int) (((float) (i + 1) + off) * p.inv_hop);
-        const float m0 = __ldg(mu + b0);
-        const float m1 = (b1 == b0) ? m0 : __ldg(mu + b1);
-        v[q] = make_float2((x.x - m0) * w.x, (x.y - m1) * w.y);
-      }
-    }
+    for (int q = 0; q < kPoints; q++) x[q] = s2[t + T * q];
     return;
   }
-  // general path: stream edges, odd alignment, pre-ops
-  const float off = (float) (p.cblk * p.hop - p.n_ov) + 0.5f;
+  const long long s0 = f * (long long) p.hop - p.n_ov;
+  const long long rel = s0 - p.origin;
+  if ((s0 >= 0) && (rel >= 0) && (rel + N <= p.count) && ((rel & 1) == 0)) {
+    const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
+#pragma unroll
+    for (int q = 0; q < kPoints; q++) x[q] = ldg2(src + t + T * q);
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < kPoints; q++) {
     float y[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const int i = 2 * (t + T * q) + e;
-      const long long s = s0 + i;
+      const long long s = s0 + 2 * (t + T * q) + e;
       const long long r = s - p.origin;
-      float x = 0.f;
-      if (s >= 0 && r >= 0 && r < p.count) {
-        x = __ldg(p.samples + r);
-        if (p.means != nullptr) {
-          const int b = (int) (((float) i + off) * p.inv_hop);
-          x -= __ldg(p.means + (f - p.cblk - p.means_first_block) + b);
-        }
-      }
-      if (p.ra9mb_a > 0.f) x = x / (p.ra9mb_a + x * x);
-      x *= __ldg(tap + i);
+      y[e] = (s >= 0 && r >= 0 && r < p.count) ? __ldg(p.samples + r) : 0.f;
+    }
+    x[q] = make_float2(y[0], y[1]);
+  }
+}
+
+// Block-mean removal inside the kernel (prepare_audio, fft.c:86-96) for the regular
+// geometry hop = 2T << QS, n_ov a multiple of hop: the frame is NB = 16 >> QS whole hop
+// blocks, block b = registers q with (q >> QS) == b.  Every thread sums its share of each
+// block, warps reduce by shuffle, the group combines through shared memory.  A block gets
+// the same summation tree in every frame it appears in, so its mean is bit-identical
+// across frames (and across time shards).  Zero history sums to a zero mean.
+template <int M, int QS>
+__device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, float *red, float inv_hop) {
+  constexpr int T = M / kPoints, NW = (T + 31) / 32, NB = kPoints >> QS;
+  constexpr int W = T < 32 ? T : 32;      // lanes of a warp that belong to this group
+  float bs[NB];
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = b << QS; q < (b + 1) << QS; q++) s += x[q].x + x[q].y;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    bs[b] = s;
+  }
+  if (NW > 1) {
+    const int w = t >> 5;
+    if ((t & 31) == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) red[b * NW + w] = bs[b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      float s = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; w2++) s += red[b * NW + w2];
+      bs[b] = s;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kPoints; q++) {
+    const float m = bs[q >> QS] * inv_hop;
+    x[q].x -= m;
+    x[q].y -= m;
+  }
+}
+
+template <int M>
+__device__ __forceinline__ void remove_block_means_qs(float2 (&x)[kPoints], int t, float *red, const KParams &p) {
+  switch (p.qs) {
+    case 4: remove_block_means<M, 4>(x, t, red, p.inv_hop_mean); break;
+    case 3: remove_block_means<M, 3>(x, t, red, p.inv_hop_mean); break;
+    case 2: remove_block_means<M, 2>(x, t, red, p.inv_hop_mean); break;
+    case 1: remove_block_means<M, 1>(x, t, red, p.inv_hop_mean); break;
+    default: remove_block_means<M, 0>(x, t, red, p.inv_hop_mean); break;
+  }
+}
+
+// pre-computed block means, any geometry: block of frame sample i is
+// f - cblk + floor((i + cblk*hop - n_ov) / hop); samples before the stream keep 0
+template <int M>
+__device__ __forceinline__ void remove_table_means(float2 (&x)[kPoints], int t, const KParams &p, long long f) {
+  constexpr int T = M / kPoints;
+  const long long s0 = f * (long long) p.hop - p.n_ov;
+  const float *mu = p.means + (f - p.cblk - p.means_first_block);
+  const float off = (float) (p.cblk * p.hop - p.n_ov) + 0.5f;
+#pragma unroll
+  for (int q = 0; q < kPoints; q++) {
+    const int i = 2 * (t + T * q);
+    if (s0 + i >= 0) x[q].x -= __ldg(mu + (int) (((float) i + off) * p.inv_hop));
+    if (s0 + i + 1 >= 0) x[q].y -= __ldg(mu + (int) (((float) (i + 1) + off) * p.inv_hop));
+  }
+}
+
+// RA9MB -> taper -> limiter (fft.c:127-156); the common case is the bare multiply
+template <int M, bool PLAIN>
+__device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (&x)[kPoints], int t, const KParams &p,
+                                            const float *tap) {
+  constexpr int T = M / kPoints;
+  const float2 *w2 = reinterpret_cast<const float2 *>(tap);
+  if (PLAIN || (p.ra9mb_a <= 0.f && p.limiter == 0)) {
+#pragma unroll
+    for (int q = 0; q < kPoints; q++) {
+      const float2 w = ldg2(w2 + t + T * q);
+      v[q] = make_float2(x[q].x * w.x, x[q].y * w.y);
+    }
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < kPoints; q++) {
+    const float2 w = ldg2(w2 + t + T * q);
+    float y[2] = {x[q].x, x[q].y};
+    const float ww[2] = {w.x, w.y};
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      if (p.ra9mb_a > 0.f) y[e] = y[e] / (p.ra9mb_a + y[e] * y[e]);
+      y[e] *= ww[e];
       if (p.limiter == 1) {
-        const float m = p.lim_scale * powf(fabsf(x), 0.1f);
-        x = (x > 0.f) ? m : -m;
+        const float m = p.lim_scale * powf(fabsf(y[e]), 0.1f);
+        y[e] = (y[e] > 0.f) ? m : -m;
       }
-      y[e] = x;
     }
     v[q] = make_float2(y[0], y[1]);
   }
 }
 
-template <int M, int P> struct MidPasses {
-  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw) {
+template <int M, int P, bool RT> struct MidPasses {
+  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr) {
     if constexpr (P < Plan<M>::NP - 1) {
       pass_load<M>(v, t, buf);
-      __syncthreads();                 // every thread has read before anyone overwrites
-      pass_store<M, P>(v, t, buf, tw);
+      if constexpr (RT) {
+        pass_compute_rt<M, P>(v, tr);
+        __syncthreads();               // every thread has read before anyone overwrites
+        pass_scatter<M, P>(v, t, buf);
+      } else {
+        __syncthreads();
+        pass_store<M, P>(v, t, buf, tw);
+      }
       __syncthreads();
-      MidPasses<M, P + 1>::run(v, t, buf, tw);
+      MidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr);
     }
   }
 };
 
-template <int M, bool MULTI>
+// MULTI: multitaper (K' tapers per frame, frame staged in shared memory by TMA one frame
+// ahead and re-read per taper).  PLAIN: no RA9MB / limiter code in the kernel.
+template <int M, bool MULTI, bool PLAIN>
 __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(const KParams p) {
-  constexpr int T = Geo<M>::T, G = Geo<M>::G;
-  extern __shared__ __align__(16) float2 smem[];
+  using GeoM = Geo<M>;
+  constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
+  constexpr bool STAGE = GeoM::STAGE && MULTI;
+  constexpr bool RT = GeoM::RT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int g = threadIdx.x / T;
   const int t = threadIdx.x % T;
-  float2 *buf = smem + (size_t) g * M;
+  unsigned char *gbase = smem_raw + (size_t) g * GeoM::group_bytes(MULTI);
+  float2 *buf = reinterpret_cast<float2 *>(gbase);
+  float *stage = reinterpret_cast<float *>(gbase + GeoM::BUF_BYTES);
+  float *red = reinterpret_cast<float *>(gbase + GeoM::BUF_BYTES + GeoM::stage_bytes(MULTI));
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + GeoM::BUF_BYTES + GeoM::stage_bytes(MULTI) + GeoM::RED_BYTES);
   const long long gid = (long long) blockIdx.x * G + g;
   const long long fb = gid * p.frames_per_group;
+  unsigned phase = 0;
+
+  TwRegs tr;
+  if constexpr (RT) load_tw_regs<M>(tr, t, p.tw, p.vtab);
+
+  if (STAGE) {
+    if (t == 0) {
+      mbar_init(mbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0 && fb < p.nframes && frame_bulk_ok(p, p.first_frame + fb, N)) {
+      const long long f0 = p.first_frame + fb;
+      mbar_expect_tx(mbar, N * 4);
+      tma_load_1d(stage, p.samples + (f0 * (long long) p.hop - p.n_ov - p.origin), N * 4, mbar);
+    }
+  }
 
   for (int it = 0; it < p.frames_per_group; ++it) {
     const long long fl = fb + it;
     const bool active = fl < p.nframes;
     const long long f = p.first_frame + fl;
+    const bool staged = STAGE && active && frame_bulk_ok(p, f, N);
+    const bool next_there = (it + 1 < p.frames_per_group) && (fl + 1 < p.nframes);
+    const bool next_staged = STAGE && next_there && frame_bulk_ok(p, f + 1, N);
+    if (staged) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    }
+    if (!STAGE && next_there) {
+      // pull the next frame's new hop block towards L2 while this frame is computed
+      const long long nb = (f + 1) * (long long) p.hop - p.origin;       // first new sample, buffer index
+      for (int i = t * 32; i < p.hop; i += T * 32)
+        if (nb + i >= 0 && nb + i < p.count) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.samples + nb + i));
+    }
     float acc[17];
     if (MULTI) {
 #pragma unroll
@@ -298,34 +458,73 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
     const int ntap = MULTI ? p.ntapers : 1;
     for (int j = 0; j < ntap; ++j) {
       float2 v[kPoints];
-      if (active) {
-        load_frame<M>(v, t, p, f, j);
-      } else {
+      {
+        float2 x[kPoints];
+        // Control flow around the warp shuffles / barriers of the mean removal depends only
+        // on j (uniform over the CTA), never on a group's own frame: groups of one warp or
+        // CTA can sit on different kinds of frames.
+        if (MULTI && STAGE && j > 0) {
+          // multitaper: tapers after the first read the cleaned copy kept in the staging buffer
+          const float2 *s2 = reinterpret_cast<const float2 *>(stage);
 #pragma unroll
-        for (int q = 0; q < kPoints; q++) v[q] = make_float2(0.f, 0.f);
-      }
-      pass_store<M, 0>(v, t, buf, p.tw);
-      __syncthreads();
-      MidPasses<M, 1>::run(v, t, buf, p.tw);
-      last_pass<M>(v, t, buf, p.tw);
-      if (MULTI) {
-        emit_bins<M>(v, t, p.vtab, [&](int slot, float2 a, bool) { acc[slot] += norm2(a); });
-      } else if (active) {
-        float *row = p.rows ? p.rows + fl * p.row_stride : nullptr;
-        float2 *sp = p.spectrum ? p.spectrum + fl * (long long) (M + 1) : nullptr;
-        const bool db = p.rows_db != 0;
-        const float ss = p.spec_scale;
-        emit_bins<M>(v, t, p.vtab, [&](int slot, float2 a, bool cj) {
-          const int bin = slot_bin<M>(t, slot);
-          if (row) {
-            float y = norm2(a);
-            if (db) y = 10.f * log10f(y);
-            row[bin] = y;
+          for (int q = 0; q < kPoints; q++) x[q] = s2[t + T * q];
+        } else {
+          if (active) {
+            load_raw<M>(x, t, p, f, stage, staged);
+          } else {
+#pragma unroll
+            for (int q = 0; q < kPoints; q++) x[q] = make_float2(0.f, 0.f);
           }
-          if (sp) sp[bin] = make_float2(a.x * ss, cj ? -a.y * ss : a.y * ss);
-        });
+          if (p.fused_mean) remove_block_means_qs<M>(x, t, red, p);
+          else if (p.means != nullptr && active) remove_table_means<M>(x, t, p, f);
+          if (MULTI && STAGE && ntap > 1) {
+            float2 *s2 = reinterpret_cast<float2 *>(stage);
+#pragma unroll
+            for (int q = 0; q < kPoints; q++) s2[t + T * q] = x[q];     // own elements only: no hazard
+          }
+        }
+        apply_taper<M, PLAIN>(v, x, t, p, p.tapers + (size_t) j * N);
       }
-      __syncthreads();                 // buffer is reused by the next taper / frame
+      if constexpr (RT) {
+        pass_compute_rt<M, 0>(v, tr);
+        __syncthreads();               // (A) the previous transform's last pass has been read by all
+        pass_scatter<M, 0>(v, t, buf);
+      } else {
+        __syncthreads();
+        pass_store<M, 0>(v, t, buf, p.tw);
+      }
+      if (STAGE && next_staged && j == ntap - 1 && t == 0) {
+        // past barrier (A) everyone is done reading the staging buffer: fetch the next frame
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, N * 4);
+        tma_load_1d(stage, p.samples + ((f + 1) * (long long) p.hop - p.n_ov - p.origin), N * 4, mbar);
+      }
+      __syncthreads();
+      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr);
+      auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
+      float *row = (!MULTI && active && p.rows) ? p.rows + fl * p.row_stride : nullptr;
+      float2 *sp = (!MULTI && active && p.spectrum) ? p.spectrum + fl * (long long) (M + 1) : nullptr;
+      const bool db = p.rows_db != 0;
+      const float ss = p.spec_scale;
+      auto sink_single = [&](int slot, float2 a, bool cj) {
+        const int bin = slot_bin<M>(t, slot);
+        if (row) {
+          float y = norm2(a);
+          if (db) y = 10.f * log10f(y);
+          row[bin] = y;
+        }
+        if (sp) sp[bin] = make_float2(a.x * ss, cj ? -a.y * ss : a.y * ss);
+      };
+      if constexpr (RT) {
+        last_pass_rt<M>(v, t, buf, p.tw, tr);
+        if (MULTI) emit_bins_rt<M>(v, t, p.vtab, tr, sink_multi);
+        else emit_bins_rt<M>(v, t, p.vtab, tr, sink_single);
+      } else {
+        last_pass<M>(v, t, buf, p.tw);
+        if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
+        else emit_bins<M>(v, t, p.vtab, sink_single);
+      }
+      // no barrier here: (A) of the next transform orders these reads before its stores
     }
     if (MULTI && active && p.rows) {
       float *row = p.rows + fl * p.row_stride;
@@ -348,13 +547,17 @@ static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  auto kern = multi ? gram_kernel<M, true> : gram_kernel<M, false>;
+  const bool plain = multi || (kp.ra9mb_a <= 0.f && kp.limiter == 0);
+  const int variant = multi ? 2 : (plain ? 1 : 0);
+  auto kern = multi ? gram_kernel<M, true, true> : (plain ? gram_kernel<M, false, true> : gram_kernel<M, false, false>);
+  // the staging buffer is only carved out for the multitaper variant
+  const size_t smem = GeoM::smem_bytes(multi);
   // per (device, variant): opt in to the dynamic shared memory once, cache the occupancy
-  static thread_local int occ_cache[2][64];
-  int &occ = occ_cache[multi ? 1 : 0][dev & 63];
+  static thread_local int occ_cache[3][64];
+  int &occ = occ_cache[variant][dev & 63];
   if (occ == 0) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GeoM::SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GeoM::THREADS, GeoM::SMEM));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GeoM::THREADS, smem));
     if (occ < 1) occ = 1;
   }
   // resident grid: every CTA slot of the chip holds G frame groups, each walking a
@@ -366,10 +569,35 @@ static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
   k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
   long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
   int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
-  kern<<<ctas, GeoM::THREADS, GeoM::SMEM, st>>>(k);
+  // regular geometry for the fused block means: hop = 2T << qs, n_ov a multiple of hop
+  k.fused_mean = 0;
+  k.qs = 0;
+  if (kp.fused_mean) {
+    const int unit = 2 * GeoM::T;
+    int qs = -1;
+    for (int s2 = 0; s2 <= 4; s2++)
+      if (kp.hop == (unit << s2)) qs = s2;
+    if (qs >= 0 && (k.n_ov % kp.hop) == 0) {
+      k.fused_mean = 1;
+      k.qs = qs;
+    } else {
+      glb_set_error("glb_launch_gram: fused block means need hop = (N/16) << s, s = 0..4");
+      return GLB_EINVAL;
+    }
+  }
+  kern<<<ctas, GeoM::THREADS, smem, st>>>(k);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;
+}
+
+extern "C" int glb_gram_fused_mean_ok(int n, int hop) {
+  if (!glb_fft_supported(n) || hop < 1 || hop > n) return 0;
+  const int unit = n / 16;            // 2T
+  if ((n - hop) % hop != 0) return 0;
+  for (int s = 0; s <= 4; s++)
+    if (hop == (unit << s)) return 1;
+  return 0;
 }
 
 extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
@@ -392,10 +620,12 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   k.ntapers = a->ntapers;
   k.means = a->block_means;
   k.means_first_block = a->means_first_block;
+  k.fused_mean = a->fused_mean;
   k.hop = a->hop;
   k.n_ov = a->n - a->hop;
   k.cblk = (k.n_ov + a->hop - 1) / a->hop;
   k.inv_hop = (float) (1.0 / (double) a->hop);
+  k.inv_hop_mean = (float) (1.0 / (double) a->hop);
   k.ra9mb_a = a->ra9mb_a;
   k.limiter = a->limiter;
   k.lim_scale = (float) pow((double) a->taper_scale, 0.9);
@@ -411,6 +641,10 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   const bool multi = a->ntapers > 1;
   if (multi && a->spectrum) {
     glb_set_error("glb_launch_gram: spectrum output is only defined for one taper");
+    return GLB_EINVAL;
+  }
+  if (a->fused_mean && a->block_means) {
+    glb_set_error("glb_launch_gram: fused_mean and block_means are exclusive");
     return GLB_EINVAL;
   }
   cudaStream_t st = (cudaStream_t) stream;

@@ -307,7 +307,9 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
 
   const float *d_means = NULL;
   long long means_first = 0;
-  if (c->sub_mean) {
+  const int fused_mean = c->sub_mean && glb_gram_fused_mean_ok(c->n, p->hop);
+  if (c->sub_mean && !fused_mean) {
+    /* irregular hop: block means from a pre-pass over the staged samples */
     const long long b_lo = lo / p->hop, b_hi = first + nframes;      /* blocks [b_lo, b_hi) */
     TRY(ensure((void **) &s->d_means, &s->means_cap, (size_t) (b_hi - b_lo), sizeof(float)));
     TRY(glb_launch_block_means(s->d_samples, s->s_origin, s->s_count, p->hop, b_lo, b_hi - b_lo, s->d_means, s->stream));
@@ -325,6 +327,7 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   g.ntapers = p->ntapers;
   g.block_means = d_means;
   g.means_first_block = means_first;
+  g.fused_mean = fused_mean;
   /* RA9MB and the limiter never reach the spectrum in multitaper mode: mtm_do rebuilds
      inbuf_fft from inbuf_audio (mtm.c:190-192) */
   g.ra9mb_a = (c->mode == GLFER_MODE_FFT) ? c->a : 0.0f;

@@ -65,6 +65,7 @@ typedef struct {
   int ntapers;                 /* 1 = periodogram, K' = kmax+1 for multitaper */
   const float *block_means;    /* device: mean of hop block b at [b - means_first_block], or NULL */
   long long means_first_block;
+  int fused_mean;              /* 1: block means computed inside the kernel (needs glb_gram_fused_mean_ok) */
   float ra9mb_a;               /* > 0: x / (a + x^2) before the taper (fft.c:127-136) */
   int limiter;                 /* 1: sign(v) |v|^0.1 after the taper (fft.c:151-156) */
   float taper_scale;           /* the scale folded into tapers (needed by limiter / spectrum output) */
@@ -79,6 +80,10 @@ typedef struct {
 } glb_gram_args;
 
 int glb_launch_gram(const glb_gram_args *a, void *stream);
+/* the in-kernel block-mean removal covers hop = (n/16) << s, s = 0..4, with (n - hop) a
+ * multiple of hop (0 %, 50 %, 75 %, 87.5 %, 93.75 % overlap); other geometries use
+ * glb_launch_block_means + block_means */
+int glb_gram_fused_mean_ok(int n, int hop);
 
 /* mean of every complete hop block: means[b - first_block] = mean(stream[b*hop, (b+1)*hop)) */
 int glb_launch_block_means(const float *samples, long long origin, long long count, int hop,

@@ -93,7 +93,9 @@ def test_fft_core_emulation(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     rows = [l.split() for l in res.stdout.strip().splitlines()]
-    assert [int(r[0]) for r in rows] == [16, 32, 64, 128, 256, 512, 1024, 2048]
+    # table-twiddle variant for every plan up to M=2048, then the register-twiddle variant
+    assert [int(r[0]) for r in rows if r[4] == "table"] == [16, 32, 64, 128, 256, 512, 1024, 2048]
+    assert [int(r[0]) for r in rows if r[4] == "rt"] == [16, 64, 128, 256, 512, 1024, 2048]
     assert all(int(r[3]) == 0 and float(r[2]) < 1e-6 for r in rows)
 
 
