@@ -125,6 +125,8 @@ def lib() -> C.CDLL:
         l.glb_window_table.restype = None
         l.glb_dpss.argtypes = [C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         l.glb_hop.argtypes = [C.c_int, C.c_float]
+        l.glb_force_generic_kernel.argtypes = [C.c_int]
+        l.glb_force_generic_kernel.restype = None
         _lib = l
     return _lib
 
@@ -329,6 +331,11 @@ def host_dpss(n: int, nw: float, kmax: int):
     if rc != 0:
         raise GlferError("glb_dpss failed")
     return t, lam
+
+
+def force_generic_kernel(on: bool) -> None:
+    """testing aid: run the general kernel where the TMA ring kernel would be chosen"""
+    lib().glb_force_generic_kernel(int(on))
 
 
 def host_hop(n: int, overlap: float) -> int:

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <atomic>
 #include <vector>
 #include <algorithm>
@@ -31,10 +32,12 @@ using namespace glb;
 // ------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
+static int g_force_generic = 0;     // tests: run the general kernel where the ring kernel would be chosen
 
 extern "C" const char *glb_last_error(void) { return g_err; }
 extern "C" void glb_set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
 extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load(); }
+extern "C" void glb_force_generic_kernel(int on) { g_force_generic = on; }
 
 #define CU(call)                                                                              \
   do {                                                                                        \
@@ -541,6 +544,226 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
   }
 }
 
+// ------------------------------------------------------------------------- ring kernel
+// The fast path for the regular geometry (hop = 2T << QS, N - hop a multiple of hop: 0, 50,
+// 75, 87.5, 93.75 % overlap; no RA9MB / limiter).  A frame is NB = 16 >> QS whole hop blocks.
+// Each frame group keeps the last NB + 1 blocks of its run in a shared-memory ring that is
+// filled by TMA bulk copies (cp.async.bulk + mbarrier), always one block ahead of the FFT,
+// so every sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM
+// latency hides behind the previous frame's transform.  Block means (sub_mean) are computed
+// once per block when it lands and kept beside the ring.
+struct RingLayout {
+  int slots;            // NB + 1
+  size_t ring_off, red_off, mu_off, mbar_off, group_bytes;
+};
+
+template <int M>
+__host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
+  RingLayout L;
+  L.slots = nb + 1;
+  L.ring_off = Geo<M>::BUF_BYTES;
+  L.red_off = L.ring_off + (size_t) L.slots * hop * sizeof(float);
+  L.mu_off = L.red_off + (size_t) 18 * Geo<M>::NW * sizeof(float);
+  L.mbar_off = ((L.mu_off + 18 * sizeof(float) + 7) / 8) * 8;
+  L.group_bytes = ((L.mbar_off + 18 * sizeof(unsigned long long) + 15) / 16) * 16;
+  return L;
+}
+
+// mean of one ring block: every thread sums its (1 << qs) float2 entries, warps reduce by
+// shuffle, the group combines through `red` (one barrier).  The summation tree of a block is
+// the same wherever the block sits in a frame: its mean is bit-identical in every frame, group
+// and time shard.  Must be called by all threads of the CTA (contains a block barrier).
+template <int M>
+__device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
+  constexpr int T = M / kPoints, NW = (T + 31) / 32, W = T < 32 ? T : 32;
+  const float2 *b2 = reinterpret_cast<const float2 *>(blk);
+  float s = 0.f;
+  for (int i = 0; i < (1 << qs); i++) {
+    const float2 a = b2[t + T * i];
+    s += a.x + a.y;
+  }
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (NW > 1) {
+    if ((t & 31) == 0) red[t >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; w++) s += red[w];
+  }
+  return s * inv_hop;
+}
+
+template <int M, int QS>
+__device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const float *ring, int hop, int slot_oldest,
+                                          int slots, const float *mu, float mu_new, bool sub) {
+  constexpr int T = M / kPoints, NB = kPoints >> QS;
+  int sidx = slot_oldest;
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const float2 *bp = reinterpret_cast<const float2 *>(ring + (size_t) sidx * hop);
+    const float m = sub ? ((b == NB - 1) ? mu_new : mu[sidx]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < (1 << QS); i++) {
+      const float2 a = bp[t + T * i];
+      x[(b << QS) + i] = make_float2(a.x - m, a.y - m);
+    }
+    sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
+  }
+}
+
+template <int M, bool MULTI>
+__global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kernel(const KParams p) {
+  using GeoM = Geo<M>;
+  constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
+  constexpr bool RT = GeoM::RT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int g = threadIdx.x / T;
+  const int t = threadIdx.x % T;
+  const int hop = p.hop, qs = p.qs, nb = kPoints >> qs;          // nb blocks per frame
+  const RingLayout L = ring_layout<M>(hop, nb);
+  const int slots = L.slots;
+  unsigned char *gbase = smem_raw + (size_t) g * L.group_bytes;
+  float2 *buf = reinterpret_cast<float2 *>(gbase);
+  float *ring = reinterpret_cast<float *>(gbase + L.ring_off);
+  float *red = reinterpret_cast<float *>(gbase + L.red_off);
+  float *mu = reinterpret_cast<float *>(gbase + L.mu_off);
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + L.mbar_off);
+  const long long gid = (long long) blockIdx.x * G + g;
+  const long long fb = gid * p.frames_per_group;
+  const bool group_active = fb < p.nframes;
+  const long long f_first = p.first_frame + fb;
+  const long long b0 = f_first - (nb - 1);                       // oldest block of the first frame
+  const bool sub = p.fused_mean != 0;
+  const unsigned blk_bytes = (unsigned) hop * 4u;
+  unsigned phase_bits = 0;                                       // one parity bit per ring slot
+
+  TwRegs tr;
+  if constexpr (RT) load_tw_regs<M>(tr, t, p.tw, p.vtab);
+
+  if (t == 0) {
+    for (int sl = 0; sl < slots; sl++) mbar_init(&mbar[sl], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // prologue: the nb blocks of the first frame (zeros before the stream start, fft.c:103-108)
+  for (int lb = 0; lb < nb; lb++) {
+    const long long blk = b0 + lb;
+    if (group_active) {
+      if (blk < 0) {
+        float2 *z = reinterpret_cast<float2 *>(ring + (size_t) lb * hop);
+        for (int i = 0; i < (1 << qs); i++) z[t + T * i] = make_float2(0.f, 0.f);
+      } else if (t == 0) {
+        mbar_expect_tx(&mbar[lb], blk_bytes);
+        tma_load_1d(ring + (size_t) lb * hop, p.samples + (blk * hop - p.origin), blk_bytes, &mbar[lb]);
+      }
+    }
+  }
+  float mu_new = 0.f;
+  for (int lb = 0; lb < nb; lb++) {
+    const long long blk = b0 + lb;
+    if (group_active && blk >= 0) {
+      mbar_wait(&mbar[lb], 0);
+      phase_bits ^= 1u << lb;
+    }
+    if (sub) {
+      __syncthreads();                                           // zero fill visible to all (uniform: groups differ in blk)
+      const float m = ring_block_mean<M>(ring + (size_t) lb * hop, qs, t, red + lb * GeoM::NW, p.inv_hop_mean);
+      mu_new = (blk < 0) ? 0.f : m;
+      if (t == 0) mu[lb] = mu_new;
+    }
+  }
+  __syncthreads();                                               // zero fill and mu[] visible
+
+  int slot_new = nb - 1;                                         // slot of the newest block of frame `it`
+  for (int it = 0; it < p.frames_per_group; ++it) {
+    const long long fl = fb + it;
+    const bool active = fl < p.nframes;
+    const long long f = p.first_frame + fl;
+    const bool next_there = (it + 1 < p.frames_per_group) && (fl + 1 < p.nframes);
+    const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
+    if (it > 0) {
+      // block f was requested one frame ago
+      if (active) {
+        mbar_wait(&mbar[slot_new], (phase_bits >> slot_new) & 1u);
+        phase_bits ^= 1u << slot_new;
+      }
+      if (sub) {
+        mu_new = ring_block_mean<M>(ring + (size_t) slot_new * hop, qs, t, red + slot_new * GeoM::NW, p.inv_hop_mean);
+        if (t == 0) mu[slot_new] = mu_new;
+      }
+    }
+    if (next_there && t == 0) {
+      // slot_next held block f - nb: its last readers passed a block barrier in frame f - 1
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&mbar[slot_next], blk_bytes);
+      tma_load_1d(ring + (size_t) slot_next * hop, p.samples + ((f + 1) * (long long) hop - p.origin), blk_bytes, &mbar[slot_next]);
+    }
+    const int slot_oldest = (slot_next + 1 == slots) ? 0 : slot_next + 1;     // = slot of block f - nb + 1
+    float acc[17];
+    if (MULTI) {
+#pragma unroll
+      for (int i = 0; i < 17; i++) acc[i] = 0.f;
+    }
+    const int ntap = MULTI ? p.ntapers : 1;
+    for (int j = 0; j < ntap; ++j) {
+      float2 v[kPoints];
+      {
+        float2 x[kPoints];
+        switch (qs) {
+          case 4: ring_load<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
+          case 3: ring_load<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
+          case 2: ring_load<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
+          case 1: ring_load<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
+          default: ring_load<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
+        }
+        apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
+      }
+      if constexpr (RT) {
+        pass_compute_rt<M, 0>(v, tr);
+        __syncthreads();               // (A) the previous transform's last pass has been read by all
+        pass_scatter<M, 0>(v, t, buf);
+      } else {
+        __syncthreads();
+        pass_store<M, 0>(v, t, buf, p.tw);
+      }
+      __syncthreads();
+      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr);
+      float *row = p.rows + fl * p.row_stride;
+      const bool db = p.rows_db != 0;
+      auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
+      auto sink_single = [&](int slot, float2 a, bool) {
+        float y = norm2(a);
+        if (db) y = 10.f * log10f(y);
+        if (active) row[slot_bin<M>(t, slot)] = y;
+      };
+      if constexpr (RT) {
+        last_pass_rt<M>(v, t, buf, p.tw, tr);
+        if (MULTI) emit_bins_rt<M>(v, t, p.vtab, tr, sink_multi);
+        else emit_bins_rt<M>(v, t, p.vtab, tr, sink_single);
+      } else {
+        last_pass<M>(v, t, buf, p.tw);
+        if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
+        else emit_bins<M>(v, t, p.vtab, sink_single);
+      }
+    }
+    if (MULTI && active) {
+      float *row = p.rows + fl * p.row_stride;
+      const bool db = p.rows_db != 0;
+#pragma unroll
+      for (int slot = 0; slot < 17; slot++) {
+        if (slot < 16 || t == 0) {
+          float y = acc[slot];
+          if (db) y = 10.f * log10f(y);
+          row[slot_bin<M>(t, slot)] = y;
+        }
+      }
+    }
+    slot_new = slot_next;
+  }
+}
+
 template <int M>
 static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
   using GeoM = Geo<M>;
@@ -548,6 +771,48 @@ static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const bool plain = multi || (kp.ra9mb_a <= 0.f && kp.limiter == 0);
+  // ---- fast path: regular geometry, rows only, 16-byte aligned blocks -> TMA ring kernel
+  {
+    const int unit = 2 * GeoM::T;
+    int qs = -1;
+    for (int s2 = 0; s2 <= 4; s2++)
+      if (kp.hop == (unit << s2)) qs = s2;
+    const bool regular = qs >= 0 && (kp.n_ov % kp.hop) == 0 && (kp.hop % 4) == 0 && (kp.origin % 4) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0);
+    if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && !g_force_generic) {
+      const int nb = kPoints >> qs;
+      const RingLayout L = ring_layout<M>(kp.hop, nb);
+      const size_t smem = (size_t) GeoM::G * L.group_bytes;
+      if (smem <= 227 * 1024) {
+        auto rk = multi ? gram_ring_kernel<M, true> : gram_ring_kernel<M, false>;
+        static thread_local int occ_ring[2][5][64];
+        int &occ = occ_ring[multi ? 1 : 0][qs][dev & 63];
+        if (occ == 0) {
+          // opt in to the device maximum once: the ring size (hence the launch's smem) varies with the overlap
+          CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk, GeoM::THREADS, smem));
+          if (occ < 1) occ = -1;
+        }
+        // big frames: the ring must not cost more residency than it saves in traffic
+        int occ_generic_bound = (int) ((227 * 1024) / GeoM::smem_bytes(false));
+        const bool worth = occ >= 2 || (occ >= 1 && occ_generic_bound <= 1) || GeoM::THREADS >= 1024;
+        if (occ >= 1 && worth) {
+          long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
+          if (groups > kp.nframes) groups = kp.nframes;
+          if (groups < 1) groups = 1;
+          KParams k = kp;
+          k.qs = qs;
+          k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
+          long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
+          int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
+          rk<<<ctas, GeoM::THREADS, smem, st>>>(k);
+          CU(cudaGetLastError());
+          g_launches++;
+          return GLB_OK;
+        }
+      }
+    }
+  }
   const int variant = multi ? 2 : (plain ? 1 : 0);
   auto kern = multi ? gram_kernel<M, true, true> : (plain ? gram_kernel<M, false, true> : gram_kernel<M, false, false>);
   // the staging buffer is only carved out for the multitaper variant
@@ -556,7 +821,7 @@ static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
   static thread_local int occ_cache[3][64];
   int &occ = occ_cache[variant][dev & 63];
   if (occ == 0) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GeoM::THREADS, smem));
     if (occ < 1) occ = 1;
   }

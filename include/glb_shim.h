@@ -84,6 +84,9 @@ int glb_launch_gram(const glb_gram_args *a, void *stream);
  * multiple of hop (0 %, 50 %, 75 %, 87.5 %, 93.75 % overlap); other geometries use
  * glb_launch_block_means + block_means */
 int glb_gram_fused_mean_ok(int n, int hop);
+/* testing aid: 1 = always use the general kernel (the TMA ring kernel is chosen automatically
+ * for the regular geometries) */
+void glb_force_generic_kernel(int on);
 
 /* mean of every complete hop block: means[b - first_block] = mean(stream[b*hop, (b+1)*hop)) */
 int glb_launch_block_means(const float *samples, long long origin, long long count, int hop,

@@ -103,6 +103,26 @@ def test_every_fft_size(gpu_api, n):
         assert_psd_close(got, ref, f"N={n} w={wt} ov={ov}")
 
 
+def test_general_kernel_on_regular_geometries(gpu_api):
+    """the regular geometries normally run the TMA ring kernel; the general kernel must give
+    the same rows (fused block means, table twiddles for large N)"""
+    x = stream(120000, seed=4)
+    try:
+        for kw in (dict(n=4096, window_type=0, overlap=0.5, sub_mean=True), dict(n=1024, window_type=7, overlap=0.75, sub_mean=True),
+                   dict(n=16384, window_type=0, overlap=0.5, sub_mean=False),
+                   dict(n=2048, mode=1, overlap=0.5, sub_mean=True, mtm_kmax=3, mtm_w=2.5)):
+            gpu_api.force_generic_kernel(False)
+            a = gpu_api.GramPlan(**kw).run(x)["psd"]
+            gpu_api.force_generic_kernel(True)
+            b = gpu_api.GramPlan(**kw).run(x)["psd"]
+            ref = O.multitaper(x, kw["n"], kw["overlap"], kw["mtm_w"], kw["mtm_kmax"], True) if kw.get("mode") else \
+                O.periodogram(x, kw["n"], kw["window_type"], kw["overlap"], kw["sub_mean"])
+            assert_psd_close(a, ref, f"ring {kw}")
+            assert_psd_close(b, ref, f"general {kw}")
+    finally:
+        gpu_api.force_generic_kernel(False)
+
+
 @pytest.mark.parametrize("ov", [0.0, 0.25, 0.3, 0.5, 0.75, 0.9, 0.97])
 def test_overlaps_including_odd_hops(gpu_api, ov):
     x = stream(60000, seed=3)
