@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         l.glb_hop.argtypes = [C.c_int, C.c_float]
         l.glb_force_generic_kernel.argtypes = [C.c_int]
         l.glb_force_generic_kernel.restype = None
+        l.glb_set_kernel_preference.argtypes = [C.c_int]
+        l.glb_set_kernel_preference.restype = None
         _lib = l
     return _lib
 
@@ -336,6 +338,11 @@ def host_dpss(n: int, nw: float, kmax: int):
 def force_generic_kernel(on: bool) -> None:
     """testing aid: run the general kernel where the TMA ring kernel would be chosen"""
     lib().glb_force_generic_kernel(int(on))
+
+
+def set_kernel_preference(pref: int) -> None:
+    """0 automatic, 1 general kernel, 2 TMA ring kernel, 3 warp-per-frame kernel"""
+    lib().glb_set_kernel_preference(pref)
 
 
 def host_hop(n: int, overlap: float) -> int:

@@ -24,6 +24,7 @@
 #include <algorithm>
 
 #include "fft_core.cuh"
+#include "fft_wpf.cuh"
 #include "tables.hpp"
 #include "../../include/glb_shim.h"
 
@@ -108,6 +109,7 @@ struct GramTables {
   int n;
   float2 *tw;
   float2 *vtab;
+  float2 *roots;     // exp(-2 pi i k / M), k < M (warp-per-frame kernel)
 };
 
 template <int M> static std::vector<float2> tw_for() { return build_twiddles<M>(); }
@@ -145,6 +147,10 @@ extern "C" int glb_tables_create(int n, void **out) {
   t->n = n;
   t->tw = nullptr;
   t->vtab = nullptr;
+  t->roots = nullptr;
+  std::vector<float2> rt = build_roots(n / 2);
+  CU(cudaMalloc(&t->roots, rt.size() * sizeof(float2)));
+  CU(cudaMemcpy(t->roots, rt.data(), rt.size() * sizeof(float2), cudaMemcpyHostToDevice));
   CU(cudaMalloc(&t->tw, tw.size() * sizeof(float2)));
   CU(cudaMalloc(&t->vtab, vt.size() * sizeof(float2)));
   CU(cudaMemcpy(t->tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
@@ -158,6 +164,7 @@ extern "C" int glb_tables_destroy(void *tp) {
   if (!t) return GLB_OK;
   cudaFree(t->tw);
   cudaFree(t->vtab);
+  cudaFree(t->roots);
   delete t;
   return GLB_OK;
 }
@@ -185,7 +192,7 @@ struct KParams {
   long long row_stride;
   int rows_db;
   float2 *spectrum;
-  const float2 *tw, *vtab;
+  const float2 *tw, *vtab, *roots;
 };
 
 #ifndef GLB_REG_TARGET
@@ -764,13 +771,178 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
   }
 }
 
+// ------------------------------------------------------------------------- warp-per-frame kernel
+// Periodogram fast path for N = 512..4096: a frame never leaves its warp (fft_wpf.cuh), so the
+// kernel has no block barrier at all.  Warps walk contiguous runs of INTERIOR frames (no zero
+// history, fully inside the staged samples, 8-byte aligned); the few edge frames of a
+// recording are launched through the general kernel by the host code below.
+#ifndef GLB_WPF_MINB
+#define GLB_WPF_MINB 5
+#endif
+constexpr int kWpfWarps = 2;          // warps per CTA (independent of each other)
+
+// block-mean removal inside one lane group: hop = 2T << QW; block b = registers q with (q >> QW) == b
+template <int M, int QW>
+__device__ __forceinline__ void wpf_remove_means(float2 (&x)[kWP], float inv_hop) {
+  constexpr int T = Wpf<M>::T, NB = kWP >> QW;
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = b << QW; q < (b + 1) << QW; q++) s += x[q].x + x[q].y;
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float m = s * inv_hop;
+#pragma unroll
+    for (int q = b << QW; q < (b + 1) << QW; q++) {
+      x[q].x -= m;
+      x[q].y -= m;
+    }
+  }
+}
+
 template <int M>
-static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
+__global__ void __launch_bounds__(32 * kWpfWarps, GLB_WPF_MINB) gram_wpf_kernel(const KParams p) {
+  constexpr int T = Wpf<M>::T, N = 2 * M, FPW = 32 / T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / T, t = lane % T;
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw) + (size_t) (warp * FPW + g) * (Wpf<M>::TILE + 2);
+  const long long gid = ((long long) blockIdx.x * kWpfWarps + warp) * FPW + g;
+  const long long fb = gid * p.frames_per_group;
+
+  WpfRegs rg;
+  wpf_load_regs<M>(rg, t, p.roots, p.vtab);
+  const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers) + t;
+  const bool db = p.rows_db != 0;
+
+  for (int it = 0; it < p.frames_per_group; ++it) {
+    const long long fl = fb + it;
+    const bool active = fl < p.nframes;
+    // inactive tail iterations recompute the group's last frame without storing (keeps the
+    // warp converged for the shuffles and __syncwarp below)
+    const long long fe = active ? fl : (p.nframes - 1);
+    const long long f = p.first_frame + fe;
+    const float2 *src = reinterpret_cast<const float2 *>(p.samples + (f * (long long) p.hop - p.n_ov - p.origin)) + t;
+    float2 v[kWP];
+#pragma unroll
+    for (int q = 0; q < kWP; q++) v[q] = ldg2(src + T * q);
+    if (fl + 1 < p.nframes && it + 1 < p.frames_per_group) {
+      // pull the next frame's new hop block towards L2 behind this frame's arithmetic
+      const float *nx = p.samples + ((f + 1) * (long long) p.hop - p.origin);
+      for (int i = t * 32; i < p.hop; i += T * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+    }
+    if (p.fused_mean) {
+      switch (p.qs) {
+        case 6: wpf_remove_means<M, 6>(v, p.inv_hop_mean); break;
+        case 5: wpf_remove_means<M, 5>(v, p.inv_hop_mean); break;
+        case 4: wpf_remove_means<M, 4>(v, p.inv_hop_mean); break;
+        case 3: wpf_remove_means<M, 3>(v, p.inv_hop_mean); break;
+        default: wpf_remove_means<M, 2>(v, p.inv_hop_mean); break;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kWP; q++) {
+      const float2 w = ldg2(w2 + T * q);
+      v[q].x *= w.x;
+      v[q].y *= w.y;
+    }
+    wpf_pass_a<M>(v);
+    __syncwarp();                      // the previous frame's gathers are done
+    wpf_scatter<M>(v, t, tile);
+    __syncwarp();
+    wpf_gather<M>(v, t, tile);
+    wpf_pass_b<M>(v, t, rg);
+    float *row = p.rows + fe * p.row_stride;
+    wpf_emit<M>(v, t, rg, [&](int, int bin, float2 a, bool) {
+      float y = norm2(a);
+      if (db) y = 10.f * log10f(y);
+      if (active) row[bin] = y;
+    });
+  }
+}
+
+template <int M>
+static int launch_wpf(const KParams &kp, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  constexpr int FPW = 32 / Wpf<M>::T;
+  const size_t smem = (size_t) kWpfWarps * FPW * (Wpf<M>::TILE + 2) * sizeof(float2);
+  static thread_local int occ_cache[64];
+  int &occ = occ_cache[dev & 63];
+  if (occ == 0) {
+    CU(cudaFuncSetAttribute(gram_wpf_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gram_wpf_kernel<M>, 32 * kWpfWarps, smem));
+    if (occ < 1) occ = 1;
+  }
+  long long groups = (long long) sms * occ * kWpfWarps * FPW;
+  if (groups > kp.nframes) groups = kp.nframes;
+  if (groups < 1) groups = 1;
+  KParams k = kp;
+  k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
+  const long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
+  const int ctas = (int) ((used + kWpfWarps * FPW - 1) / (kWpfWarps * FPW));
+  gram_wpf_kernel<M><<<ctas, 32 * kWpfWarps, smem, st>>>(k);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+// which kernel family serves a launch (tests / experiments can pin one)
+static int g_kernel_pref = 0;        // 0 auto, 1 general, 2 ring, 3 warp-per-frame
+extern "C" void glb_set_kernel_preference(int pref) { g_kernel_pref = pref; }
+
+template <int M>
+static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st, int allow) {
   using GeoM = Geo<M>;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const bool plain = multi || (kp.ra9mb_a <= 0.f && kp.limiter == 0);
+  // ---- fastest path (N <= 4096 periodograms): warp-per-frame kernel on the interior frames
+  if constexpr (M >= 256 && M <= 2048) {
+    constexpr int unitw = 2 * Wpf<M>::T;
+    int qw = -1;
+    for (int s2 = 2; s2 <= 6; s2++)
+      if (kp.hop == (unitw << s2)) qw = s2;
+    const bool mean_ok = !kp.fused_mean || (qw >= 0 && (kp.n_ov % kp.hop) == 0);
+    const bool pref_ok = (allow & 4) != 0;
+    if (pref_ok && !multi && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && mean_ok &&
+        (kp.hop % 2) == 0 && ((kp.n_ov + kp.origin) % 2) == 0 && ((reinterpret_cast<uintptr_t>(kp.samples) & 7) == 0)) {
+      // interior frames: f*hop - n_ov >= max(origin, 0) and the frame ends inside the staged samples
+      const long long lo_s = kp.origin > 0 ? kp.origin : 0;
+      long long f_lo = (lo_s + kp.n_ov + kp.hop - 1) / kp.hop;
+      long long f_hi = (kp.origin + kp.count - kp.hop) / kp.hop + 1;       // exclusive: (f+1)*hop <= origin+count
+      if (f_lo < kp.first_frame) f_lo = kp.first_frame;
+      if (f_hi > kp.first_frame + kp.nframes) f_hi = kp.first_frame + kp.nframes;
+      if (f_hi > f_lo) {
+        KParams kw = kp;
+        kw.qs = qw;
+        kw.first_frame = f_lo;
+        kw.nframes = f_hi - f_lo;
+        kw.rows = kp.rows + (f_lo - kp.first_frame) * kp.row_stride;
+        int rc = launch_wpf<M>(kw, st);
+        if (rc != GLB_OK) return rc;
+        // edge frames before / after the interior run go through the kernels below
+        KParams ke = kp;
+        if (f_lo > kp.first_frame) {
+          ke.nframes = f_lo - kp.first_frame;
+          rc = launch_gram_m<M>(ke, multi, groups_hint, st, 1);
+          if (rc != GLB_OK) return rc;
+        }
+        if (f_hi < kp.first_frame + kp.nframes) {
+          ke = kp;
+          ke.first_frame = f_hi;
+          ke.nframes = kp.first_frame + kp.nframes - f_hi;
+          ke.rows = kp.rows + (f_hi - kp.first_frame) * kp.row_stride;
+          rc = launch_gram_m<M>(ke, multi, groups_hint, st, 1);
+          if (rc != GLB_OK) return rc;
+        }
+        return GLB_OK;
+      }
+    }
+  }
   // ---- fast path: regular geometry, rows only, 16-byte aligned blocks -> TMA ring kernel
   {
     const int unit = 2 * GeoM::T;
@@ -779,7 +951,7 @@ static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
       if (kp.hop == (unit << s2)) qs = s2;
     const bool regular = qs >= 0 && (kp.n_ov % kp.hop) == 0 && (kp.hop % 4) == 0 && (kp.origin % 4) == 0 &&
                          ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0);
-    if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && !g_force_generic) {
+    if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && (allow & 2) != 0) {
       const int nb = kPoints >> qs;
       const RingLayout L = ring_layout<M>(kp.hop, nb);
       const size_t smem = (size_t) GeoM::G * L.group_bytes;
@@ -903,6 +1075,7 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   k.spectrum = (float2 *) a->spectrum;
   k.tw = tb->tw;
   k.vtab = tb->vtab;
+  k.roots = tb->roots;
   const bool multi = a->ntapers > 1;
   if (multi && a->spectrum) {
     glb_set_error("glb_launch_gram: spectrum output is only defined for one taper");
@@ -913,18 +1086,25 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
     return GLB_EINVAL;
   }
   cudaStream_t st = (cudaStream_t) stream;
+  // kernel families this launch may use: 1 general, 2 TMA ring, 4 warp-per-frame
+  // (automatic = ring then general: measured on B200 the ring kernel is the fastest family at
+  // N = 4096, 0.726 ms vs 0.746 ms for warp-per-frame, whose 67 KB of straight-line code per
+  // frame stalls on instruction fetch; warp-per-frame stays selectable for experiments)
+  int allow = 3;
+  if (g_force_generic || g_kernel_pref == 1) allow = 1;
+  else if (g_kernel_pref == 3) allow = 7;
   switch (a->n / 2) {
-    case 16: return launch_gram_m<16>(k, multi, a->groups_hint, st);
-    case 32: return launch_gram_m<32>(k, multi, a->groups_hint, st);
-    case 64: return launch_gram_m<64>(k, multi, a->groups_hint, st);
-    case 128: return launch_gram_m<128>(k, multi, a->groups_hint, st);
-    case 256: return launch_gram_m<256>(k, multi, a->groups_hint, st);
-    case 512: return launch_gram_m<512>(k, multi, a->groups_hint, st);
-    case 1024: return launch_gram_m<1024>(k, multi, a->groups_hint, st);
-    case 2048: return launch_gram_m<2048>(k, multi, a->groups_hint, st);
-    case 4096: return launch_gram_m<4096>(k, multi, a->groups_hint, st);
-    case 8192: return launch_gram_m<8192>(k, multi, a->groups_hint, st);
-    case 16384: return launch_gram_m<16384>(k, multi, a->groups_hint, st);
+    case 16: return launch_gram_m<16>(k, multi, a->groups_hint, st, allow);
+    case 32: return launch_gram_m<32>(k, multi, a->groups_hint, st, allow);
+    case 64: return launch_gram_m<64>(k, multi, a->groups_hint, st, allow);
+    case 128: return launch_gram_m<128>(k, multi, a->groups_hint, st, allow);
+    case 256: return launch_gram_m<256>(k, multi, a->groups_hint, st, allow);
+    case 512: return launch_gram_m<512>(k, multi, a->groups_hint, st, allow);
+    case 1024: return launch_gram_m<1024>(k, multi, a->groups_hint, st, allow);
+    case 2048: return launch_gram_m<2048>(k, multi, a->groups_hint, st, allow);
+    case 4096: return launch_gram_m<4096>(k, multi, a->groups_hint, st, allow);
+    case 8192: return launch_gram_m<8192>(k, multi, a->groups_hint, st, allow);
+    case 16384: return launch_gram_m<16384>(k, multi, a->groups_hint, st, allow);
   }
   return GLB_EINVAL;
 }

@@ -44,6 +44,17 @@ inline std::vector<float2> build_twiddles() {
   return tw;
 }
 
+// roots[k] = exp(-2 pi i k / M), k = 0..M-1
+inline std::vector<float2> build_roots(int M) {
+  std::vector<float2> v(M);
+  for (int k = 0; k < M; k++) {
+    double c, s;
+    unit_root(k, M, c, s);
+    v[k] = make_float2((float) c, (float) s);
+  }
+  return v;
+}
+
 // vtab[k] = -i exp(-2 pi i k / N), N = 2M, k = 0..M-1
 inline std::vector<float2> build_vtab(int M) {
   std::vector<float2> v(M);

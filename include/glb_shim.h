@@ -87,6 +87,9 @@ int glb_gram_fused_mean_ok(int n, int hop);
 /* testing aid: 1 = always use the general kernel (the TMA ring kernel is chosen automatically
  * for the regular geometries) */
 void glb_force_generic_kernel(int on);
+/* 0 = automatic choice, 1 = general kernel, 2 = TMA ring kernel, 3 = warp-per-frame kernel
+ * (a preference: launches a family cannot serve fall through to the next one) */
+void glb_set_kernel_preference(int pref);
 
 /* mean of every complete hop block: means[b - first_block] = mean(stream[b*hop, (b+1)*hop)) */
 int glb_launch_block_means(const float *samples, long long origin, long long count, int hop,

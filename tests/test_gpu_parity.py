@@ -103,24 +103,31 @@ def test_every_fft_size(gpu_api, n):
         assert_psd_close(got, ref, f"N={n} w={wt} ov={ov}")
 
 
-def test_general_kernel_on_regular_geometries(gpu_api):
-    """the regular geometries normally run the TMA ring kernel; the general kernel must give
-    the same rows (fused block means, table twiddles for large N)"""
-    x = stream(120000, seed=4)
+def test_every_kernel_family_on_regular_geometries(gpu_api):
+    """Three kernel families serve the same launches: general (1), TMA ring (2), warp-per-frame
+    (3; N <= 4096 periodograms, edge frames through the general kernel).  Each must match the
+    oracle; the automatic choice is whatever is fastest."""
+    x = stream(150000, seed=4)
     try:
         for kw in (dict(n=4096, window_type=0, overlap=0.5, sub_mean=True), dict(n=1024, window_type=7, overlap=0.75, sub_mean=True),
+                   dict(n=4096, window_type=3, overlap=0.0, sub_mean=True), dict(n=2048, window_type=1, overlap=0.875, sub_mean=True),
+                   dict(n=512, window_type=6, overlap=0.5, sub_mean=False), dict(n=4096, window_type=0, overlap=0.5, sub_mean=False, scale_db=True),
                    dict(n=16384, window_type=0, overlap=0.5, sub_mean=False),
                    dict(n=2048, mode=1, overlap=0.5, sub_mean=True, mtm_kmax=3, mtm_w=2.5)):
-            gpu_api.force_generic_kernel(False)
-            a = gpu_api.GramPlan(**kw).run(x)["psd"]
-            gpu_api.force_generic_kernel(True)
-            b = gpu_api.GramPlan(**kw).run(x)["psd"]
-            ref = O.multitaper(x, kw["n"], kw["overlap"], kw["mtm_w"], kw["mtm_kmax"], True) if kw.get("mode") else \
-                O.periodogram(x, kw["n"], kw["window_type"], kw["overlap"], kw["sub_mean"])
-            assert_psd_close(a, ref, f"ring {kw}")
-            assert_psd_close(b, ref, f"general {kw}")
+            if kw.get("mode"):
+                ref = O.multitaper(x, kw["n"], kw["overlap"], kw["mtm_w"], kw["mtm_kmax"], True)
+            else:
+                ref = O.periodogram(x, kw["n"], kw["window_type"], kw["overlap"], kw["sub_mean"])
+            for pref in (1, 2, 3, 0):
+                gpu_api.set_kernel_preference(pref)
+                got = gpu_api.GramPlan(**kw).run(x)["psd"]
+                if kw.get("scale_db"):
+                    big = ref > ref.mean(axis=1, keepdims=True) * 1e-5
+                    assert np.max(np.abs(got - 10 * np.log10(ref.astype(np.float64)))[big]) < 0.01, (pref, kw)
+                else:
+                    assert_psd_close(got, ref, f"family {pref} {kw}")
     finally:
-        gpu_api.force_generic_kernel(False)
+        gpu_api.set_kernel_preference(0)
 
 
 @pytest.mark.parametrize("ov", [0.0, 0.25, 0.3, 0.5, 0.75, 0.9, 0.97])

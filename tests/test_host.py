@@ -99,6 +99,17 @@ def test_fft_core_emulation(tmp_path):
     assert all(int(r[3]) == 0 and float(r[2]) < 1e-6 for r in rows)
 
 
+def test_warp_per_frame_core_emulation(tmp_path):
+    """fft_wpf.cuh (two-pass, 64 points per lane) on the CPU, lane by lane"""
+    exe = str(tmp_path / "emu_wpf")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "emu_wpf.cpp")], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    rows = [l.split() for l in res.stdout.strip().splitlines()]
+    assert [int(r[0]) for r in rows] == [256, 512, 1024, 2048]
+    assert all(int(r[3]) == 0 and float(r[2]) < 1e-6 for r in rows)
+
+
 def test_no_cpu_fallback(api):
     if api.device_count() > 0:
         pytest.skip("a CUDA device is present")
