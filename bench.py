@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -185,7 +185,7 @@ def cpu_reference_rate(kw, target_s=6.0, cores=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="metric", choices=sorted(WORKLOADS))
@@ -269,11 +269,13 @@ def main():
     plan.sync()
 
     # ---- device-resident timing -------------------------------------------------
+    # the sampler runs from before the warm-up to the end of the end-to-end region (nvidia-smi
+    # needs ~0.1 s to start); "under load" = samples in the upper half of the power range
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         plan.exec(first, nf, timed=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     launches0 = api.kernel_launches()
     step_ms, gram_ms = [], []
     t_wall0 = time.perf_counter()
@@ -283,7 +285,6 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = api.kernel_launches() - launches0
-    clocks = sampler.stop()
     dev_s = max_over_ranks(sum(step_ms) * 1e-3)
     gram_s = sum(gram_ms) * 1e-3 / len(gram_ms)
     value = world * nf * args.steps / dev_s          # all ranks do nf (+-1) frames per step
@@ -311,6 +312,7 @@ def main():
     else:
         checksum = None
 
+    clocks = sampler.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -121,6 +121,7 @@ void glfer_gram_config_default(glfer_gram_config *c)
   c->device = 0;
 }
 
+int glb_plan_sub_mean(const glfer_gram_plan *p) { return p->cfg.sub_mean; }
 int glfer_gram_hop(const glfer_gram_plan *p) { return p->hop; }
 int glfer_gram_bins(const glfer_gram_plan *p) { return p->bins; }
 long long glfer_gram_num_frames(const glfer_gram_plan *p, long long nsamples) { return nsamples / p->hop; }

@@ -63,6 +63,9 @@ long long glfer_wav_num_frames(const glfer_gram_plan *plan, const glfer_wav *wav
   return (bytes + hop * bps - 1) / (hop * bps);
 }
 
+/* the sub_mean flag of a plan (gram.c) */
+int glb_plan_sub_mean(const glfer_gram_plan *plan);
+
 int glfer_gram_run_wav(glfer_gram_plan *plan, const glfer_wav *wav, float *psd_rows, float *avg_rows,
                        double *avg_ret, int *avg_peakbin, double *avg_variance)
 {
@@ -70,9 +73,14 @@ int glfer_gram_run_wav(glfer_gram_plan *plan, const glfer_wav *wav, float *psd_r
   const long long nframes = glfer_wav_num_frames(plan, wav);
   if (nframes == 0) return 0;
   const long long total = nframes * hop;
-  if (wav->bits == 16) {
-    /* pad the final block the way a short read does: samples the read did not reach keep
-       the previous block's values (zeros if there is none) */
+  /* The stream as the block-by-block reader presents it, as floats: 8-bit (x-128)/128 and
+     16-bit x/32768 exactly (wav_fmt.c:108,113).  A short final read leaves the previous
+     block's tail in the reader's buffer (:102-119) -- and with sub_mean that buffer has already
+     had the previous block's mean subtracted in place by prepare_audio (fft.c:93-95), so the
+     tail is padded with the mean-removed values. */
+  const int partial = (wav->nsamples % hop) != 0;
+  if (wav->bits == 16 && !(partial && glb_plan_sub_mean(plan) && nframes >= 2)) {
+    /* common case: ship the PCM and convert on the device */
     short *pcm = malloc(sizeof(short) * (size_t) total);
     if (!pcm) { glb_set_error("out of memory"); return GLFER_ENOMEM; }
     memcpy(pcm, wav->data, sizeof(short) * (size_t) wav->nsamples);
@@ -82,12 +90,22 @@ int glfer_gram_run_wav(glfer_gram_plan *plan, const glfer_wav *wav, float *psd_r
     free(pcm);
     return rc;
   }
-  /* 8-bit: convert on the host side of the upload as (x - 128) / 128 exactly (wav_fmt.c:108) */
   float *x = malloc(sizeof(float) * (size_t) total);
   if (!x) { glb_set_error("out of memory"); return GLFER_ENOMEM; }
-  const unsigned char *b = wav->data;
-  for (long long i = 0; i < wav->nsamples; i++) x[i] = ((float) b[i] - 128) / 128;
-  for (long long i = wav->nsamples; i < total; i++) x[i] = (i >= hop) ? x[i - hop] : 0.0f;
+  if (wav->bits == 16) {
+    const short *b = wav->data;
+    for (long long i = 0; i < wav->nsamples; i++) x[i] = (float) b[i] / 32768;
+  } else {
+    const unsigned char *b = wav->data;
+    for (long long i = 0; i < wav->nsamples; i++) x[i] = ((float) b[i] - 128) / 128;
+  }
+  float prev_mean = 0.0f;
+  if (partial && glb_plan_sub_mean(plan) && nframes >= 2) {
+    const float *pb = x + (nframes - 2) * hop;
+    for (long long i = 0; i < hop; i++) prev_mean += pb[i];
+    prev_mean /= hop;
+  }
+  for (long long i = wav->nsamples; i < total; i++) x[i] = (i >= hop) ? x[i - hop] - prev_mean : 0.0f;
   const int rc = glfer_gram_run(plan, x, 0, total, 0, nframes, psd_rows, avg_rows, avg_ret, avg_peakbin, avg_variance);
   free(x);
   return rc;

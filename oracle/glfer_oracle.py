@@ -324,14 +324,16 @@ def compute_floor(psd: np.ndarray):
 
 
 # ------------------------------------------------------------------------------ WAV
-def read_wav_blocks(path: str, hop: int):
+def read_wav_blocks(path: str, hop: int, sub_mean: bool = False):
     """wav_fmt.c:45-121 restated for LP64 (the reference's header struct uses u_long and
     mis-parses on x86-64): skip the canonical 44-byte header
     (:58-66), rate / bits from it (:69-70), then one block of hop samples per read
     (:87,102); u8 -> (x-128)/128, s16 -> x/32768 (:105-116), channels not
     de-interleaved; a short final read leaves the stale tail of the previous block in
-    place (:102-119, buffer is calloc'ed once :91-100).  Returns (float32 stream of
-    whole blocks, sample_rate, bits)."""
+    place (:102-119, buffer is calloc'ed once :91-100).  With sub_mean the estimator has
+    already subtracted the previous block's mean IN PLACE in that very buffer
+    (fft.c:93-95 mutates audio_buf = wav_fmt.c's buff), so the stale tail carries the
+    mean-removed values.  Returns (float32 stream of whole blocks, sample_rate, bits)."""
     with open(path, "rb") as fh:
         hd = fh.read(44)
         rate = struct.unpack_from("<I", hd, 24)[0]
@@ -349,5 +351,8 @@ def read_wav_blocks(path: str, hop: int):
         buff = buff.copy()
         buff[: len(v)] = v
         blocks.append(buff)
+        if sub_mean:
+            # what prepare_audio leaves in the reader's buffer for the next read
+            buff = subtract_block_means(buff, hop)
     stream = np.concatenate(blocks) if blocks else np.zeros(0, dtype=np.float32)
     return stream, rate, bits

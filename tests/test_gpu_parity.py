@@ -343,11 +343,50 @@ def test_wav_source_with_stale_tail(gpu_api, tmp_path):
     synth.write_wav16(path, pcm, 8000)
     p = gpu_api.GramPlan(n=1024, window_type=0, overlap=0.5, sub_mean=True)
     r = p.run_wav(path)
-    strm, rate, bits = O.read_wav_blocks(path, 512)
+    strm, rate, bits = O.read_wav_blocks(path, 512, sub_mean=True)
     assert r["sample_rate"] == 8000 and r["bits"] == 16 and rate == 8000
     ref = O.periodogram(strm, 1024, 0, 0.5, True)
     assert r["psd"].shape == ref.shape == (-(-len(pcm) // 512), 513)
     assert_psd_close(r["psd"], ref, "WAV")
+    p0 = gpu_api.GramPlan(n=1024, window_type=0, overlap=0.5, sub_mean=False)
+    strm0, _, _ = O.read_wav_blocks(path, 512)
+    assert_psd_close(p0.run_wav(path)["psd"], O.periodogram(strm0, 1024, 0, 0.5, False), "WAV no mean")
+
+
+def test_headless_harness_per_call_and_batch(gpu_api, tmp_path):
+    """tools/glfer_headless: the reference's per-block loop written against fft.h/mtm.h/avg.h,
+    linked with libglfer_b200 (and, in oracle/_ref, with the unmodified reference)."""
+    import subprocess
+    from glfer_b200 import build
+    exe = build.build_tools()
+    pcm = GOLD["pcm"][:8000 * 2 + 77]
+    wav = str(tmp_path / "t.wav")
+    synth.write_wav16(wav, pcm, 8000)
+    ref_exe = os.path.join(os.path.dirname(R.path()), "glfer_headless_ref")
+    for args in (["-n", "1024", "-w", "0", "-o", "0.5", "-s", "1"], ["-n", "1024", "-m", "mtm", "-k", "7", "-W", "4", "-o", "0.5"],
+                 ["-n", "2048", "-w", "7", "-o", "0.75", "-A", "2", "-d", "4"]):
+        outs = {}
+        for tag, extra in (("percall", []), ("batch", ["-B"])):
+            out = str(tmp_path / f"{tag}.f32")
+            res = subprocess.run([exe, "-f", wav, "-O", out] + args + extra, capture_output=True, text=True)
+            assert res.returncode == 0, res.stderr
+            outs[tag] = np.fromfile(out, dtype=np.float32)
+        assert outs["percall"].shape == outs["batch"].shape
+        n = int(args[1])
+        a = outs["percall"].reshape(-1, n // 2 + 1).astype(np.float64)
+        b = outs["batch"].reshape(-1, n // 2 + 1).astype(np.float64)
+        if "-A" in args:
+            assert np.allclose(a, b, rtol=5e-4, atol=1e-15)
+        else:
+            assert_psd_close(a, b, "per-call vs batch")
+        if os.path.exists(ref_exe):
+            out = str(tmp_path / "ref.f32")
+            subprocess.run([ref_exe, "-f", wav, "-O", out] + args, check=True, capture_output=True)
+            r = np.fromfile(out, dtype=np.float32).reshape(a.shape).astype(np.float64)
+            if "-A" in args:
+                assert np.allclose(a, r, rtol=5e-4, atol=1e-15)
+            else:
+                assert_psd_close(a, r, "headless product vs reference build")
 
 
 # ------------------------------------------------------------------ time sharding

@@ -98,6 +98,36 @@ def test_wav_reader_stale_tail(tmp_path):
     assert rate == 8000 and bits == 16 and len(stream) == 1500
     assert np.array_equal(stream[:1300], synth.pcm16_to_float(pcm))
     assert np.array_equal(stream[1300:], stream[800:1000])        # stale tail of the previous block
+    # with sub_mean the stale tail was already mean-subtracted in place (fft.c:93-95)
+    s2, _, _ = O.read_wav_blocks(str(p), 500, sub_mean=True)
+    prev = stream[500:1000]
+    assert np.array_equal(s2[1300:], O.subtract_block_means(prev, 500)[300:])
+    assert np.array_equal(s2[:1300], stream[:1300])
+
+
+@have_ref
+def test_headless_loop_on_reference_equals_restatement(tmp_path):
+    """tools/glfer_headless.c (the per-block loop of source.c) linked against the unmodified
+    reference (oracle/_ref/glfer_headless_ref) reproduces the restatement bit for bit,
+    including the stale, mean-removed tail of a partial last block"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(R.path()), "glfer_headless_ref")
+    if not os.path.exists(exe):
+        pytest.skip("glfer_headless_ref not built")
+    pcm = GOLD["pcm"][:8000 * 2 + 77]
+    wav = tmp_path / "t.wav"
+    synth.write_wav16(str(wav), pcm, 8000)
+    for args, fn in ((["-n", "1024", "-w", "0", "-o", "0.5", "-s", "1"],
+                      lambda st: O.periodogram(st, 1024, 0, 0.5, True)),
+                     (["-n", "512", "-w", "7", "-o", "0.75", "-s", "0"],
+                      lambda st: O.periodogram(st, 512, 7, 0.75, False))):
+        out = tmp_path / "rows.f32"
+        subprocess.run([exe, "-f", str(wav), "-O", str(out)] + args, check=True, capture_output=True)
+        n = int(args[1])
+        hop = O.hop_size(n, float(args[5]))
+        st, _, _ = O.read_wav_blocks(str(wav), hop, sub_mean=args[7] == "1")
+        got = np.fromfile(str(out), dtype=np.float32).reshape(-1, n // 2 + 1)
+        assert np.array_equal(got, fn(st))
 
 
 @have_ref
