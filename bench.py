@@ -192,12 +192,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seconds", type=int, default=0, help="override the seconds of signal per rank")
+    ap.add_argument("--no-submean", action="store_true", help="experiment: opt.autoscale = 0 (no block-mean removal)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     desc, kw, seconds = WORKLOADS[args.workload]
+    kw = dict(kw)
+    if args.no_submean:
+        kw["sub_mean"] = False
     if args.seconds:
         seconds = args.seconds
     n = kw["n"]

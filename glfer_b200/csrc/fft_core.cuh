@@ -66,8 +66,36 @@ template <int M> struct TwOffset<M, 0> { static constexpr int value = 0; };
 template <int M> struct TwTotal { static constexpr int value = TwOffset<M, Plan<M>::NP>::value; };
 
 // ------------------------------------------------------------------ complex helpers
+// Complex add / subtract.  On sm_100a (device code, GLB_PACKED_ADD) they are single packed
+// instructions (FADD2 on an aligned register pair): half the issue slots of the scalar form.
+#if !defined(GLB_PACKED_ADD)
+#define GLB_PACKED_ADD 1
+#endif
+#if defined(__CUDA_ARCH__) && GLB_PACKED_ADD
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&r))
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  float2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&r))
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return r;
+}
+// component-wise product (window / taper multiply): one FMUL2
+__device__ __forceinline__ float2 emul(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&r))
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return r;
+}
+#else
 GLB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 GLB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+GLB_HD float2 emul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
 GLB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 GLB_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
 GLB_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
@@ -243,8 +271,9 @@ GLB_HD void last_pass(float2 *v, int t, const float2 *buf, const float2 *tw) {
 // vk = -i exp(-2 pi i k / N), returns 2 X[k] in a and 2 X[M-k]^* in b
 // (scaled by whatever scale the input carried).
 GLB_HD void split_pair(float2 zk, float2 zm, float2 vk, float2 &a, float2 &b) {
-  float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
-  float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
+  const float2 czm = make_float2(zm.x, -zm.y);
+  float2 p = cadd(zk, czm);
+  float2 q = csub(zk, czm);
   float2 vq = cmul(vk, q);
   a = cadd(p, vq);
   b = csub(p, vq);
@@ -443,8 +472,9 @@ GLB_HD float2 w16_mul(float2 q, int e) {
 
 // split with V_k = V_t W_16^rp rebuilt from the kept V_t
 GLB_HD void split_pair_rt(float2 zk, float2 zm, float2 v0, int rp, float2 &a, float2 &b) {
-  float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
-  float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
+  const float2 czm = make_float2(zm.x, -zm.y);
+  float2 p = cadd(zk, czm);
+  float2 q = csub(zk, czm);
   float2 vq = cmul(v0, w16_mul(q, rp));
   a = cadd(p, vq);
   b = csub(p, vq);

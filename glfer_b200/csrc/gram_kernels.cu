@@ -367,7 +367,7 @@ __device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (
 #pragma unroll
     for (int q = 0; q < kPoints; q++) {
       const float2 w = ldg2(w2 + t + T * q);
-      v[q] = make_float2(x[q].x * w.x, x[q].y * w.y);
+      v[q] = emul(x[q], w);
     }
     return;
   }
@@ -559,15 +559,18 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 // so every sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM
 // latency hides behind the previous frame's transform.  Block means (sub_mean) are computed
 // once per block when it lands and kept beside the ring.
+#ifndef GLB_RING_EXTRA
+#define GLB_RING_EXTRA 0  // 1: one spare slot, the next block is requested at the top of a frame;
+#endif                    // 0: NB slots, requested after barrier (A) into the oldest block's slot
 struct RingLayout {
-  int slots;            // NB + 1
+  int slots;            // NB + GLB_RING_EXTRA
   size_t ring_off, red_off, mu_off, mbar_off, group_bytes;
 };
 
 template <int M>
 __host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
   RingLayout L;
-  L.slots = nb + 1;
+  L.slots = nb + GLB_RING_EXTRA;
   L.ring_off = Geo<M>::BUF_BYTES;
   L.red_off = L.ring_off + (size_t) L.slots * hop * sizeof(float);
   L.mu_off = L.red_off + (size_t) 18 * Geo<M>::NW * sizeof(float);
@@ -580,9 +583,26 @@ __host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
 // shuffle, the group combines through `red` (one barrier).  The summation tree of a block is
 // the same wherever the block sits in a frame: its mean is bit-identical in every frame, group
 // and time shard.  Must be called by all threads of the CTA (contains a block barrier).
+#ifndef GLB_MEAN_PER_WARP
+#define GLB_MEAN_PER_WARP 0
+#endif
 template <int M>
 __device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
   constexpr int T = M / kPoints, NW = (T + 31) / 32, W = T < 32 ? T : 32;
+  if (GLB_MEAN_PER_WARP && NW > 1) {
+    // every warp sums the whole block on its own (hop/32 floats per lane, 128-bit loads):
+    // a little redundant shared-memory traffic instead of a block barrier per frame
+    const int hop = (2 * T) << qs;
+    const float4 *b4 = reinterpret_cast<const float4 *>(blk);
+    float s = 0.f;
+    for (int i = (t & 31); i < hop / 4; i += 32) {
+      const float4 a = b4[i];
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s * inv_hop;
+  }
   const float2 *b2 = reinterpret_cast<const float2 *>(blk);
   float s = 0.f;
   for (int i = 0; i < (1 << qs); i++) {
@@ -613,7 +633,7 @@ __device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const flo
 #pragma unroll
     for (int i = 0; i < (1 << QS); i++) {
       const float2 a = bp[t + T * i];
-      x[(b << QS) + i] = make_float2(a.x - m, a.y - m);
+      x[(b << QS) + i] = csub(a, make_float2(m, m));
     }
     sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
   }
@@ -701,13 +721,15 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
         if (t == 0) mu[slot_new] = mu_new;
       }
     }
-    if (next_there && t == 0) {
-      // slot_next held block f - nb: its last readers passed a block barrier in frame f - 1
+    auto request_next = [&]() {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&mbar[slot_next], blk_bytes);
       tma_load_1d(ring + (size_t) slot_next * hop, p.samples + ((f + 1) * (long long) hop - p.origin), blk_bytes, &mbar[slot_next]);
-    }
-    const int slot_oldest = (slot_next + 1 == slots) ? 0 : slot_next + 1;     // = slot of block f - nb + 1
+    };
+    // spare slot: slot_next held block f - nb, whose last readers passed a block barrier in frame f - 1
+    if (GLB_RING_EXTRA && next_there && t == 0) request_next();
+    // slot of block f - nb + 1: next to the spare slot, or (tight ring) the slot block f + 1 will take
+    const int slot_oldest = GLB_RING_EXTRA ? ((slot_next + 1 == slots) ? 0 : slot_next + 1) : slot_next;
     float acc[17];
     if (MULTI) {
 #pragma unroll
@@ -735,6 +757,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
         __syncthreads();
         pass_store<M, 0>(v, t, buf, p.tw);
       }
+      // tight ring: past (A) of the last taper nobody reads the oldest block any more
+      if (!GLB_RING_EXTRA && next_there && j == ntap - 1 && t == 0) request_next();
       __syncthreads();
       MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr);
       float *row = p.rows + fl * p.row_stride;
@@ -1307,6 +1331,98 @@ __global__ void __launch_bounds__(256) avg_kernel(const glb_avg_args a, int chun
   }
 }
 
+// Direct form for small depths: one warp per frame, no block barrier, no state carried
+// between frames.  The window sum of every band bin is re-read from the PSD rows (depth loads
+// per bin, L2-resident: consecutive frames share depth-1 of them); pass 1 reduces max / first
+// argmax / sum / min over the band with shuffles, pass 2 recomputes the sums and writes the
+// normalised row.  Frames are fully independent, so the grid is sized by the frame count.
+template <typename OutT>
+__global__ void __launch_bounds__(256) avg_direct_kernel(const glb_avg_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  const int band = a.maxbin - a.minbin;
+  OutT *out_base = (OutT *) a.avg_rows;
+  auto psd_row = [&](long long g2) -> const float * {
+    const long long r = a.psd_ring_rows > 0 ? g2 % a.psd_ring_rows : g2 - a.psd_first_frame;
+    return a.psd + r * a.psd_stride;
+  };
+  for (long long fl = warp; fl < a.nframes; fl += nwarps) {
+    const long long f = a.first_frame + fl;
+    const long long eff = (f + 1 < a.depth) ? f + 1 : a.depth;
+    const long long g0 = f - eff + 1;
+    auto window_sum = [&](int b) {
+      double c = 0.0;
+      for (long long g2 = g0; g2 <= f; ++g2) c += (double) psd_row(g2)[b];
+      return c;
+    };
+    double mx = -1.0, sum = 0.0, mn = 1.0;
+    int arg = -1;
+    for (int i = lane; i < band; i += 32) {
+      const int b = a.minbin + i;
+      const double c = window_sum(b);
+      if (arg < 0 || c > mx) { mx = c; arg = b; }
+      sum += c;
+      if (c < mn) mn = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (oarg >= 0 && (arg < 0 || omx > mx || (omx == mx && oarg < arg))) { mx = omx; arg = oarg; }
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const double omn = __shfl_xor_sync(0xffffffffu, mn, o);
+      if (omn < mn) mn = omn;
+    }
+    const double m0 = (double) psd_row(f)[a.minbin];            // `double max = psd[minbin]` (avg.c:111)
+    const int cand = (arg >= 0 && mx > m0) ? arg : -1;
+    const double vmax = (cand >= 0) ? mx : m0;
+    // *peakbin after this frame: the new candidate, else the caller's value -- known only for
+    // the very first frame of the call; otherwise the frame is flagged for the in-order kernel
+    const bool carry_known = (cand >= 0) || (fl == 0);
+    const int pk = (cand >= 0) ? cand : a.peakbin_init;
+    double avgspec = 0.0, retv;
+    if (a.mode == 2) {
+      retv = (sum - vmax) / ((double) (band - 1) * (double) (eff + 1));
+    } else {
+      avgspec = (sum - vmax) / (double) (band - 1);
+      retv = vmax / avgspec;
+    }
+    OutT *orow = out_base + fl * a.out_stride;
+    double var = 0.0;
+    int cnt = 0;
+    for (int b = lane; b < a.nbins; b += 32) {
+      double y = 1e-15;
+      if (b >= a.minbin && b < a.maxbin) {
+        const double c = window_sum(b);
+        if (a.mode == 2) {
+          y = c / (double) (eff + 1);
+        } else if (a.mode == 3) {
+          y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
+        } else if (c - avgspec > 0) {
+          y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
+          if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
+        }
+      }
+      if (sizeof(OutT) == 4 && a.rows_db) y = 10.0 * log10(y);
+      orow[b] = (OutT) y;
+    }
+    if (a.mode == 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        var += __shfl_xor_sync(0xffffffffu, var, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+    }
+    if (lane == 0) {
+      if (a.ret) a.ret[fl] = retv;
+      if (a.peak_cand) a.peak_cand[fl] = cand;
+      if (a.variance) a.variance[fl] = (a.mode == 1) ? var / (double) cnt : 0.0;
+      if (a.mode == 1 && !carry_known && a.unresolved) atomicAdd(a.unresolved, 1);
+    }
+  }
+}
+
 extern "C" int glb_launch_avg(const glb_avg_args *a, void *stream) {
   if (!a || a->mode < 1 || a->mode > 3 || a->depth < 1 || a->minbin < 0 || a->maxbin < a->minbin) {
     glb_set_error("glb_launch_avg: invalid arguments");
@@ -1316,6 +1432,16 @@ extern "C" int glb_launch_avg(const glb_avg_args *a, void *stream) {
   const int band = a->maxbin - a->minbin;
   const size_t smem = (size_t) (band > 0 ? band : 1) * sizeof(double);
   if (smem > 200 * 1024) { glb_set_error("glb_launch_avg: band too wide"); return GLB_EINVAL; }
+  cudaStream_t st = (cudaStream_t) stream;
+  if (!a->sequential && a->depth <= 32) {
+    long long ctas = (a->nframes * 32 + 255) / 256;
+    if (ctas > 148 * 64) ctas = 148 * 64;
+    if (a->out_double) avg_direct_kernel<double><<<(int) ctas, 256, 0, st>>>(*a);
+    else avg_direct_kernel<float><<<(int) ctas, 256, 0, st>>>(*a);
+    CU(cudaGetLastError());
+    g_launches++;
+    return GLB_OK;
+  }
   int chunk;
   if (a->sequential) {
     chunk = (int) std::min<long long>(a->nframes, 0x7fffffff);
@@ -1326,7 +1452,6 @@ extern "C" int glb_launch_avg(const glb_avg_args *a, void *stream) {
     chunk = (int) std::max(want, by_grid);
   }
   long long ctas = (a->nframes + chunk - 1) / chunk;
-  cudaStream_t st = (cudaStream_t) stream;
   if (a->out_double) {
     CU(cudaFuncSetAttribute(avg_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     avg_kernel<double><<<(int) ctas, 256, smem, st>>>(*a, chunk);
