@@ -323,6 +323,14 @@ def main():
         return
 
     peak, peak_src = measured_peak_gbs()
+    traffic = None          # DRAM read+write bytes of the kernel per launch, from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("workload") == args.workload and not args.seconds:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     alg_bytes = nf * (hop * 4 + bins * 4)
     achieved = alg_bytes / gram_s / 1e9
     line = {"metric": "spectrogram_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -331,7 +339,7 @@ def main():
             "data": "synthetic QRSS/DFCW multi-tone + noise (int16-quantised, /32768), 20 s block tiled to length",
             "config": config, "samples_per_sec": value * hop,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "gram_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "gram_kernel",
                          "kernel_ms": 1e3 * gram_s, "algorithmic_bytes_per_launch": alg_bytes,
                          "fp32_flops_per_launch": nf * ntap * 5 * n * int(np.log2(n)),
                          "fp32_tflops_5nlogn": nf * ntap * 5 * n * np.log2(n) / gram_s / 1e12},

@@ -198,6 +198,9 @@ struct KParams {
 #ifndef GLB_REG_TARGET
 #define GLB_REG_TARGET 80
 #endif
+#ifndef GLB_PACKED_WIN
+#define GLB_PACKED_WIN 0
+#endif
 template <int M> struct Geo {
   static constexpr int N = 2 * M;
   static constexpr int T = M / kPoints;
@@ -216,7 +219,7 @@ template <int M> struct Geo {
   static __host__ __device__ constexpr size_t group_bytes(bool multi) { return ((BUF_BYTES + stage_bytes(multi) + RED_BYTES + 16 + 15) / 16) * 16; }
   static __host__ __device__ constexpr size_t smem_bytes(bool multi) { return (size_t) G * group_bytes(multi); }
   // CTAs per SM the register allocation is tuned for (~GLB_REG_TARGET registers per thread)
-  static constexpr int MINB_ = 65536 / (THREADS * GLB_REG_TARGET);
+  static constexpr int MINB_ = 65536 / (THREADS * (THREADS >= 512 ? 64 : GLB_REG_TARGET));
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
 };
 
@@ -367,7 +370,11 @@ __device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (
 #pragma unroll
     for (int q = 0; q < kPoints; q++) {
       const float2 w = ldg2(w2 + t + T * q);
+#if GLB_PACKED_WIN
       v[q] = emul(x[q], w);
+#else
+      v[q] = make_float2(x[q].x * w.x, x[q].y * w.y);
+#endif
     }
     return;
   }
@@ -633,7 +640,11 @@ __device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const flo
 #pragma unroll
     for (int i = 0; i < (1 << QS); i++) {
       const float2 a = bp[t + T * i];
+#if GLB_PACKED_WIN
       x[(b << QS) + i] = csub(a, make_float2(m, m));
+#else
+      x[(b << QS) + i] = make_float2(a.x - m, a.y - m);
+#endif
     }
     sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
   }
