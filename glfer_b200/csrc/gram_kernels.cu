@@ -1402,20 +1402,42 @@ __global__ void __launch_bounds__(256) avg_direct_kernel(const glb_avg_args a) {
     OutT *orow = out_base + fl * a.out_stride;
     double var = 0.0;
     int cnt = 0;
-    for (int b = lane; b < a.nbins; b += 32) {
-      double y = 1e-15;
-      if (b >= a.minbin && b < a.maxbin) {
-        const double c = window_sum(b);
-        if (a.mode == 2) {
-          y = c / (double) (eff + 1);
-        } else if (a.mode == 3) {
-          y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
-        } else if (c - avgspec > 0) {
-          y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
-          if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
-        }
+    // outside the band the row is the constant 1e-15 (avg.c:152-153): plain streaming stores
+    const bool out_db = sizeof(OutT) == 4 && a.rows_db;
+    const OutT fill = (OutT) (out_db ? -150.0 : 1e-15);
+    auto fill_range = [&](int lo, int hi) {
+      if (sizeof(OutT) == 4) {
+        // rows have an odd stride: align to 16 bytes per row, then 128-bit stores
+        float *base = reinterpret_cast<float *>(orow);
+        int head = (int) (((16 - (reinterpret_cast<uintptr_t>(base + lo) & 15)) & 15) >> 2);
+        if (head > hi - lo) head = hi - lo;
+        if (lane < head) base[lo + lane] = (float) fill;
+        const int body = (hi - lo - head) >> 2;
+        float4 *b4 = reinterpret_cast<float4 *>(base + lo + head);
+        const float4 f4 = make_float4((float) fill, (float) fill, (float) fill, (float) fill);
+        for (int i = lane; i < body; i += 32) b4[i] = f4;
+        const int done = lo + head + 4 * body;
+        if (done + lane < hi) base[done + lane] = (float) fill;
+      } else {
+        for (int b = lo + lane; b < hi; b += 32) orow[b] = fill;
       }
-      if (sizeof(OutT) == 4 && a.rows_db) y = 10.0 * log10(y);
+    };
+    fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
+    if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
+    for (int b = a.minbin + lane; b < a.maxbin && b < a.nbins; b += 32) {
+      double y;
+      const double c = window_sum(b);
+      if (a.mode == 2) {
+        y = c / (double) (eff + 1);
+      } else if (a.mode == 3) {
+        y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
+      } else if (c - avgspec > 0) {
+        y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
+        if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
+      } else {
+        y = 1e-15;
+      }
+      if (out_db) y = 10.0 * log10(y);
       orow[b] = (OutT) y;
     }
     if (a.mode == 1) {
