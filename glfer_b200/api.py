@@ -48,6 +48,11 @@ class AvgData(C.Structure):            # include/avg.h (reference avg.h:28-36)
                 ("cum", C.POINTER(C.c_double)), ("avgarray", C.POINTER(C.POINTER(C.c_double)))]
 
 
+class DisplayConfig(C.Structure):      # include/glfer_b200.h glfer_display_config
+    _fields_ = [("log_scale", C.c_int), ("autoscale", C.c_int), ("max_level_db", C.c_float),
+                ("min_level_db", C.c_float), ("thr_level", C.c_float), ("colortab", C.c_void_p)]
+
+
 class Wav(C.Structure):
     _fields_ = [("sample_rate", C.c_int), ("bits", C.c_int), ("channels", C.c_int), ("nsamples", C.c_longlong),
                 ("data", C.c_void_p)]
@@ -88,6 +93,10 @@ def lib() -> C.CDLL:
         l.glfer_gram_sync.argtypes = [C.c_void_p]
         l.glfer_gram_last_gram_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         l.glfer_gram_fetch.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        disp_args = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong,
+                     C.POINTER(DisplayConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.glfer_gram_run_display.argtypes = disp_args
+        l.glfer_gram_run_display_pcm16.argtypes = disp_args
         l.glfer_gram_run_sharded.argtypes = [C.POINTER(GramConfig), C.c_int, C.POINTER(C.c_int), C.c_void_p,
                                              C.c_longlong] + [C.c_void_p] * 5
         l.glfer_gram_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong),
@@ -281,6 +290,30 @@ class GramPlan:
         psd, avg, ret, pk, var = self._outs(nframes, want_psd)
         _check(lib().glfer_gram_fetch(self._h, _ptr(psd), _ptr(avg), _ptr(ret), _ptr(pk), _ptr(var)))
         return dict(psd=psd, avg=avg, ret=ret, peakbin=pk, variance=var)
+
+    def run_display(self, samples: np.ndarray, log_scale=True, autoscale=True, max_level_db=-20.0, min_level_db=-80.0,
+                    thr_level=0.0, colortab: np.ndarray | None = None, origin: int = 0, first_frame: int = 0,
+                    nframes: int | None = None, agc_state: np.ndarray | None = None, want_rgb: bool = False,
+                    out: dict | None = None):
+        """glfer_gram_run_display: rows -> 8-bit levels (and RGB) as main_window_draw maps them."""
+        pcm = samples.dtype == np.int16
+        assert samples.flags["C_CONTIGUOUS"] and (pcm or samples.dtype == np.float32)
+        if nframes is None:
+            nframes = (origin + len(samples)) // self.hop - first_frame
+        out = out or {}
+        levels = out.get("levels") if "levels" in out else np.empty((nframes, self.bins), np.uint8)
+        rgb = np.empty((nframes, self.bins, 3), np.uint8) if want_rgb else None
+        rng = np.empty((nframes, 2), np.float32) if autoscale else None
+        if colortab is not None:
+            colortab = np.ascontiguousarray(colortab, dtype=np.uint8)
+            assert colortab.size == 768
+        dc = DisplayConfig(int(log_scale), int(autoscale), max_level_db, min_level_db, thr_level,
+                           colortab.ctypes.data if colortab is not None else None)
+        state = agc_state if agc_state is not None else np.zeros(2, np.float32)
+        fn = lib().glfer_gram_run_display_pcm16 if pcm else lib().glfer_gram_run_display
+        _check(fn(self._h, samples.ctypes.data, origin, len(samples), first_frame, nframes, C.byref(dc), state.ctypes.data,
+                  _ptr(levels), _ptr(rgb), _ptr(rng)))
+        return dict(levels=levels, rgb=rgb, range=rng, agc_state=state)
 
     def run_wav(self, path: str, want_psd: bool = True):
         wav = Wav()

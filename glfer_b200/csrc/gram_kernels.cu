@@ -1626,3 +1626,100 @@ extern "C" int glb_launch_floor_stats(const float *rows, long long stride, int n
   g_launches++;
   return GLB_OK;
 }
+
+// ------------------------------------------------------------------------- display mapping
+// main_window_draw, g_main.c:1109-1229, minus the GTK drawing: AGC of the display range from
+// the per-row floor statistics, then level -> 8-bit palette index (-> RGB).
+//
+// agc_kernel: the display range is a recurrence over frames in mixed double/float arithmetic
+// with a rounding to float at every step (static float display_max_lvl, g_main.c:1080,
+// 1118-1123), so it is walked in order by one thread: O(frames) scalar work, exact semantics.
+// state[0..1] = (display_max_lvl, display_min_lvl) carried between calls; stats = floor_stats rows.
+__global__ void agc_kernel(const float *__restrict__ stats, long long nframes, long long first_frame, float overlap,
+                           int log_scale, float *__restrict__ state, float *__restrict__ range /* [nframes][2] */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float mx = state[0], mn = state[1];
+  for (long long i = 0; i < nframes; i++) {
+    float sig = stats[4 * i + 0], flo = stats[4 * i + 1];
+    if (first_frame + i == 0) {                      // glfer.first_buffer == TRUE (g_main.c:1112-1120)
+      if (overlap > 0.0f) { sig /= overlap; flo /= overlap; }
+      mx = sig;
+      mn = flo;
+    } else {                                         // g_main.c:1122-1123
+      mx = (float) ((1.0 - 0.99) * (double) sig + 0.99 * (double) mx);
+      mn = (float) ((1.0 - 0.99) * (double) flo + 0.99 * (double) mn);
+    }
+    if (log_scale) {                                 // g_main.c:1132-1135
+      range[2 * i + 0] = (float) (10.0 * log10((double) mx));
+      range[2 * i + 1] = (float) (10.0 * log10((double) mn));
+    } else {
+      range[2 * i + 0] = mx;
+      range[2 * i + 1] = mn;
+    }
+  }
+  state[0] = mx;
+  state[1] = mn;
+}
+
+// levels_kernel: one warp per row.  Pixel i of a row shows bin n-1-i (g_main.c:1193-1201); in
+// the log scales the level first passes through the reference's `short` level buffer
+// (sig_level = levbuf[..] = 10 log10(x): integer-truncated dB, g_main.c:68,1193-1195).
+__device__ __forceinline__ float short_db(float x) {
+  const double d = 10.0 * log10((double) x);
+  if (!(fabs(d) < 2147483648.0)) return 0.f;        // x86 cvttsd2si overflow -> 0x80000000 -> (short) 0
+  return (float) (short) (int) d;
+}
+
+__global__ void __launch_bounds__(256) levels_kernel(const float *__restrict__ rows, long long stride, int nbins,
+                                                     long long nframes, const float *__restrict__ range,
+                                                     const float *__restrict__ fixed_range, int log_scale, float thr,
+                                                     const unsigned char *__restrict__ colortab,
+                                                     unsigned char *__restrict__ levels, unsigned char *__restrict__ rgb) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
+  for (long long f = warp; f < nframes; f += nwarps) {
+    const float dmax = range ? range[2 * f] : fixed_range[0];
+    const float dmin = range ? range[2 * f + 1] : fixed_range[1];
+    const float *row = rows + f * stride;
+    for (int i = lane; i < nbins; i += 32) {
+      const float x = row[nbins - 1 - i];
+      const float sig_level = log_scale ? short_db(x) : x;
+      const float fl = 255 * ((sig_level - dmin) / (dmax - dmin));
+      unsigned char v;
+      if ((double) fl < 255.0 * (double) thr) v = 0;
+      else if (fl > 255) v = 255;
+      else v = (unsigned char) (((double) fl - 255.0 * (double) thr) / (1.0 - (double) thr));
+      if (levels) levels[f * nbins + i] = v;
+      if (rgb) {
+        unsigned char *px = rgb + (f * nbins + i) * 3;
+        px[0] = colortab[3 * v];
+        px[1] = colortab[3 * v + 1];
+        px[2] = colortab[3 * v + 2];
+      }
+    }
+  }
+}
+
+extern "C" int glb_launch_agc(const float *stats, long long nframes, long long first_frame, float overlap, int log_scale,
+                              float *state, float *range, void *stream) {
+  if (nframes <= 0) return GLB_OK;
+  agc_kernel<<<1, 32, 0, (cudaStream_t) stream>>>(stats, nframes, first_frame, overlap, log_scale, state, range);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
+extern "C" int glb_launch_levels(const float *rows, long long stride, int nbins, long long nframes, const float *range,
+                                 const float *fixed_range, int log_scale, float thr, const unsigned char *colortab,
+                                 unsigned char *levels, unsigned char *rgb, void *stream) {
+  if (nframes <= 0) return GLB_OK;
+  if ((!range && !fixed_range) || (rgb && !colortab)) { glb_set_error("glb_launch_levels: missing range / palette"); return GLB_EINVAL; }
+  long long ctas = (nframes * 32 + 255) / 256;
+  if (ctas > 148 * 64) ctas = 148 * 64;
+  levels_kernel<<<(int) ctas, 256, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nframes, range, fixed_range, log_scale, thr,
+                                                              colortab, levels, rgb);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}

@@ -40,6 +40,11 @@ typedef struct {
   int *d_cand, *d_peak, *d_unres;
   size_t scal_cap;      /* frames */
   long long out_first, out_nframes, out_halo;
+  /* display mapping */
+  void *ev_agc;
+  float *d_stats, *d_range;
+  unsigned char *d_levels, *d_rgb;
+  size_t stats_cap, levels_cap, rgb_cap;
 } slot_t;
 
 struct glfer_gram_plan {
@@ -54,6 +59,8 @@ struct glfer_gram_plan {
   slot_t slot[NSLOT];
   int *d_cand_all, *d_peak_all;   /* whole-run *peakbin candidates / carried values */
   size_t cand_all_cap;
+  float *d_agc_state, *d_fixed_range;   /* display mapping: carried AGC levels, fixed display range */
+  unsigned char *d_colortab;
 };
 
 static __thread char g_msg[512];
@@ -167,11 +174,14 @@ void glfer_gram_plan_destroy(glfer_gram_plan *p)
     glb_free(s->d_samples); glb_free(s->d_pcm); glb_free(s->d_means); glb_free(s->d_psd); glb_free(s->d_avg);
     glb_free(s->d_ret); glb_free(s->d_var); glb_free(s->d_cand); glb_free(s->d_peak); glb_free(s->d_unres);
     glb_event_destroy(s->ev0); glb_event_destroy(s->ev1); glb_event_destroy(s->ev2); glb_event_destroy(s->ev3);
+    glb_event_destroy(s->ev_agc);
+    glb_free(s->d_stats); glb_free(s->d_range); glb_free(s->d_levels); glb_free(s->d_rgb);
     glb_stream_destroy(s->stream);
   }
   glb_free(p->d_tapers);
   glb_free(p->d_cand_all);
   glb_free(p->d_peak_all);
+  glb_free(p->d_agc_state); glb_free(p->d_fixed_range); glb_free(p->d_colortab);
   glb_tables_destroy(p->tables);
   free(p->h_window); free(p->h_tapers); free(p->h_lambda);
   free(p);
@@ -250,6 +260,7 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
     if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev1));
     if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev2));
     if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev3));
+    if (rc == 0) rc = shim(glb_event_create(&p->slot[i].ev_agc));
     if (rc == 0) rc = shim(glb_malloc((void **) &p->slot[i].d_unres, sizeof(int)));
   }
   if (rc != 0) {
@@ -582,6 +593,126 @@ int glfer_gram_run_pcm16(glfer_gram_plan *p, const short *pcm, long long origin,
   if (!p || !pcm) return fail(GLFER_EINVAL, "null argument");
   return run_impl(p, NULL, pcm, origin, count, first_frame, nframes, psd_rows, avg_rows, avg_ret, avg_peakbin,
                   avg_variance);
+}
+
+/* ---------------------------------------------------------------- display mapping
+ * The tail of main_window_draw (g_main.c:1109-1229) for a whole run: per-row floor statistics
+ * (compute_floor), the AGC of the display range (a recurrence over frames, walked in order on
+ * the device and carried from chunk to chunk through an event chain between the two slots),
+ * then 8-bit levels / RGB.  Only 1 (levels) or 3 (RGB) bytes per bin go back to the host. */
+static int run_display_impl(glfer_gram_plan *p, const float *samples, const short *pcm, long long origin,
+                            long long count, long long first_frame, long long nframes,
+                            const glfer_display_config *dc, float *agc_state, unsigned char *levels,
+                            unsigned char *rgb, float *range_out)
+{
+  g_msg[0] = 0;
+  if (!dc) return fail(GLFER_EINVAL, "null display config");
+  if (nframes < 0 || first_frame < 0) return fail(GLFER_EINVAL, "negative frame range");
+  if (p->cfg.scale_db) return fail(GLFER_EINVAL, "display mapping needs linear rows (scale_db = 0)");
+  if (rgb && !dc->colortab) return fail(GLFER_EINVAL, "RGB output needs a 256-entry palette");
+  if (dc->autoscale && first_frame > 0 && !agc_state)
+    return fail(GLFER_EINVAL, "autoscale from frame > 0 needs the carried AGC state");
+  if (nframes == 0) return 0;
+  TRY(glb_set_device(p->cfg.device));
+  long long lo, hi;
+  glfer_gram_required_span(p, first_frame, nframes, &lo, &hi);
+  if (lo < 0) lo = 0;
+  if (lo < origin || hi > origin + count)
+    return fail(GLFER_EINVAL, "samples do not cover the requested frames (see glfer_gram_required_span)");
+  if (!p->d_agc_state) {
+    TRY(glb_malloc((void **) &p->d_agc_state, 2 * sizeof(float)));
+    TRY(glb_malloc((void **) &p->d_fixed_range, 2 * sizeof(float)));
+    TRY(glb_malloc((void **) &p->d_colortab, 768));
+  }
+  void *st0 = p->slot[0].stream;
+  float state[2] = { agc_state ? agc_state[0] : 0.0f, agc_state ? agc_state[1] : 0.0f };
+  TRY(glb_memcpy_h2d(p->d_agc_state, state, sizeof state, st0));
+  if (!dc->autoscale) {
+    /* fixed levels, g_main.c:1126-1138 */
+    float mx = pow(10.0, dc->max_level_db / 10.0);
+    float mn = pow(10.0, dc->min_level_db / 10.0);
+    mn = (mx > mn ? mn : mx / 10.0);
+    float r[2];
+    if (dc->log_scale) { r[0] = 10.0 * log10(mx); r[1] = 10.0 * log10(mn); }
+    else { r[0] = mx; r[1] = mn; }
+    TRY(glb_memcpy_h2d(p->d_fixed_range, r, sizeof r, st0));
+  }
+  if (dc->colortab) TRY(glb_memcpy_h2d(p->d_colortab, dc->colortab, 768, st0));
+  TRY(glb_stream_sync(st0));
+  const float thr = dc->thr_level / 100.0;                  /* g_main.c:1098 */
+  const long long cf = chunk_frames(p);
+  const int avg_on = p->cfg.avg_mode != GLFER_NO_AVG;
+  int rc = 0, ci = 0;
+  long long done = 0;
+  while (done < nframes && rc == 0) {
+    slot_t *s = &p->slot[ci % NSLOT];
+    const long long c0 = first_frame + done;
+    const long long cn = (nframes - done < cf) ? nframes - done : cf;
+    rc = shim(glb_stream_sync(s->stream));
+    if (rc) break;
+    long long clo, chi;
+    glfer_gram_required_span(p, c0, cn, &clo, &chi);
+    if (clo < 0) clo = 0;
+    rc = stage_slot(p, s, samples ? samples + (clo - origin) : NULL, pcm ? pcm + (clo - origin) : NULL, clo, chi - clo);
+    if (rc) break;
+    rc = exec_slot(p, s, c0, cn, NULL);
+    if (rc) break;
+    const float *d_psd = s->d_psd + (size_t) s->out_halo * p->bins;
+    const float *d_shown = avg_on ? s->d_avg : d_psd;               /* g_main.c:1192-1201 */
+    rc = ensure((void **) &s->d_levels, &s->levels_cap, (size_t) cn * p->bins, 1);
+    if (rc == 0 && rgb) rc = ensure((void **) &s->d_rgb, &s->rgb_cap, (size_t) cn * p->bins * 3, 1);
+    if (rc) break;
+    const float *d_range = NULL;
+    if (dc->autoscale) {
+      if ((size_t) cn > s->stats_cap) {
+        glb_free(s->d_stats); glb_free(s->d_range);
+        s->d_stats = s->d_range = NULL; s->stats_cap = 0;
+        rc = shim(glb_malloc((void **) &s->d_stats, sizeof(float) * 4 * (size_t) cn));
+        if (rc == 0) rc = shim(glb_malloc((void **) &s->d_range, sizeof(float) * 2 * (size_t) cn));
+        if (rc) break;
+        s->stats_cap = (size_t) cn;
+      }
+      /* compute_floor always looks at the raw PSD row (g_main.c:1109) */
+      rc = shim(glb_launch_floor_stats(d_psd, p->bins, p->bins, cn, s->d_stats, s->stream));
+      /* the recurrence continues where the previous chunk (other slot) stopped */
+      if (rc == 0 && ci > 0) rc = shim(glb_stream_wait_event(s->stream, p->slot[(ci - 1) % NSLOT].ev_agc));
+      if (rc == 0) rc = shim(glb_launch_agc(s->d_stats, cn, c0, p->cfg.overlap, dc->log_scale, p->d_agc_state, s->d_range, s->stream));
+      if (rc == 0) rc = shim(glb_event_record(s->ev_agc, s->stream));
+      if (rc) break;
+      d_range = s->d_range;
+      if (range_out) rc = shim(glb_memcpy_d2h(range_out + 2 * done, s->d_range, sizeof(float) * 2 * (size_t) cn, s->stream));
+      if (rc) break;
+    }
+    rc = shim(glb_launch_levels(d_shown, p->bins, p->bins, cn, d_range, p->d_fixed_range, dc->log_scale, thr,
+                                dc->colortab ? p->d_colortab : NULL, s->d_levels, rgb ? s->d_rgb : NULL, s->stream));
+    if (rc) break;
+    if (levels) rc = shim(glb_memcpy_d2h(levels + (size_t) done * p->bins, s->d_levels, (size_t) cn * p->bins, s->stream));
+    if (rc == 0 && rgb) rc = shim(glb_memcpy_d2h(rgb + (size_t) done * p->bins * 3, s->d_rgb, (size_t) cn * p->bins * 3, s->stream));
+    done += cn;
+    ci++;
+  }
+  for (int i = 0; i < NSLOT; i++) {
+    int r2 = shim(glb_stream_sync(p->slot[i].stream));
+    if (rc == 0) rc = r2;
+  }
+  if (rc == 0 && agc_state && dc->autoscale) rc = shim(glb_memcpy_d2h(agc_state, p->d_agc_state, 2 * sizeof(float), NULL));
+  return rc;
+}
+
+int glfer_gram_run_display(glfer_gram_plan *p, const float *samples, long long origin, long long count,
+                           long long first_frame, long long nframes, const glfer_display_config *dc,
+                           float *agc_state, unsigned char *levels, unsigned char *rgb, float *display_range)
+{
+  if (!p || !samples) return fail(GLFER_EINVAL, "null argument");
+  return run_display_impl(p, samples, NULL, origin, count, first_frame, nframes, dc, agc_state, levels, rgb, display_range);
+}
+
+int glfer_gram_run_display_pcm16(glfer_gram_plan *p, const short *pcm, long long origin, long long count,
+                                 long long first_frame, long long nframes, const glfer_display_config *dc,
+                                 float *agc_state, unsigned char *levels, unsigned char *rgb, float *display_range)
+{
+  if (!p || !pcm) return fail(GLFER_EINVAL, "null argument");
+  return run_display_impl(p, NULL, pcm, origin, count, first_frame, nframes, dc, agc_state, levels, rgb, display_range);
 }
 
 /* ---------------------------------------------------------------- time sharding */

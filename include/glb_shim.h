@@ -139,6 +139,17 @@ int glb_launch_halfcomplex_psd(const float *hc, int n, float *psd, float *phase,
 int glb_launch_floor_stats(const float *rows, long long stride, int nbins, long long nrows, float *stats,
                            void *stream);
 
+/* Display mapping of main_window_draw (g_main.c:1109-1229).  stats: [nframes][4] from
+ * glb_launch_floor_stats; state[2] = (display_max_lvl, display_min_lvl) carried between calls;
+ * range: [nframes][2] (display_max, display_min) per frame (dB in the log scales). */
+int glb_launch_agc(const float *stats, long long nframes, long long first_frame, float overlap, int log_scale,
+                   float *state, float *range, void *stream);
+/* rows -> 8-bit levels (pixel i = bin nbins-1-i) and optional RGB through a 256-entry palette.
+ * range per frame, or fixed_range[2] for all frames. */
+int glb_launch_levels(const float *rows, long long stride, int nbins, long long nframes, const float *range,
+                      const float *fixed_range, int log_scale, float thr, const unsigned char *colortab,
+                      unsigned char *levels, unsigned char *rgb, void *stream);
+
 /* counters */
 unsigned long long glb_kernel_launches(void);
 

@@ -114,6 +114,30 @@ int glfer_gram_sync(glfer_gram_plan *plan);
 int glfer_gram_fetch(glfer_gram_plan *plan, float *psd_rows, float *avg_rows, double *avg_ret,
                      int *avg_peakbin, double *avg_variance);
 
+/* ---- display mapping: what main_window_draw does with a row (g_main.c:1109-1229) ----
+ * compute_floor statistics -> AGC of the display range (autoscale) or fixed dB levels ->
+ * level = 10*log10 (through the reference's `short` level buffer: integer dB) or linear ->
+ * 8-bit palette index with threshold and clipping, pixel i = bin bins-1-i -> optional RGB.
+ * The rows shown are the averaged rows when the plan averages, else the PSD rows. */
+typedef struct {
+  int log_scale;          /* opt.scale_type is SCALE_LOG or SCALE_LOG_MAX0 (g_main.c:1132,1191) */
+  int autoscale;          /* opt.autoscale (g_main.c:1111) */
+  float max_level_db;     /* opt.max_level_db / opt.min_level_db, used when !autoscale (g_main.c:1126-1128) */
+  float min_level_db;
+  float thr_level;        /* opt.thr_level, percent (g_main.c:1098) */
+  const unsigned char *colortab;   /* 256 RGB triplets (set_palette, g_main.c:651-762) or NULL */
+} glfer_display_config;
+/* levels [nframes][bins] and/or rgb [nframes][bins][3]; display_range [nframes][2] (max, min)
+ * when autoscale (optional).  agc_state [2] = (display_max_lvl, display_min_lvl): in when
+ * first_frame > 0, out always (lets time shards chain the recurrence); may be NULL for runs
+ * that start at frame 0. */
+int glfer_gram_run_display(glfer_gram_plan *plan, const float *samples, long long origin, long long count,
+                           long long first_frame, long long nframes, const glfer_display_config *dc,
+                           float *agc_state, unsigned char *levels, unsigned char *rgb, float *display_range);
+int glfer_gram_run_display_pcm16(glfer_gram_plan *plan, const short *pcm, long long origin, long long count,
+                                 long long first_frame, long long nframes, const glfer_display_config *dc,
+                                 float *agc_state, unsigned char *levels, unsigned char *rgb, float *display_range);
+
 /* ---- time-sharded multi-GPU run inside one process (one host thread per device) ----
  * Frames [0, nframes) are split into ndev contiguous ranges; device g gets samples
  * [F_g*hop - halo, F_{g+1}*hop) (halo = N - hop, plus (depth-1) frames when averaging);

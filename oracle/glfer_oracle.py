@@ -323,6 +323,56 @@ def compute_floor(psd: np.ndarray):
     return float(srt[0]), float(floor), float(max(psd.max(), 0.0)), peak_bin
 
 
+# ------------------------------------------------------------------------ display mapping
+def display_levels(psd_rows: np.ndarray, shown_rows: np.ndarray, overlap: float, log_scale: bool, autoscale: bool,
+                   max_level_db: float = -20.0, min_level_db: float = -80.0, thr_level: float = 0.0,
+                   first_frame: int = 0, agc_state=(0.0, 0.0)):
+    """main_window_draw, g_main.c:1109-1229, without the GTK drawing.  PARITY UNPINNED: g_main.c
+    needs GTK and cannot be built here, so this restatement has no reference run behind it.
+    Per frame: compute_floor on the PSD row (:1109); AGC with float state and double
+    arithmetic (:1111-1124) or fixed levels (:1126-1128); dB range (:1132-1135); per pixel i:
+    bin n-1-i, level through the `short` level buffer in the log scales (:68,1193-1195),
+    f = 255 (level - min) / (max - min) in float (:1206), threshold / clip / scale (:1221-1229).
+    Returns (levels uint8 [F][n], range float32 [F][2], final agc state)."""
+    nf, n = shown_rows.shape
+    thr = np.float32(np.float32(thr_level) / 100.0)
+    mx_lvl, mn_lvl = np.float32(agc_state[0]), np.float32(agc_state[1])
+    levels = np.empty((nf, n), dtype=np.uint8)
+    rng = np.empty((nf, 2), dtype=np.float32)
+    ov = np.float32(overlap)
+    for f in range(nf):
+        if autoscale:
+            sig, flo, _, _ = compute_floor(psd_rows[f])
+            sig, flo = np.float32(sig), np.float32(flo)
+            if first_frame + f == 0:
+                if ov > 0.0:
+                    sig = np.float32(sig / ov)
+                    flo = np.float32(flo / ov)
+                mx_lvl, mn_lvl = sig, flo
+            else:
+                mx_lvl = np.float32((1.0 - 0.99) * float(sig) + 0.99 * float(mx_lvl))
+                mn_lvl = np.float32((1.0 - 0.99) * float(flo) + 0.99 * float(mn_lvl))
+        else:
+            mx_lvl = np.float32(10.0 ** (float(np.float32(max_level_db)) / 10.0))
+            mn_lvl = np.float32(10.0 ** (float(np.float32(min_level_db)) / 10.0))
+            mn_lvl = mn_lvl if mx_lvl > mn_lvl else np.float32(float(mx_lvl) / 10.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if log_scale:
+                dmax = np.float32(10.0 * np.log10(float(mx_lvl)))
+                dmin = np.float32(10.0 * np.log10(float(mn_lvl)))
+                d = 10.0 * np.log10(shown_rows[f][::-1].astype(np.float64))
+                sig_level = np.where(np.abs(d) < 2147483648.0, np.trunc(d), 0.0).astype(np.float32)
+            else:
+                dmax, dmin = mx_lvl, mn_lvl
+                sig_level = shown_rows[f][::-1].astype(np.float32)
+            fl = (np.float32(255) * ((sig_level - dmin) / (dmax - dmin))).astype(np.float32)
+            scaled = (fl.astype(np.float64) - 255.0 * float(thr)) / (1.0 - float(thr))
+            v = np.where(fl.astype(np.float64) < 255.0 * float(thr), 0, np.where(fl > 255, 255, np.nan_to_num(scaled)))
+        levels[f] = v.astype(np.int64).astype(np.uint8)
+        rng[f] = (dmax, dmin)
+    return levels, rng, (float(mx_lvl), float(mn_lvl))
+
+
 # ------------------------------------------------------------------------------ WAV
 def read_wav_blocks(path: str, hop: int, sub_mean: bool = False):
     """wav_fmt.c:45-121 restated for LP64 (the reference's header struct uses u_long and

@@ -336,6 +336,43 @@ def test_compute_floor(gpu_api):
         assert f.value == pytest.approx(f2, rel=1e-5)
 
 
+# ------------------------------------------------------------------ display mapping
+def test_display_levels_vs_oracle(gpu_api):
+    """rows -> 8-bit levels as main_window_draw maps them (floor statistics, AGC recurrence,
+    integer-dB level buffer, threshold, bin reversal).  Levels are compared to the restatement
+    applied to the GPU's own float rows; a pixel may differ by one step when a dB value sits
+    on an integer boundary of the `short` level buffer."""
+    x = stream(120000, seed=51)
+    n = 1024
+    pal = (np.arange(768) % 251).astype(np.uint8)
+    for kw, disp in ((dict(n=n, window_type=0, overlap=0.5, sub_mean=True), dict(log_scale=True, autoscale=True, thr_level=10.0)),
+                     (dict(n=n, window_type=7, overlap=0.75, sub_mean=True), dict(log_scale=False, autoscale=True, thr_level=0.0)),
+                     (dict(n=n, window_type=0, overlap=0.5, sub_mean=True), dict(log_scale=True, autoscale=False, max_level_db=-30.0, min_level_db=-90.0, thr_level=5.0)),
+                     (dict(n=n, window_type=0, overlap=0.5, sub_mean=True, avg_mode=2, avg_depth=4, avg_minbin=20, avg_maxbin=200),
+                      dict(log_scale=True, autoscale=True, thr_level=0.0))):
+        p = gpu_api.GramPlan(**kw)
+        r = p.run(x)
+        shown = r["avg"] if kw.get("avg_mode") else r["psd"]
+        d = p.run_display(x, colortab=pal, want_rgb=True, **disp)
+        lev, rng, state = O.display_levels(r["psd"], shown, kw["overlap"], disp["log_scale"], disp["autoscale"],
+                                           disp.get("max_level_db", -20.0), disp.get("min_level_db", -80.0), disp["thr_level"])
+        assert d["levels"].shape == lev.shape
+        diff = np.abs(d["levels"].astype(np.int32) - lev.astype(np.int32))
+        assert np.mean(diff == 0) > 0.999, (kw, disp, np.mean(diff == 0))
+        assert diff.max() <= (8 if disp["log_scale"] else 1)        # one integer-dB step of the level buffer at most
+        if disp["autoscale"]:
+            assert np.allclose(d["range"], rng, rtol=2e-5, atol=1e-3)
+            assert np.allclose(d["agc_state"], state, rtol=2e-5)
+        assert np.array_equal(d["rgb"], pal.reshape(256, 3)[d["levels"]])
+    # chaining the AGC across two calls equals one call
+    p = gpu_api.GramPlan(n=n, window_type=0, overlap=0.5, sub_mean=True)
+    full = p.run_display(x, log_scale=True, autoscale=True)
+    nf = full["levels"].shape[0]
+    a = p.run_display(x, log_scale=True, autoscale=True, nframes=nf // 2)
+    b = p.run_display(x, log_scale=True, autoscale=True, first_frame=nf // 2, nframes=nf - nf // 2, agc_state=a["agc_state"])
+    assert np.array_equal(np.concatenate([a["levels"], b["levels"]]), full["levels"])
+
+
 # ------------------------------------------------------------------ WAV source
 def test_wav_source_with_stale_tail(gpu_api, tmp_path):
     pcm = GOLD["pcm"][:8000 * 3 + 123]
