@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seconds", type=int, default=0, help="override the seconds of signal per rank")
+    ap.add_argument("--kernel-pref", type=int, default=0, help="experiment: 0 auto, 1 general, 2 ring, 3 warp-per-frame")
     ap.add_argument("--no-submean", action="store_true", help="experiment: opt.autoscale = 0 (no block-mean removal)")
     args = ap.parse_args()
 
@@ -268,6 +269,8 @@ def main():
     nsamp = hi - lo
     x_host = api.pinned_empty((nsamp,), np.float32)
     x_host[:] = synth.tiled_stream(nsamp, fs=FS, block_s=20.0, seed=0x5EED + rank)
+    if args.kernel_pref:
+        api.set_kernel_preference(args.kernel_pref)
     plan = api.GramPlan(device=local_rank, **kw)
     plan.stage(x_host, origin=lo)
     plan.sync()

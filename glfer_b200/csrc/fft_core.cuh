@@ -270,18 +270,9 @@ GLB_HD void last_pass(float2 *v, int t, const float2 *buf, const float2 *tw) {
 // Real-FFT split of one conjugate pair: given Zk = Z[k], Zm = Z[M-k] and
 // vk = -i exp(-2 pi i k / N), returns 2 X[k] in a and 2 X[M-k]^* in b
 // (scaled by whatever scale the input carried).
-#ifndef GLB_PACKED_SPLIT
-#define GLB_PACKED_SPLIT 0
-#endif
 GLB_HD void split_pair(float2 zk, float2 zm, float2 vk, float2 &a, float2 &b) {
-#if GLB_PACKED_SPLIT
-  const float2 czm = make_float2(zm.x, -zm.y);
-  float2 p = cadd(zk, czm);
-  float2 q = csub(zk, czm);
-#else
   float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
   float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
-#endif
   float2 vq = cmul(vk, q);
   a = cadd(p, vq);
   b = csub(p, vq);
@@ -480,14 +471,8 @@ GLB_HD float2 w16_mul(float2 q, int e) {
 
 // split with V_k = V_t W_16^rp rebuilt from the kept V_t
 GLB_HD void split_pair_rt(float2 zk, float2 zm, float2 v0, int rp, float2 &a, float2 &b) {
-#if GLB_PACKED_SPLIT
-  const float2 czm = make_float2(zm.x, -zm.y);
-  float2 p = cadd(zk, czm);
-  float2 q = csub(zk, czm);
-#else
   float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
   float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
-#endif
   float2 vq = cmul(v0, w16_mul(q, rp));
   a = cadd(p, vq);
   b = csub(p, vq);

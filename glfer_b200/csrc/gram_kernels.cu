@@ -198,9 +198,10 @@ struct KParams {
 #ifndef GLB_REG_TARGET
 #define GLB_REG_TARGET 80
 #endif
-#ifndef GLB_PACKED_WIN
-#define GLB_PACKED_WIN 0
+#ifndef GLB_STREAM_STORE
+#define GLB_STREAM_STORE 1
 #endif
+
 template <int M> struct Geo {
   static constexpr int N = 2 * M;
   static constexpr int T = M / kPoints;
@@ -222,6 +223,10 @@ template <int M> struct Geo {
   static constexpr int MINB_ = 65536 / (THREADS * (THREADS >= 512 ? 64 : GLB_REG_TARGET));
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
 };
+
+// Barrier over the frame groups of a CTA.  (Tried and dropped, B200: mapping a 4-warp group onto
+// one SM sub-partition with its own named barrier -- no gain over the CTA-wide barrier.)
+template <int M> __device__ __forceinline__ void group_sync(int) { __syncthreads(); }
 
 // ---- mbarrier / TMA bulk-copy helpers (1-D cp.async.bulk global -> shared) ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -297,7 +302,7 @@ __device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KPar
 // the same summation tree in every frame it appears in, so its mean is bit-identical
 // across frames (and across time shards).  Zero history sums to a zero mean.
 template <int M, int QS>
-__device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, float *red, float inv_hop) {
+__device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, float *red, float inv_hop, int g) {
   constexpr int T = M / kPoints, NW = (T + 31) / 32, NB = kPoints >> QS;
   constexpr int W = T < 32 ? T : 32;      // lanes of a warp that belong to this group
   float bs[NB];
@@ -316,7 +321,7 @@ __device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, 
 #pragma unroll
       for (int b = 0; b < NB; b++) red[b * NW + w] = bs[b];
     }
-    __syncthreads();
+    group_sync<M>(g);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
       float s = 0.f;
@@ -334,13 +339,13 @@ __device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, 
 }
 
 template <int M>
-__device__ __forceinline__ void remove_block_means_qs(float2 (&x)[kPoints], int t, float *red, const KParams &p) {
+__device__ __forceinline__ void remove_block_means_qs(float2 (&x)[kPoints], int t, float *red, const KParams &p, int g) {
   switch (p.qs) {
-    case 4: remove_block_means<M, 4>(x, t, red, p.inv_hop_mean); break;
-    case 3: remove_block_means<M, 3>(x, t, red, p.inv_hop_mean); break;
-    case 2: remove_block_means<M, 2>(x, t, red, p.inv_hop_mean); break;
-    case 1: remove_block_means<M, 1>(x, t, red, p.inv_hop_mean); break;
-    default: remove_block_means<M, 0>(x, t, red, p.inv_hop_mean); break;
+    case 4: remove_block_means<M, 4>(x, t, red, p.inv_hop_mean, g); break;
+    case 3: remove_block_means<M, 3>(x, t, red, p.inv_hop_mean, g); break;
+    case 2: remove_block_means<M, 2>(x, t, red, p.inv_hop_mean, g); break;
+    case 1: remove_block_means<M, 1>(x, t, red, p.inv_hop_mean, g); break;
+    default: remove_block_means<M, 0>(x, t, red, p.inv_hop_mean, g); break;
   }
 }
 
@@ -370,11 +375,7 @@ __device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (
 #pragma unroll
     for (int q = 0; q < kPoints; q++) {
       const float2 w = ldg2(w2 + t + T * q);
-#if GLB_PACKED_WIN
-      v[q] = emul(x[q], w);
-#else
-      v[q] = make_float2(x[q].x * w.x, x[q].y * w.y);
-#endif
+      v[q] = make_float2(x[q].x * w.x, x[q].y * w.y);     // (packed FMUL2 here measured slower)
     }
     return;
   }
@@ -397,19 +398,19 @@ __device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (
 }
 
 template <int M, int P, bool RT> struct MidPasses {
-  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr) {
+  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr, int g) {
     if constexpr (P < Plan<M>::NP - 1) {
       pass_load<M>(v, t, buf);
       if constexpr (RT) {
         pass_compute_rt<M, P>(v, tr);
-        __syncthreads();               // every thread has read before anyone overwrites
+        group_sync<M>(g);               // every thread has read before anyone overwrites
         pass_scatter<M, P>(v, t, buf);
       } else {
-        __syncthreads();
+        group_sync<M>(g);
         pass_store<M, P>(v, t, buf, tw);
       }
-      __syncthreads();
-      MidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr);
+      group_sync<M>(g);
+      MidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, g);
     }
   }
 };
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 #pragma unroll
             for (int q = 0; q < kPoints; q++) x[q] = make_float2(0.f, 0.f);
           }
-          if (p.fused_mean) remove_block_means_qs<M>(x, t, red, p);
+          if (p.fused_mean) remove_block_means_qs<M>(x, t, red, p, g);
           else if (p.means != nullptr && active) remove_table_means<M>(x, t, p, f);
           if (MULTI && STAGE && ntap > 1) {
             float2 *s2 = reinterpret_cast<float2 *>(stage);
@@ -504,10 +505,10 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
       }
       if constexpr (RT) {
         pass_compute_rt<M, 0>(v, tr);
-        __syncthreads();               // (A) the previous transform's last pass has been read by all
+        group_sync<M>(g);              // (A) the previous transform's last pass has been read by all
         pass_scatter<M, 0>(v, t, buf);
       } else {
-        __syncthreads();
+        group_sync<M>(g);
         pass_store<M, 0>(v, t, buf, p.tw);
       }
       if (STAGE && next_staged && j == ntap - 1 && t == 0) {
@@ -516,8 +517,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
         mbar_expect_tx(mbar, N * 4);
         tma_load_1d(stage, p.samples + ((f + 1) * (long long) p.hop - p.n_ov - p.origin), N * 4, mbar);
       }
-      __syncthreads();
-      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr);
+      group_sync<M>(g);
+      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
       float *row = (!MULTI && active && p.rows) ? p.rows + fl * p.row_stride : nullptr;
       float2 *sp = (!MULTI && active && p.spectrum) ? p.spectrum + fl * (long long) (M + 1) : nullptr;
@@ -590,26 +591,9 @@ __host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
 // shuffle, the group combines through `red` (one barrier).  The summation tree of a block is
 // the same wherever the block sits in a frame: its mean is bit-identical in every frame, group
 // and time shard.  Must be called by all threads of the CTA (contains a block barrier).
-#ifndef GLB_MEAN_PER_WARP
-#define GLB_MEAN_PER_WARP 0
-#endif
 template <int M>
 __device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
   constexpr int T = M / kPoints, NW = (T + 31) / 32, W = T < 32 ? T : 32;
-  if (GLB_MEAN_PER_WARP && NW > 1) {
-    // every warp sums the whole block on its own (hop/32 floats per lane, 128-bit loads):
-    // a little redundant shared-memory traffic instead of a block barrier per frame
-    const int hop = (2 * T) << qs;
-    const float4 *b4 = reinterpret_cast<const float4 *>(blk);
-    float s = 0.f;
-    for (int i = (t & 31); i < hop / 4; i += 32) {
-      const float4 a = b4[i];
-      s += (a.x + a.y) + (a.z + a.w);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return s * inv_hop;
-  }
   const float2 *b2 = reinterpret_cast<const float2 *>(blk);
   float s = 0.f;
   for (int i = 0; i < (1 << qs); i++) {
@@ -640,11 +624,7 @@ __device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const flo
 #pragma unroll
     for (int i = 0; i < (1 << QS); i++) {
       const float2 a = bp[t + T * i];
-#if GLB_PACKED_WIN
-      x[(b << QS) + i] = csub(a, make_float2(m, m));
-#else
       x[(b << QS) + i] = make_float2(a.x - m, a.y - m);
-#endif
     }
     sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
   }
@@ -771,14 +751,18 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
       // tight ring: past (A) of the last taper nobody reads the oldest block any more
       if (!GLB_RING_EXTRA && next_there && j == ntap - 1 && t == 0) request_next();
       __syncthreads();
-      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr);
+      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
       float *row = p.rows + fl * p.row_stride;
       const bool db = p.rows_db != 0;
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
       auto sink_single = [&](int slot, float2 a, bool) {
         float y = norm2(a);
         if (db) y = 10.f * log10f(y);
+#if GLB_STREAM_STORE
+        if (active) __stcs(row + slot_bin<M>(t, slot), y);
+#else
         if (active) row[slot_bin<M>(t, slot)] = y;
+#endif
       };
       if constexpr (RT) {
         last_pass_rt<M>(v, t, buf, p.tw, tr);
@@ -1002,7 +986,7 @@ static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
         }
         // big frames: the ring must not cost more residency than it saves in traffic
         int occ_generic_bound = (int) ((227 * 1024) / GeoM::smem_bytes(false));
-        const bool worth = occ >= 2 || (occ >= 1 && occ_generic_bound <= 1) || GeoM::THREADS >= 1024;
+        const bool worth = occ >= 2 || (occ >= 1 && occ_generic_bound <= 1) || GeoM::THREADS >= 1024 || g_kernel_pref == 2;
         if (occ >= 1 && worth) {
           long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
           if (groups > kp.nframes) groups = kp.nframes;
