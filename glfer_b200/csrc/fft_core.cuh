@@ -66,40 +66,84 @@ template <int M> struct TwOffset<M, 0> { static constexpr int value = 0; };
 template <int M> struct TwTotal { static constexpr int value = TwOffset<M, Plan<M>::NP>::value; };
 
 // ------------------------------------------------------------------ complex helpers
-// Complex add / subtract.  On sm_100a (device code, GLB_PACKED_ADD) they are single packed
-// instructions (FADD2 on an aligned register pair): half the issue slots of the scalar form.
-#if !defined(GLB_PACKED_ADD)
-#define GLB_PACKED_ADD 1
+// A complex value is one float2 = one aligned 64-bit register pair (re, im).  On sm_100a the
+// FP32 pipe has packed two-lane instructions (FADD2 / FMUL2 / FFMA2: PTX add/mul/fma.rn.f32x2)
+// whose SASS operands can be the pair as it is, the pair with its halves swapped, one 32-bit
+// register broadcast to both lanes, or a broadcast immediate, each optionally negated -- ptxas
+// folds swp(), bc() and neg() below into those operand forms.  With them every step of a
+// complex FFT is a packed instruction on the natural (re, im) pair:
+//   a + b, a - b                      one FADD2
+//   a -/+ i b                         one FFMA2: swp(b) * (1,-1) + a
+//   a * w, w kept as (wr, (-wi, wi))  two: FMUL2 swp(a) * q, FFMA2 a * bc(wr) + t
+// i.e. half the issue slots of the scalar form at the same FP32 lane throughput.
+#if !defined(GLB_PACKED)
+#define GLB_PACKED 1
 #endif
-#if defined(__CUDA_ARCH__) && GLB_PACKED_ADD
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && GLB_PACKED
+#define GLB_U64(x) (*reinterpret_cast<unsigned long long *>(&(x)))
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
   float2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&r))
-      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(GLB_U64(r)) : "l"(GLB_U64(a)), "l"(GLB_U64(b)));
   return r;
 }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
   float2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&r))
-      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(GLB_U64(r)) : "l"(GLB_U64(a)), "l"(GLB_U64(b)));
   return r;
 }
-// component-wise product (window / taper multiply): one FMUL2
-__device__ __forceinline__ float2 emul(float2 a, float2 b) {
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   float2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long *>(&r))
-      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(GLB_U64(r)) : "l"(GLB_U64(a)), "l"(GLB_U64(b)));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(GLB_U64(r)) : "l"(GLB_U64(a)), "l"(GLB_U64(b)), "l"(GLB_U64(c)));
   return r;
 }
 #else
-GLB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-GLB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-GLB_HD float2 emul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+GLB_HD float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+GLB_HD float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+GLB_HD float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#if defined(__CUDA_ARCH__)
+GLB_HD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+GLB_HD float2 fma2(float2 a, float2 b, float2 c) { return make_float2(std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)); }
 #endif
-GLB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-GLB_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
-GLB_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
-GLB_HD float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
+#endif
+GLB_HD float2 swp(float2 a) { return make_float2(a.y, a.x); }       // operand form .LO_HI
+GLB_HD float2 bc(float s) { return make_float2(s, s); }             // operand form .F32 / immediate
+GLB_HD float2 neg(float2 a) { return make_float2(-a.x, -a.y); }     // operand negation
+GLB_HD float2 pm() { return make_float2(1.f, -1.f); }
+GLB_HD float2 mp() { return make_float2(-1.f, 1.f); }
+
+GLB_HD float2 cadd(float2 a, float2 b) { return add2(a, b); }
+GLB_HD float2 csub(float2 a, float2 b) { return sub2(a, b); }
+GLB_HD float2 emul(float2 a, float2 b) { return mul2(a, b); }        // component-wise (window / taper)
+GLB_HD float2 add_mi(float2 a, float2 b) { return fma2(swp(b), pm(), a); }   // a - i b
+GLB_HD float2 add_pi(float2 a, float2 b) { return fma2(swp(b), mp(), a); }   // a + i b
+GLB_HD float2 mul_mi(float2 a) { return mul2(swp(a), pm()); }        // a * (-i)
+GLB_HD float2 mul_pi(float2 a) { return mul2(swp(a), mp()); }        // a * (+i)
+// a * w and a * conj(w) with w as a plain (re, im) pair: three packed instructions
+GLB_HD float2 cmul(float2 a, float2 w) { return fma2(mul2(swp(a), bc(w.y)), mp(), mul2(a, bc(w.x))); }
+GLB_HD float2 cmulc(float2 a, float2 w) { return fma2(mul2(swp(a), bc(w.y)), pm(), mul2(a, bc(w.x))); }
+// a * w with a compile-time constant w = (WR, WI): two packed instructions
+#define GLB_CMULK(a, WR, WI) fma2((a), bc(WR), mul2(swp(a), make_float2(-(WI), (WI))))
+
+// A twiddle kept in registers across frames: wr and the pair (-wi, wi); a * w and a * conj(w)
+// are then two packed instructions each.
+struct Tw3 {
+  float r;
+  float2 q;
+};
+GLB_HD Tw3 make_tw3(float2 w) {
+  Tw3 t;
+  t.r = w.x;
+  t.q = make_float2(-w.y, w.y);
+  return t;
+}
+GLB_HD float2 cmul(float2 a, const Tw3 &w) { return fma2(a, bc(w.r), mul2(swp(a), w.q)); }
+GLB_HD float2 cmulc(float2 a, const Tw3 &w) { return fma2(a, bc(w.r), neg(mul2(swp(a), w.q))); }
 
 // Padded float2 index: 2 spare entries after every 16 (16 B alignment of even entries is
 // kept, so pairs can move as one 128-bit access).  pad(a + c) = pad(a) + c + c/8 whenever
@@ -118,32 +162,33 @@ template <int S> GLB_HD void dft2(float2 *v) {
 
 template <int S> GLB_HD void dft4(float2 *v) {
   float2 a = v[0], b = v[S], c = v[2 * S], d = v[3 * S];
-  float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
-  v[0] = cadd(apc, bpd);
-  v[S] = cadd(amc, mul_mi(bmd));
-  v[2 * S] = csub(apc, bpd);
-  v[3 * S] = cadd(amc, mul_pi(bmd));
+  float2 apc = add2(a, c), amc = sub2(a, c), bpd = add2(b, d), bmd = sub2(b, d);
+  v[0] = add2(apc, bpd);
+  v[S] = add_mi(amc, bmd);
+  v[2 * S] = sub2(apc, bpd);
+  v[3 * S] = add_pi(amc, bmd);
 }
 
+// 26 packed instructions: the W8 factors are folded into the last butterflies
 template <int S> GLB_HD void dft8(float2 *v) {
   const float h = 0.70710678118654752440f;
   float2 e[4] = {v[0], v[2 * S], v[4 * S], v[6 * S]};
   float2 o[4] = {v[S], v[3 * S], v[5 * S], v[7 * S]};
   dft4<1>(e);
   dft4<1>(o);
-  float2 o1 = make_float2((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h);      // * W8^1
-  float2 o2 = mul_mi(o[2]);                                                    // * W8^2
-  float2 o3 = make_float2((o[3].y - o[3].x) * h, -(o[3].x + o[3].y) * h);     // * W8^3
-  v[0] = cadd(e[0], o[0]);
-  v[4 * S] = csub(e[0], o[0]);
-  v[S] = cadd(e[1], o1);
-  v[5 * S] = csub(e[1], o1);
-  v[2 * S] = cadd(e[2], o2);
-  v[6 * S] = csub(e[2], o2);
-  v[3 * S] = cadd(e[3], o3);
-  v[7 * S] = csub(e[3], o3);
+  const float2 s1 = fma2(swp(o[1]), pm(), o[1]);        // (x + y, y - x)   = o1 W8^1 / h
+  const float2 s3 = fma2(swp(o[3]), pm(), neg(o[3]));   // (y - x, -x - y)  = o3 W8^3 / h
+  v[0] = add2(e[0], o[0]);
+  v[4 * S] = sub2(e[0], o[0]);
+  v[S] = fma2(s1, bc(h), e[1]);
+  v[5 * S] = fma2(s1, bc(-h), e[1]);
+  v[2 * S] = add_mi(e[2], o[2]);
+  v[6 * S] = add_pi(e[2], o[2]);
+  v[3 * S] = fma2(s3, bc(h), e[3]);
+  v[7 * S] = fma2(s3, bc(-h), e[3]);
 }
 
+// 81 packed instructions
 template <int S> GLB_HD void dft16(float2 *v) {
   // n = 4 n1 + n2, k = k1 + 4 k2
   const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;   // cos, sin(pi/8)
@@ -156,15 +201,15 @@ template <int S> GLB_HD void dft16(float2 *v) {
     y[n2][0] = t[0]; y[n2][1] = t[1]; y[n2][2] = t[2]; y[n2][3] = t[3];
   }
   // twiddle y[n2][k1] *= W16^(n2 k1), W16^e = exp(-2 pi i e / 16)
-  y[1][1] = cmul(y[1][1], make_float2(c1, -s1));                                  // e = 1
-  y[1][2] = make_float2((y[1][2].x + y[1][2].y) * h, (y[1][2].y - y[1][2].x) * h);  // e = 2
-  y[1][3] = cmul(y[1][3], make_float2(s1, -c1));                                  // e = 3
-  y[2][1] = make_float2((y[2][1].x + y[2][1].y) * h, (y[2][1].y - y[2][1].x) * h);  // e = 2
-  y[2][2] = mul_mi(y[2][2]);                                                      // e = 4
-  y[2][3] = make_float2((y[2][3].y - y[2][3].x) * h, -(y[2][3].x + y[2][3].y) * h); // e = 6
-  y[3][1] = cmul(y[3][1], make_float2(s1, -c1));                                  // e = 3
-  y[3][2] = make_float2((y[3][2].y - y[3][2].x) * h, -(y[3][2].x + y[3][2].y) * h); // e = 6
-  y[3][3] = cmul(y[3][3], make_float2(-c1, s1));                                  // e = 9
+  y[1][1] = GLB_CMULK(y[1][1], c1, -s1);     // e = 1
+  y[1][2] = GLB_CMULK(y[1][2], h, -h);       // e = 2
+  y[1][3] = GLB_CMULK(y[1][3], s1, -c1);     // e = 3
+  y[2][1] = GLB_CMULK(y[2][1], h, -h);       // e = 2
+  y[2][2] = mul_mi(y[2][2]);                 // e = 4
+  y[2][3] = GLB_CMULK(y[2][3], -h, -h);      // e = 6
+  y[3][1] = GLB_CMULK(y[3][1], s1, -c1);     // e = 3
+  y[3][2] = GLB_CMULK(y[3][2], -h, -h);      // e = 6
+  y[3][3] = GLB_CMULK(y[3][3], -c1, s1);     // e = 9
 #pragma unroll
   for (int k1 = 0; k1 < 4; k1++) {
     float2 t[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
@@ -271,11 +316,11 @@ GLB_HD void last_pass(float2 *v, int t, const float2 *buf, const float2 *tw) {
 // vk = -i exp(-2 pi i k / N), returns 2 X[k] in a and 2 X[M-k]^* in b
 // (scaled by whatever scale the input carried).
 GLB_HD void split_pair(float2 zk, float2 zm, float2 vk, float2 &a, float2 &b) {
-  float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
-  float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
-  float2 vq = cmul(vk, q);
-  a = cadd(p, vq);
-  b = csub(p, vq);
+  float2 p = fma2(zm, pm(), zk);      // (zk.x + zm.x, zk.y - zm.y)
+  float2 q = fma2(zm, mp(), zk);      // (zk.x - zm.x, zk.y + zm.y)
+  float2 vq = cmul(q, vk);
+  a = add2(p, vq);
+  b = sub2(p, vq);
 }
 
 GLB_HD float norm2(float2 a) { return a.x * a.x + a.y * a.y; }
@@ -298,10 +343,17 @@ template <> struct TwBases<4> { static constexpr int n = 3; };
 template <> struct TwBases<2> { static constexpr int n = 1; };
 template <> struct TwBases<1> { static constexpr int n = 0; };
 
+// first bin of the upper four pairs of thread t (see "bins of the final pass" below)
+template <int M> GLB_HD int khi(int t) {
+  constexpr int T = M / kPoints;
+  return t != 0 ? t + 8 * T : T;
+}
+
 struct TwRegs {
-  float2 mid[2][12];   // passes 1 and 2 (when they are not the last): [u * nbases + i]
-  float2 last[4];      // w_a^1..w_a^4, w_a = W_M^t
-  float2 v0;           // V_t = -i exp(-2 pi i t / N)
+  Tw3 mid[2][12];   // passes 1 and 2 (when they are not the last): [u * nbases + i]
+  Tw3 last[4];      // w_a^1..w_a^4, w_a = W_M^t
+  Tw3 v0;           // V_t = -i exp(-2 pi i t / N): split factor of the pairs rp < 4 (times W_16^rp)
+  Tw3 v0hi;         // V_khi(t): pairs rp >= 4 (times W_16^(rp-4))
 };
 
 template <int M, int P>
@@ -316,10 +368,10 @@ GLB_HD void load_mid_bases(TwRegs &tr, int t, const float2 *tw) {
       if constexpr (R == 16) {
         const int e[6] = {1, 2, 3, 4, 8, 12};
 #pragma unroll
-        for (int i = 0; i < 6; i++) tr.mid[P - 1][u * NB + i] = twp[(e[i] - 1) * Ns];
+        for (int i = 0; i < 6; i++) tr.mid[P - 1][u * NB + i] = make_tw3(twp[(e[i] - 1) * Ns]);
       } else {
 #pragma unroll
-        for (int i = 0; i < NB; i++) tr.mid[P - 1][u * NB + i] = twp[i * Ns];
+        for (int i = 0; i < NB; i++) tr.mid[P - 1][u * NB + i] = make_tw3(twp[i * Ns]);
       }
     }
   }
@@ -332,39 +384,39 @@ GLB_HD void load_tw_regs(TwRegs &tr, int t, const float2 *tw, const float2 *vtab
   load_mid_bases<M, 2>(tr, t, tw);
   const float2 *twA = tw + TwOffset<M, NP - 1>::value + t;
 #pragma unroll
-  for (int i = 0; i < 4; i++) tr.last[i] = twA[i * 2 * T];
-  tr.v0 = vtab[t];
+  for (int i = 0; i < 4; i++) tr.last[i] = make_tw3(twA[i * 2 * T]);
+  tr.v0 = make_tw3(vtab[t]);
+  tr.v0hi = make_tw3(vtab[khi<M>(t)]);
 }
 
-// v[u + r S] *= w^r for r = 1..R-1 from the kept bases
+// v[u + r S] *= w^r for r = 1..R-1 from the kept bases; w^(4a+b) is applied as two successive
+// multiplications (w^(4a) then w^b): no derived twiddle is ever formed
 template <int R, int S>
-GLB_HD void apply_tw_bases(float2 *v, const float2 *b) {
+GLB_HD void apply_tw_bases(float2 *v, const Tw3 *b) {
   if constexpr (R == 16) {
-    const float2 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3], w8 = b[4], w12 = b[5];
-    v[1 * S] = cmul(v[1 * S], w1);
-    v[2 * S] = cmul(v[2 * S], w2);
-    v[3 * S] = cmul(v[3 * S], w3);
-    v[4 * S] = cmul(v[4 * S], w4);
-    v[5 * S] = cmul(v[5 * S], cmul(w4, w1));
-    v[6 * S] = cmul(v[6 * S], cmul(w4, w2));
-    v[7 * S] = cmul(v[7 * S], cmul(w4, w3));
-    v[8 * S] = cmul(v[8 * S], w8);
-    v[9 * S] = cmul(v[9 * S], cmul(w8, w1));
-    v[10 * S] = cmul(v[10 * S], cmul(w8, w2));
-    v[11 * S] = cmul(v[11 * S], cmul(w8, w3));
-    v[12 * S] = cmul(v[12 * S], w12);
-    v[13 * S] = cmul(v[13 * S], cmul(w12, w1));
-    v[14 * S] = cmul(v[14 * S], cmul(w12, w2));
-    v[15 * S] = cmul(v[15 * S], cmul(w12, w3));
+    const Tw3 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3], w8 = b[4], w12 = b[5];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      v[(4 + l) * S] = cmul(v[(4 + l) * S], w4);
+      v[(8 + l) * S] = cmul(v[(8 + l) * S], w8);
+      v[(12 + l) * S] = cmul(v[(12 + l) * S], w12);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      v[(4 * a + 1) * S] = cmul(v[(4 * a + 1) * S], w1);
+      v[(4 * a + 2) * S] = cmul(v[(4 * a + 2) * S], w2);
+      v[(4 * a + 3) * S] = cmul(v[(4 * a + 3) * S], w3);
+    }
   } else if constexpr (R == 8) {
-    const float2 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3];
-    v[1 * S] = cmul(v[1 * S], w1);
-    v[2 * S] = cmul(v[2 * S], w2);
-    v[3 * S] = cmul(v[3 * S], w3);
-    v[4 * S] = cmul(v[4 * S], w4);
-    v[5 * S] = cmul(v[5 * S], cmul(w4, w1));
-    v[6 * S] = cmul(v[6 * S], cmul(w4, w2));
-    v[7 * S] = cmul(v[7 * S], cmul(w4, w3));
+    const Tw3 w1 = b[0], w2 = b[1], w3 = b[2], w4 = b[3];
+#pragma unroll
+    for (int l = 0; l < 4; l++) v[(4 + l) * S] = cmul(v[(4 + l) * S], w4);
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      v[(4 * a + 1) * S] = cmul(v[(4 * a + 1) * S], w1);
+      v[(4 * a + 2) * S] = cmul(v[(4 * a + 2) * S], w2);
+      v[(4 * a + 3) * S] = cmul(v[(4 * a + 3) * S], w3);
+    }
   } else if constexpr (R == 4) {
     v[1 * S] = cmul(v[1 * S], b[0]);
     v[2 * S] = cmul(v[2 * S], b[1]);
@@ -410,6 +462,35 @@ GLB_HD void pass_scatter(const float2 *v, int t, float2 *buf) {
   }
 }
 
+GLB_HD float2 w16_mul(float2 q, int e) {
+  // q * exp(-2 pi i e / 16), e = 0..7, constants folded after unrolling
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  switch (e) {
+    case 0: return q;
+    case 1: return GLB_CMULK(q, c1, -s1);
+    case 2: return GLB_CMULK(q, h, -h);
+    case 3: return GLB_CMULK(q, s1, -c1);
+    case 4: return mul_mi(q);
+    case 5: return GLB_CMULK(q, -s1, -c1);
+    case 6: return GLB_CMULK(q, -h, -h);
+    default: return GLB_CMULK(q, -c1, -s1);
+  }
+}
+GLB_HD float2 w16_mulc(float2 q, int e) {
+  // q * exp(+2 pi i e / 16)
+  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  switch (e) {
+    case 0: return q;
+    case 1: return GLB_CMULK(q, c1, s1);
+    case 2: return GLB_CMULK(q, h, h);
+    case 3: return GLB_CMULK(q, s1, c1);
+    case 4: return mul_pi(q);
+    case 5: return GLB_CMULK(q, -s1, c1);
+    case 6: return GLB_CMULK(q, -h, h);
+    default: return GLB_CMULK(q, -c1, s1);
+  }
+}
+
 // last pass with register twiddles; on return v[r'] = Z[jA + r' 2T], v[8 + r'] = Z[jB + r' 2T]
 template <int M>
 GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, const TwRegs &tr) {
@@ -430,141 +511,112 @@ GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, 
       v[8 + r] = buf[pad(jB + r * Ns)];
     }
   }
-  const float2 w1 = tr.last[0], w2 = tr.last[1], w3 = tr.last[2], w4 = tr.last[3];
-  const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
-  const float2 w[8] = {make_float2(1.f, 0.f), w1, w2, w3, w4, w5, w6, w7};
+  const Tw3 w1 = tr.last[0], w2 = tr.last[1], w3 = tr.last[2], w4 = tr.last[3];
+  // A: x_r w_a^r, w_a^(4+b) applied as w_a^4 then w_a^b
 #pragma unroll
-  for (int r = 1; r < 8; r++) v[r] = cmul(v[r], w[r]);
+  for (int l = 0; l < 4; l++) v[4 + l] = cmul(v[4 + l], w4);
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    v[4 * a + 1] = cmul(v[4 * a + 1], w1);
+    v[4 * a + 2] = cmul(v[4 * a + 2], w2);
+    v[4 * a + 3] = cmul(v[4 * a + 3], w3);
+  }
   dft8<1>(v);
-  if (t != 0) {
-    // B: x_r conj(w_a^r), DFT8, outputs shifted by one place
-    float2 y[8];
-    y[0] = v[8];
+  // B = butterfly 2T - t: x_r conj(w_a^r), DFT8, outputs shifted by one place (the W_8^r factor).
+  // Thread 0 holds butterfly T instead (twiddles W_16^r, w_a = 1): pre-multiplying its inputs by
+  // conj(W_16^r) = W_16^r W_8^-r lets it share the code below, shift included.
+  float2 y[8];
 #pragma unroll
-    for (int r = 1; r < 8; r++) y[r] = cmulc(v[8 + r], w[r]);
-    dft8<1>(y);
+  for (int r = 0; r < 8; r++) y[r] = v[8 + r];
+  if (t == 0) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[8 + r] = y[(r + 1) & 7];
-  } else {
-    // thread 0: butterfly T, twiddles W_M^(T r) = W_16^r from the table
-    const float2 *twB = tw + TwOffset<M, NP - 1>::value + T;
-#pragma unroll
-    for (int r = 1; r < 8; r++) v[8 + r] = cmul(v[8 + r], twB[(r - 1) * Ns]);
-    dft8<1>(v + 8);
+    for (int r = 1; r < 8; r++) y[r] = w16_mulc(y[r], r);
   }
-}
-
-GLB_HD float2 w16_mul(float2 q, int e) {
-  // q * exp(-2 pi i e / 16), e = 0..7, constants folded after unrolling
-  const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
-  switch (e) {
-    case 0: return q;
-    case 1: return cmul(q, make_float2(c1, -s1));
-    case 2: return make_float2((q.x + q.y) * h, (q.y - q.x) * h);
-    case 3: return cmul(q, make_float2(s1, -c1));
-    case 4: return mul_mi(q);
-    case 5: return cmul(q, make_float2(-s1, -c1));
-    case 6: return make_float2((q.y - q.x) * h, -(q.x + q.y) * h);
-    default: return cmul(q, make_float2(-c1, -s1));
+#pragma unroll
+  for (int l = 0; l < 4; l++) y[4 + l] = cmulc(y[4 + l], w4);
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    y[4 * a + 1] = cmulc(y[4 * a + 1], w1);
+    y[4 * a + 2] = cmulc(y[4 * a + 2], w2);
+    y[4 * a + 3] = cmulc(y[4 * a + 3], w3);
   }
+  dft8<1>(y);
+#pragma unroll
+  for (int r = 0; r < 8; r++) v[8 + r] = y[(r + 1) & 7];
 }
 
-// split with V_k = V_t W_16^rp rebuilt from the kept V_t
-GLB_HD void split_pair_rt(float2 zk, float2 zm, float2 v0, int rp, float2 &a, float2 &b) {
-  float2 p = make_float2(zk.x + zm.x, zk.y - zm.y);
-  float2 q = make_float2(zk.x - zm.x, zk.y + zm.y);
-  float2 vq = cmul(v0, w16_mul(q, rp));
-  a = cadd(p, vq);
-  b = csub(p, vq);
-}
-
-template <int M, class F>
-GLB_HD void emit_bins_rt(const float2 *v, int t, const float2 *vtab, const TwRegs &tr, F &&f) {
-  constexpr int T = M / kPoints;
-  float2 a, b;
-  if (t != 0) {
-#pragma unroll
-    for (int rp = 0; rp < 8; rp++) {
-      split_pair_rt(v[rp], v[8 + 7 - rp], tr.v0, rp, a, b);
-      f(2 * rp, a, false);
-      f(2 * rp + 1, b, true);
-    }
-  } else {
-    split_pair(v[0], v[0], vtab[0], a, b);
-    f(0, a, false);
-    f(1, b, true);
-#pragma unroll
-    for (int rp = 1; rp < 4; rp++) {
-      split_pair(v[rp], v[8 - rp], vtab[rp * 2 * T], a, b);
-      f(2 * rp, a, false);
-      f(2 * rp + 1, b, true);
-    }
-    split_pair(v[4], v[4], vtab[M / 2], a, b);
-    f(8, a, false);
-#pragma unroll
-    for (int rp = 0; rp < 4; rp++) {
-      split_pair(v[8 + rp], v[8 + 7 - rp], vtab[T + rp * 2 * T], a, b);
-      f(9 + 2 * rp, a, false);
-      f(10 + 2 * rp, b, true);
-    }
-  }
-}
-
-// Bin bookkeeping of the final pass.  For thread t >= 1 pair r' (0..7) is
-// (Z[k], Z[M-k]) with k = t + r' 2T held in (v[r'], v[8 + 7 - r']).  Thread 0 pairs
-// inside each butterfly: A: (v[r'], v[(8 - r') & 7]) k = r' 2T, r' = 0..4 (k = 0 and
-// k = M/2 are self-paired); B: (v[8 + r'], v[8 + 7 - r']) k = T + r' 2T, r' = 0..3.
-// Results are numbered by "slot": a thread owns slots 0..15 (thread 0: 0..16) and
-// slot_bin() gives the PSD bin of a slot, so accumulators can live in registers
-// across tapers.  Every bin 0..M belongs to exactly one (thread, slot).
+// ------------------------------------------------------------------ bins of the final pass
+// After the last pass thread t >= 1 holds butterflies A = t and B = 2T - t: pair rp (0..7) is
+// (Z[k], Z[M-k]) with k = t + rp 2T in (v[rp], v[15 - rp]).  Thread 0 holds the two self-paired
+// butterflies 0 and T; thread0_fixup() re-orders its registers so that the same 8 (v[rp],
+// v[15 - rp]) pairs are (Z[k], Z[M-k]) for k = rp 2T (rp < 4) and k = T + (rp - 4) 2T (rp >= 4),
+// and returns the one value left over, Z[M/2].  All threads then run the same split code; only
+// the base index of the upper four pairs differs (khi).  Results are numbered by "slot": slot
+// 2 rp is bin k, slot 2 rp + 1 is bin M - k, slot 16 (thread 0 only) is bin M/2, so accumulators
+// can live in registers across tapers.  Every bin 0..M belongs to exactly one (thread, slot).
 template <int M> GLB_HD int slot_bin(int t, int slot) {
   constexpr int T = M / kPoints;
-  if (t != 0) {
-    const int k = t + (slot >> 1) * 2 * T;
-    return (slot & 1) ? M - k : k;
-  }
-  if (slot < 8) {
-    const int k = (slot >> 1) * 2 * T;
-    return (slot & 1) ? M - k : k;
-  }
-  if (slot == 8) return M / 2;
-  const int k = T + ((slot - 9) >> 1) * 2 * T;
-  return ((slot - 9) & 1) ? M - k : k;
+  if (slot == 16) return M / 2;
+  const int rp = slot >> 1;
+  const int k = rp < 4 ? t + rp * 2 * T : khi<M>(t) + (rp - 4) * 2 * T;
+  return (slot & 1) ? M - k : k;
 }
 template <int M> GLB_HD int slot_count(int t) { return t != 0 ? 16 : 17; }
 
-// f(slot, value, conjugated): value = 2 X[slot_bin(t, slot)] (conjugated when the flag
-// is set), still carrying the scale folded into the taper.
+GLB_HD float2 thread0_fixup(float2 *v) {
+  const float2 a4 = v[4];
+  const float2 a5 = v[5], a6 = v[6], a7 = v[7], a0 = v[0];
+#pragma unroll
+  for (int r = 0; r < 8; r++) v[4 + r] = v[8 + r];      // B0..B7 -> v[4..11]
+  v[12] = a5;
+  v[13] = a6;
+  v[14] = a7;
+  v[15] = a0;
+  return a4;
+}
+
+// split with V_k = vb W_16^e rebuilt from a kept base factor
+GLB_HD void split_pair_rt(float2 zk, float2 zm, const Tw3 &vb, int e, float2 &a, float2 &b) {
+  float2 p = fma2(zm, pm(), zk);      // (zk.x + zm.x, zk.y - zm.y)
+  float2 q = fma2(zm, mp(), zk);      // (zk.x - zm.x, zk.y + zm.y)
+  float2 vq = cmul(w16_mul(q, e), vb);
+  a = add2(p, vq);
+  b = sub2(p, vq);
+}
+
+// f(slot, value, conjugated): value = 2 X[slot_bin(t, slot)] (conjugated when the flag is set),
+// still carrying the scale folded into the taper.
 template <int M, class F>
-GLB_HD void emit_bins(const float2 *v, int t, const float2 *vtab, F &&f) {
+GLB_HD void emit_bins_rt(float2 *v, int t, const TwRegs &tr, F &&f) {
+  float2 a, b;
+  if (t == 0) {
+    const float2 z = thread0_fixup(v);                  // X[M/2] = conj(Z[M/2])
+    f(16, make_float2(2.f * z.x, -2.f * z.y), false);
+  }
+#pragma unroll
+  for (int rp = 0; rp < 8; rp++) {
+    if (rp < 4) split_pair_rt(v[rp], v[15 - rp], tr.v0, rp, a, b);
+    else split_pair_rt(v[rp], v[15 - rp], tr.v0hi, rp - 4, a, b);
+    f(2 * rp, a, false);
+    f(2 * rp + 1, b, true);
+  }
+}
+
+template <int M, class F>
+GLB_HD void emit_bins(float2 *v, int t, const float2 *vtab, F &&f) {
   constexpr int T = M / kPoints;
   float2 a, b;
-  if (t != 0) {
+  if (t == 0) {
+    const float2 z = thread0_fixup(v);
+    f(16, make_float2(2.f * z.x, -2.f * z.y), false);
+  }
+  const int kh = khi<M>(t);
 #pragma unroll
-    for (int rp = 0; rp < 8; rp++) {
-      const int k = t + rp * 2 * T;
-      split_pair(v[rp], v[8 + 7 - rp], vtab[k], a, b);
-      f(2 * rp, a, false);
-      f(2 * rp + 1, b, true);
-    }
-  } else {
-    split_pair(v[0], v[0], vtab[0], a, b);
-    f(0, a, false);
-    f(1, b, true);
-#pragma unroll
-    for (int rp = 1; rp < 4; rp++) {
-      split_pair(v[rp], v[8 - rp], vtab[rp * 2 * T], a, b);
-      f(2 * rp, a, false);
-      f(2 * rp + 1, b, true);
-    }
-    split_pair(v[4], v[4], vtab[M / 2], a, b);
-    f(8, a, false);
-#pragma unroll
-    for (int rp = 0; rp < 4; rp++) {
-      split_pair(v[8 + rp], v[8 + 7 - rp], vtab[T + rp * 2 * T], a, b);
-      f(9 + 2 * rp, a, false);
-      f(10 + 2 * rp, b, true);
-    }
+  for (int rp = 0; rp < 8; rp++) {
+    const int k = rp < 4 ? t + rp * 2 * T : kh + (rp - 4) * 2 * T;
+    split_pair(v[rp], v[15 - rp], vtab[k], a, b);
+    f(2 * rp, a, false);
+    f(2 * rp + 1, b, true);
   }
 }
 

@@ -375,7 +375,7 @@ __device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (
 #pragma unroll
     for (int q = 0; q < kPoints; q++) {
       const float2 w = ldg2(w2 + t + T * q);
-      v[q] = make_float2(x[q].x * w.x, x[q].y * w.y);     // (packed FMUL2 here measured slower)
+      v[q] = mul2(x[q], w);
     }
     return;
   }
@@ -535,8 +535,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
       };
       if constexpr (RT) {
         last_pass_rt<M>(v, t, buf, p.tw, tr);
-        if (MULTI) emit_bins_rt<M>(v, t, p.vtab, tr, sink_multi);
-        else emit_bins_rt<M>(v, t, p.vtab, tr, sink_single);
+        if (MULTI) emit_bins_rt<M>(v, t, tr, sink_multi);
+        else emit_bins_rt<M>(v, t, tr, sink_single);
       } else {
         last_pass<M>(v, t, buf, p.tw);
         if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
@@ -624,10 +624,33 @@ __device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const flo
 #pragma unroll
     for (int i = 0; i < (1 << QS); i++) {
       const float2 a = bp[t + T * i];
-      x[(b << QS) + i] = make_float2(a.x - m, a.y - m);
+      x[(b << QS) + i] = sub2(a, bc(m));
     }
     sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
   }
+}
+
+// One PSD row out of the registers (slot numbering of fft_core.cuh): slot 2 rp is bin k, slot
+// 2 rp + 1 is bin M - k, k = t + rp 2T except for the upper four pairs of thread 0; base pointers
+// plus immediates.  Thread 0 also owns bin M/2.
+__device__ __forceinline__ void st_row(float *p, float y) {
+#if GLB_STREAM_STORE
+  __stcs(p, y);
+#else
+  *p = y;
+#endif
+}
+template <int M>
+__device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[17]) {
+  constexpr int T = M / kPoints;
+  const int kh = khi<M>(t) - 8 * T;
+  float *ra = row + t, *rb = row + (M - t), *rah = row + kh, *rbh = row + (M - kh);
+#pragma unroll
+  for (int rp = 0; rp < 8; rp++) {
+    st_row((rp < 4 ? ra : rah) + rp * 2 * T, yv[2 * rp]);
+    st_row((rp < 4 ? rb : rbh) - rp * 2 * T, yv[2 * rp + 1]);
+  }
+  if (t == 0) st_row(row + M / 2, yv[16]);
 }
 
 template <int M, bool MULTI>
@@ -754,24 +777,27 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
       MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
       float *row = p.rows + fl * p.row_stride;
       const bool db = p.rows_db != 0;
+      float yv[17];
+      yv[16] = 1.f;                     // only thread 0 has a 17th bin
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
-      auto sink_single = [&](int slot, float2 a, bool) {
-        float y = norm2(a);
-        if (db) y = 10.f * log10f(y);
-#if GLB_STREAM_STORE
-        if (active) __stcs(row + slot_bin<M>(t, slot), y);
-#else
-        if (active) row[slot_bin<M>(t, slot)] = y;
-#endif
-      };
+      auto sink_single = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
       if constexpr (RT) {
         last_pass_rt<M>(v, t, buf, p.tw, tr);
-        if (MULTI) emit_bins_rt<M>(v, t, p.vtab, tr, sink_multi);
-        else emit_bins_rt<M>(v, t, p.vtab, tr, sink_single);
+        if (MULTI) emit_bins_rt<M>(v, t, tr, sink_multi);
+        else emit_bins_rt<M>(v, t, tr, sink_single);
       } else {
         last_pass<M>(v, t, buf, p.tw);
         if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
         else emit_bins<M>(v, t, p.vtab, sink_single);
+      }
+      if (!MULTI) {
+        // the row leaves the registers here: one store per bin, streaming (written once, never
+        // re-read by this kernel); the dB conversion is a single uniform branch per frame
+        if (db) {
+#pragma unroll
+          for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
+        }
+        if (active) store_row<M>(row, t, yv);
       }
     }
     if (MULTI && active) {

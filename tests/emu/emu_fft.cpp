@@ -74,7 +74,7 @@ template <int M> int check(unsigned seed, bool rt = false) {
     };
   };
   for (int t = 0; t < T; t++) {
-    if (rt) emit_bins_rt<M>(regs[t].data(), t, vtab.data(), tr[t], sink(t));
+    if (rt) emit_bins_rt<M>(regs[t].data(), t, tr[t], sink(t));
     else emit_bins<M>(regs[t].data(), t, vtab.data(), sink(t));
   }
   double maxrel = 0, maxabs = 0, ref_rms = 0;
