@@ -4,7 +4,7 @@
 // z[m] = x[2m] + i x[2m+1], followed by the even/odd split.  One frame is owned by
 // T = M/16 threads; every thread holds P = 16 complex points in registers and the
 // passes exchange data through one M-entry float2 buffer in shared memory
-// (Stockham auto-sort indexing; the buffer is padded by 2 entries per 16 so that the
+// (Stockham auto-sort indexing; the buffer is padded by 1 entry per 16 so that the
 // strided first-pass stores and the unit-stride loads are both bank-conflict free AND
 // every address is a per-thread base plus a compile-time immediate).
 //
@@ -145,11 +145,23 @@ GLB_HD Tw3 make_tw3(float2 w) {
 GLB_HD float2 cmul(float2 a, const Tw3 &w) { return fma2(a, bc(w.r), mul2(swp(a), w.q)); }
 GLB_HD float2 cmulc(float2 a, const Tw3 &w) { return fma2(a, bc(w.r), neg(mul2(swp(a), w.q))); }
 
-// Padded float2 index: 2 spare entries after every 16 (16 B alignment of even entries is
-// kept, so pairs can move as one 128-bit access).  pad(a + c) = pad(a) + c + c/8 whenever
-// c is a multiple of 16: strided accesses become base + immediate.
-GLB_HD int pad(int p) { return p + 2 * (p >> 4); }
+// Padded float2 index: 1 spare entry after every 16, so that 64-bit accesses of 16 lanes that
+// are 16 entries apart (first-pass stores) or 1 entry apart (loads) hit 16 different banks.
+// pad(a + c) = pad(a) + c + c/16 whenever c is a multiple of 16: strided accesses become a
+// per-thread base plus a compile-time immediate.  (128-bit stores with a pad of 2 need four
+// register moves each to line the pairs up: slower.)
+GLB_HD int pad(int p) { return p + (p >> 4); }
 template <int M> struct BufSize { static constexpr int value = M + M / 8 + 2; };   // float2 entries
+
+// Layout of the exchange that feeds the final radix-8 pass (plans with a mid pass): entry
+// j + r 2T (butterfly j, input r) lives at 9 j + r.  The uniform stride of 9 entries keeps the
+// ascending loads of butterfly t, the descending loads of butterfly 2T - t (whatever their
+// alignment) and the stores of the pass before all bank-conflict free with 64-bit accesses.
+#if !defined(GLB_LAST9)
+#define GLB_LAST9 1
+#endif
+template <int M> struct LastLayout { static constexpr bool value = GLB_LAST9 && Plan<M>::NP >= 3; };
+GLB_HD int last_phys(int j, int r) { return 9 * j + r; }
 
 // ------------------------------------------------------------------ in-register DFTs
 // Forward transforms (kernel e^{-2 pi i nk/R}) over v[0], v[S], ..., v[(R-1)S];
@@ -231,7 +243,7 @@ template <int S> struct Dft<16, S> { static GLB_HD void run(float2 *v) { dft16<S
 // Element q of thread t in every non-final pass is entry t + T*q of the buffer.
 template <int M> GLB_HD int ld_index(int t, int q) {
   constexpr int T = M / kPoints;
-  if constexpr (T % 16 == 0) return pad(t) + q * (T + T / 8);
+  if constexpr (T % 16 == 0) return pad(t) + q * (T + T / 16);
   else return pad(t + T * q);
 }
 
@@ -255,14 +267,18 @@ GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
     }
     Dft<R, S>::run(v + u);
     if constexpr (P == 0 && R == 16) {
-      // 16 consecutive entries 16j..16j+15 -> padded 18j..18j+15, as eight 128-bit stores
-      float4 *dst = reinterpret_cast<float4 *>(buf + 18 * j);
+      // 16 consecutive entries 16j..16j+15 -> padded 17j..17j+15 (64-bit stores: lanes 17 entries apart)
+      float2 *dst = buf + 17 * j;
 #pragma unroll
-      for (int r = 0; r < 16; r += 2) dst[r / 2] = make_float4(v[u + r * S].x, v[u + r * S].y, v[u + (r + 1) * S].x, v[u + (r + 1) * S].y);
+      for (int r = 0; r < 16; r++) dst[r] = v[u + r * S];
+    } else if constexpr (LastLayout<M>::value && P == Plan<M>::NP - 2) {
+      const int base = last_phys(k, (j - k) / Ns);
+#pragma unroll
+      for (int r = 0; r < R; r++) buf[base + r * 9 * Ns] = v[u + r * S];
     } else if constexpr (Ns % 16 == 0) {
       const int base = pad((j - k) * R + k);
 #pragma unroll
-      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 8)] = v[u + r * S];
+      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 16)] = v[u + r * S];
     } else {
       const int base = (j - k) * R + k;
 #pragma unroll
@@ -289,12 +305,19 @@ GLB_HD void last_pass(float2 *v, int t, const float2 *buf, const float2 *tw) {
   const int jB = (t == 0) ? T : 2 * T - t;
   const float2 *twA = tw + TwOffset<M, NP - 1>::value + jA;
   const float2 *twB = tw + TwOffset<M, NP - 1>::value + jB;
-  if constexpr (Ns % 16 == 0) {
+  if constexpr (LastLayout<M>::value) {
+    const int bA = last_phys(jA, 0), bB = last_phys(jB, 0);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      v[r] = buf[bA + r];
+      v[8 + r] = buf[bB + r];
+    }
+  } else if constexpr (Ns % 16 == 0) {
     const int bA = pad(jA), bB = pad(jB);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      v[r] = buf[bA + r * (Ns + Ns / 8)];
-      v[8 + r] = buf[bB + r * (Ns + Ns / 8)];
+      v[r] = buf[bA + r * (Ns + Ns / 16)];
+      v[8 + r] = buf[bB + r * (Ns + Ns / 16)];
     }
   } else {
 #pragma unroll
@@ -447,13 +470,17 @@ GLB_HD void pass_scatter(const float2 *v, int t, float2 *buf) {
     const int j = t + u * T;
     const int k = j & (Ns - 1);
     if constexpr (P == 0 && R == 16) {
-      float4 *dst = reinterpret_cast<float4 *>(buf + 18 * j);
+      float2 *dst = buf + 17 * j;
 #pragma unroll
-      for (int r = 0; r < 16; r += 2) dst[r / 2] = make_float4(v[u + r * S].x, v[u + r * S].y, v[u + (r + 1) * S].x, v[u + (r + 1) * S].y);
+      for (int r = 0; r < 16; r++) dst[r] = v[u + r * S];
+    } else if constexpr (LastLayout<M>::value && P == Plan<M>::NP - 2) {
+      const int base = last_phys(k, (j - k) / Ns);
+#pragma unroll
+      for (int r = 0; r < R; r++) buf[base + r * 9 * Ns] = v[u + r * S];
     } else if constexpr (Ns % 16 == 0) {
       const int base = pad((j - k) * R + k);
 #pragma unroll
-      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 8)] = v[u + r * S];
+      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 16)] = v[u + r * S];
     } else {
       const int base = (j - k) * R + k;
 #pragma unroll
@@ -497,12 +524,19 @@ GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, 
   constexpr int T = M / kPoints, NP = Plan<M>::NP, Ns = 2 * T;
   const int jA = t;
   const int jB = (t == 0) ? T : 2 * T - t;
-  if constexpr (Ns % 16 == 0) {
+  if constexpr (LastLayout<M>::value) {
+    const int bA = last_phys(jA, 0), bB = last_phys(jB, 0);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      v[r] = buf[bA + r];
+      v[8 + r] = buf[bB + r];
+    }
+  } else if constexpr (Ns % 16 == 0) {
     const int bA = pad(jA), bB = pad(jB);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      v[r] = buf[bA + r * (Ns + Ns / 8)];
-      v[8 + r] = buf[bB + r * (Ns + Ns / 8)];
+      v[r] = buf[bA + r * (Ns + Ns / 16)];
+      v[8 + r] = buf[bB + r * (Ns + Ns / 16)];
     }
   } else {
 #pragma unroll
@@ -586,10 +620,12 @@ GLB_HD void split_pair_rt(float2 zk, float2 zm, const Tw3 &vb, int e, float2 &a,
 
 // f(slot, value, conjugated): value = 2 X[slot_bin(t, slot)] (conjugated when the flag is set),
 // still carrying the scale folded into the taper.
-template <int M, class F>
+// T0 = false: the caller knows that t != 0 (warps without thread 0 then carry no trace of the
+// re-ordering: the compiler needs ~17 register moves around it)
+template <int M, bool T0 = true, class F>
 GLB_HD void emit_bins_rt(float2 *v, int t, const TwRegs &tr, F &&f) {
   float2 a, b;
-  if (t == 0) {
+  if (T0 && t == 0) {
     const float2 z = thread0_fixup(v);                  // X[M/2] = conj(Z[M/2])
     f(16, make_float2(2.f * z.x, -2.f * z.y), false);
   }
@@ -602,11 +638,11 @@ GLB_HD void emit_bins_rt(float2 *v, int t, const TwRegs &tr, F &&f) {
   }
 }
 
-template <int M, class F>
+template <int M, bool T0 = true, class F>
 GLB_HD void emit_bins(float2 *v, int t, const float2 *vtab, F &&f) {
   constexpr int T = M / kPoints;
   float2 a, b;
-  if (t == 0) {
+  if (T0 && t == 0) {
     const float2 z = thread0_fixup(v);
     f(16, make_float2(2.f * z.x, -2.f * z.y), false);
   }

@@ -254,6 +254,21 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 }
 
 __device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
+// The taper table is the one global array every frame re-reads; with ~28 KB of L1 left beside the
+// shared-memory carve-out it stays resident only if its lines are the last to go and the row
+// stores do not allocate.
+#ifndef GLB_L1_POLICY
+#define GLB_L1_POLICY 1
+#endif
+__device__ __forceinline__ float2 ld_taper(const float2 *p) {
+#if GLB_L1_POLICY
+  float2 r;
+  asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
 
 // frame f can be fetched by one bulk copy: entirely inside the staged samples, no zero
 // history, 16-byte aligned
@@ -374,7 +389,7 @@ __device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (
   if (PLAIN || (p.ra9mb_a <= 0.f && p.limiter == 0)) {
 #pragma unroll
     for (int q = 0; q < kPoints; q++) {
-      const float2 w = ldg2(w2 + t + T * q);
+      const float2 w = ld_taper(w2 + t + T * q);
       v[q] = mul2(x[q], w);
     }
     return;
@@ -567,6 +582,10 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 // so every sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM
 // latency hides behind the previous frame's transform.  Block means (sub_mean) are computed
 // once per block when it lands and kept beside the ring.
+#ifndef GLB_MEAN_AHEAD
+#define GLB_MEAN_AHEAD 0  // 1: the next block's mean is formed before the last barrier of the current transform
+                          //    (measured 4 % slower: the block has to land 40 % of a frame earlier)
+#endif
 #ifndef GLB_RING_EXTRA
 #define GLB_RING_EXTRA 0  // 1: one spare slot, the next block is requested at the top of a frame;
 #endif                    // 0: NB slots, requested after barrier (A) into the oldest block's slot
@@ -592,7 +611,7 @@ __host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
 // the same wherever the block sits in a frame: its mean is bit-identical in every frame, group
 // and time shard.  Must be called by all threads of the CTA (contains a block barrier).
 template <int M>
-__device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
+__device__ __forceinline__ float ring_block_partial(const float *blk, int qs, int t, float *red) {
   constexpr int T = M / kPoints, NW = (T + 31) / 32, W = T < 32 ? T : 32;
   const float2 *b2 = reinterpret_cast<const float2 *>(blk);
   float s = 0.f;
@@ -602,31 +621,72 @@ __device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t
   }
 #pragma unroll
   for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (NW > 1 && (t & 31) == 0) red[t >> 5] = s;
+  return s;
+}
+// after a block barrier that follows ring_block_partial()
+template <int M>
+__device__ __forceinline__ float ring_block_total(float s_warp, const float *red, float inv_hop) {
+  constexpr int T = M / kPoints, NW = (T + 31) / 32;
+  float s = s_warp;
   if (NW > 1) {
-    if ((t & 31) == 0) red[t >> 5] = s;
-    __syncthreads();
     s = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; w++) s += red[w];
   }
   return s * inv_hop;
 }
+template <int M>
+__device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
+  constexpr int T = M / kPoints, NW = (T + 31) / 32;
+  const float s = ring_block_partial<M>(blk, qs, t, red);
+  if (NW > 1) __syncthreads();
+  return ring_block_total<M>(s, red, inv_hop);
+}
 
+// Top of a frame: the NB blocks of the frame from the ring into registers, block means removed.
+// `new_mean`: the newest block has just landed and its mean is not known yet; it is summed from
+// the registers just loaded (same order as ring_block_partial, so the mean of a block is the
+// same bits wherever it is formed), combined across the warps of the group through `red` with
+// one block barrier, and left in mu_new / mu[slot_newest].  The loads of the other blocks are
+// in flight across that barrier.
 template <int M, int QS>
-__device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const float *ring, int hop, int slot_oldest,
-                                          int slots, const float *mu, float mu_new, bool sub) {
-  constexpr int T = M / kPoints, NB = kPoints >> QS;
+__device__ __forceinline__ void ring_fetch(float2 (&x)[kPoints], int t, const float *ring, int hop, int slot_oldest,
+                                           int slots, float *mu, float &mu_new, bool sub, bool new_mean, float *red,
+                                           float inv_hop) {
+  constexpr int T = M / kPoints, NB = kPoints >> QS, NW = (T + 31) / 32, W = T < 32 ? T : 32;
   int sidx = slot_oldest;
+  int slot_of[NB];
 #pragma unroll
   for (int b = 0; b < NB; b++) {
     const float2 *bp = reinterpret_cast<const float2 *>(ring + (size_t) sidx * hop);
-    const float m = sub ? ((b == NB - 1) ? mu_new : mu[sidx]) : 0.f;
+    slot_of[b] = sidx;
+#pragma unroll
+    for (int i = 0; i < (1 << QS); i++) x[(b << QS) + i] = bp[t + T * i];
+    sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
+  }
+  if (!sub) return;
+  if (new_mean) {
+    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < (1 << QS); i++) {
-      const float2 a = bp[t + T * i];
-      x[(b << QS) + i] = sub2(a, bc(m));
+      const float2 a = x[((NB - 1) << QS) + i];
+      s += a.x + a.y;
     }
-    sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (NW > 1) {
+      if ((t & 31) == 0) red[t >> 5] = s;
+      __syncthreads();
+    }
+    mu_new = ring_block_total<M>(s, red, inv_hop);
+    if (t == 0) mu[slot_of[NB - 1]] = mu_new;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const float m = (b == NB - 1) ? mu_new : mu[slot_of[b]];
+#pragma unroll
+    for (int i = 0; i < (1 << QS); i++) x[(b << QS) + i] = sub2(x[(b << QS) + i], bc(m));
   }
 }
 
@@ -634,7 +694,9 @@ __device__ __forceinline__ void ring_load(float2 (&x)[kPoints], int t, const flo
 // 2 rp + 1 is bin M - k, k = t + rp 2T except for the upper four pairs of thread 0; base pointers
 // plus immediates.  Thread 0 also owns bin M/2.
 __device__ __forceinline__ void st_row(float *p, float y) {
-#if GLB_STREAM_STORE
+#if GLB_L1_POLICY
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(y) : "memory");
+#elif GLB_STREAM_STORE
   __stcs(p, y);
 #else
   *p = y;
@@ -652,6 +714,27 @@ __device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[1
   }
   if (t == 0) st_row(row + M / 2, yv[16]);
 }
+
+// mid passes of the ring kernel; `hook` runs before the last block barrier ahead of the final pass
+template <int M, int P, bool RT> struct RingMidPasses {
+  template <class H>
+  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr, H &&hook) {
+    if constexpr (P < Plan<M>::NP - 1) {
+      pass_load<M>(v, t, buf);
+      if constexpr (RT) {
+        pass_compute_rt<M, P>(v, tr);
+        __syncthreads();                // every thread has read before anyone overwrites
+        pass_scatter<M, P>(v, t, buf);
+      } else {
+        __syncthreads();
+        pass_store<M, P>(v, t, buf, tw);
+      }
+      if constexpr (P == Plan<M>::NP - 2) hook();
+      __syncthreads();
+      RingMidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, hook);
+    }
+  }
+};
 
 template <int M, bool MULTI>
 __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kernel(const KParams p) {
@@ -724,17 +807,13 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
     const long long f = p.first_frame + fl;
     const bool next_there = (it + 1 < p.frames_per_group) && (fl + 1 < p.nframes);
     const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
-    if (it > 0) {
+#if !GLB_MEAN_AHEAD
+    if (it > 0 && active) {
       // block f was requested one frame ago
-      if (active) {
-        mbar_wait(&mbar[slot_new], (phase_bits >> slot_new) & 1u);
-        phase_bits ^= 1u << slot_new;
-      }
-      if (sub) {
-        mu_new = ring_block_mean<M>(ring + (size_t) slot_new * hop, qs, t, red + slot_new * GeoM::NW, p.inv_hop_mean);
-        if (t == 0) mu[slot_new] = mu_new;
-      }
+      mbar_wait(&mbar[slot_new], (phase_bits >> slot_new) & 1u);
+      phase_bits ^= 1u << slot_new;
     }
+#endif
     auto request_next = [&]() {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&mbar[slot_next], blk_bytes);
@@ -750,19 +829,36 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
       for (int i = 0; i < 17; i++) acc[i] = 0.f;
     }
     const int ntap = MULTI ? p.ntapers : 1;
+    float mu_next = 0.f;
     for (int j = 0; j < ntap; ++j) {
       float2 v[kPoints];
       {
         float2 x[kPoints];
+        // (mean-ahead variant: the mean is already in mu_new)
+        const bool nm = !GLB_MEAN_AHEAD && it > 0 && j == 0;
+        float *redn = red + slot_new * GeoM::NW;
         switch (qs) {
-          case 4: ring_load<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
-          case 3: ring_load<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
-          case 2: ring_load<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
-          case 1: ring_load<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
-          default: ring_load<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub); break;
+          case 4: ring_fetch<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+          case 3: ring_fetch<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+          case 2: ring_fetch<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+          case 1: ring_fetch<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+          default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
         }
         apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
       }
+      // Block f + 1 was requested after barrier (A) of this frame's last taper; before the last
+      // block barrier of the transform every thread waits for it and leaves its share of the
+      // block sum in `red`, so the mean is there after that barrier: the next frame starts
+      // without a barrier of its own and without waiting for DRAM.
+      const bool last_tap = (j == ntap - 1);
+      float s_warp = 0.f;
+      auto land_next = [&]() {
+        if (GLB_MEAN_AHEAD && last_tap && next_there) {
+          mbar_wait(&mbar[slot_next], (phase_bits >> slot_next) & 1u);
+          phase_bits ^= 1u << slot_next;
+          if (sub) s_warp = ring_block_partial<M>(ring + (size_t) slot_next * hop, qs, t, red);
+        }
+      };
       if constexpr (RT) {
         pass_compute_rt<M, 0>(v, tr);
         __syncthreads();               // (A) the previous transform's last pass has been read by all
@@ -772,23 +868,39 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
         pass_store<M, 0>(v, t, buf, p.tw);
       }
       // tight ring: past (A) of the last taper nobody reads the oldest block any more
-      if (!GLB_RING_EXTRA && next_there && j == ntap - 1 && t == 0) request_next();
+      if (!GLB_RING_EXTRA && next_there && last_tap && t == 0) request_next();
+      if constexpr (Plan<M>::NP == 2) land_next();
       __syncthreads();
-      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
+      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, land_next);
+      if (GLB_MEAN_AHEAD && last_tap && next_there && sub) {
+        mu_next = ring_block_total<M>(s_warp, red, p.inv_hop_mean);
+        if (t == 0) mu[slot_next] = mu_next;
+      }
       float *row = p.rows + fl * p.row_stride;
       const bool db = p.rows_db != 0;
       float yv[17];
       yv[16] = 1.f;                     // only thread 0 has a 17th bin
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
       auto sink_single = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
+      const bool w0 = t < 32;           // warp-uniform: only the warp that holds thread 0 pays for its re-ordering
       if constexpr (RT) {
         last_pass_rt<M>(v, t, buf, p.tw, tr);
-        if (MULTI) emit_bins_rt<M>(v, t, tr, sink_multi);
-        else emit_bins_rt<M>(v, t, tr, sink_single);
+        if (MULTI) {
+          if (w0) emit_bins_rt<M, true>(v, t, tr, sink_multi);
+          else emit_bins_rt<M, false>(v, t, tr, sink_multi);
+        } else {
+          if (w0) emit_bins_rt<M, true>(v, t, tr, sink_single);
+          else emit_bins_rt<M, false>(v, t, tr, sink_single);
+        }
       } else {
         last_pass<M>(v, t, buf, p.tw);
-        if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
-        else emit_bins<M>(v, t, p.vtab, sink_single);
+        if (MULTI) {
+          if (w0) emit_bins<M, true>(v, t, p.vtab, sink_multi);
+          else emit_bins<M, false>(v, t, p.vtab, sink_multi);
+        } else {
+          if (w0) emit_bins<M, true>(v, t, p.vtab, sink_single);
+          else emit_bins<M, false>(v, t, p.vtab, sink_single);
+        }
       }
       if (!MULTI) {
         // the row leaves the registers here: one store per bin, streaming (written once, never
@@ -813,6 +925,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
       }
     }
     slot_new = slot_next;
+    if (GLB_MEAN_AHEAD) mu_new = mu_next;
   }
 }
 
