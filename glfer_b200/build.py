@@ -14,9 +14,10 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libglfer_b200.so")
 OBJ = os.path.join(HERE, "_build")
 
-CU_SOURCES = ["csrc/gram_kernels.cu"]
+# (source, tag, extra flags): gram_part.cu is compiled once per subset of FFT sizes, in parallel
+CU_UNITS = [("csrc/gram_kernels.cu", "", [])] + [("csrc/gram_part.cu", f".p{k}", [f"-DGLB_PART={k}"]) for k in range(4)]
 C_SOURCES = ["host/window.c", "host/dpss.c", "host/gram.c", "host/dropin.c", "host/wav.c"]
-HEADERS = ["csrc/fft_core.cuh", "csrc/tables.hpp", "host/glb_host.h", "../include/glb_shim.h", "../include/fft.h",
+HEADERS = ["csrc/fft_core.cuh", "csrc/fft_wpf.cuh", "csrc/gram_common.cuh", "csrc/tables.hpp", "host/glb_host.h", "../include/glb_shim.h", "../include/fft.h",
            "../include/mtm.h", "../include/avg.h", "../include/glfer_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -49,16 +50,32 @@ def _run(cmd: list[str], log: str | None = None) -> None:
         raise RuntimeError("build step failed: " + " ".join(cmd))
 
 
+def _compile_cu(nvcc: str, extra: list[str], tag: str, force: bool, hdrs: list[str], verbose: bool) -> list[str]:
+    """All CUDA translation units (in parallel); returns the object files."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs, objs = [], []
+    for src, part, flags in CU_UNITS:
+        s = os.path.join(HERE, src)
+        o = os.path.join(OBJ, os.path.basename(src) + part + (f".{tag}" if tag else "") + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            if verbose:
+                print("nvcc", src, " ".join(flags))
+            jobs.append(([nvcc] + NVCC_FLAGS + extra + flags + ["-c", s, "-o", o], o + ".log"))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            for fut in [ex.submit(_run, cmd, log) for cmd, log in jobs]:
+                fut.result()
+    return objs
+
+
 def build_variant(tag: str, extra_nvcc: list[str]) -> str:
     """Experiment helper: a second library with extra nvcc flags (e.g. another register
     target), selected at run time with GLFER_B200_LIB=<path>."""
     build()
     nvcc = _nvcc()
-    objs = []
-    for src in CU_SOURCES:
-        o = os.path.join(OBJ, os.path.basename(src) + f".{tag}.o")
-        _run([nvcc] + NVCC_FLAGS + extra_nvcc + ["-c", os.path.join(HERE, src), "-o", o], log=o + ".log")
-        objs.append(o)
+    hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = _compile_cu(nvcc, extra_nvcc, tag, True, hdrs, False)
     objs += [os.path.join(OBJ, os.path.basename(src) + ".o") for src in C_SOURCES]
     out = os.path.join(HERE, f"libglfer_b200_{tag}.so")
     _run([nvcc, "-shared", "-o", out] + objs + ["-Xcompiler", "-pthread", "-lm", "-lpthread"])
@@ -68,16 +85,8 @@ def build_variant(tag: str, extra_nvcc: list[str]) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    objs = []
     nvcc = _nvcc()
-    for src in CU_SOURCES:
-        s = os.path.join(HERE, src)
-        o = os.path.join(OBJ, os.path.basename(src) + ".o")
-        if force or _stale(o, [s] + hdrs):
-            if verbose:
-                print("nvcc", src)
-            _run([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o], log=o + ".log")
-        objs.append(o)
+    objs = _compile_cu(nvcc, [], "", force, hdrs, verbose)
     for src in C_SOURCES:
         s = os.path.join(HERE, src)
         o = os.path.join(OBJ, os.path.basename(src) + ".o")

@@ -1,9 +1,12 @@
-// gram_kernels.cu -- sm_100a kernels of the spectrogram hot path + the C-ABI shim.
+// gram_kernels.cu -- the C-ABI CUDA shim: stream/event/memory plumbing, constant tables, the
+// launch entry points and the small kernels around the spectrogram kernels proper (which live in
+// gram_common.cuh and are instantiated per FFT size by gram_part.cu).
 //
 // Kernels (all hand-written, no library FFT):
-//   gram_kernel<M>        overlapped-frame gather -> [block-mean removal] -> [RA9MB] ->
+//   gram_kernel<M> / gram_ring_kernel<M> / gram_wpf_kernel<M>   (gram_common.cuh)
+//                         overlapped-frame gather -> [block-mean removal] -> [RA9MB] ->
 //                         taper multiply -> [limiter] -> real FFT (N = 2M, in registers +
-//                         swizzled shared memory) -> |X|^2 -> [sum over K' tapers with the
+//                         padded shared memory) -> |X|^2 -> [sum over K' tapers with the
 //                         1/lambda weights folded into the tapers] -> [10 log10] -> one PSD
 //                         row per frame straight to HBM.  Replaces prepare_audio + fft_do +
 //                         fft_psd (fft.c:66-226) and the taper loop of mtm_do (mtm.c:189-220).
@@ -15,41 +18,19 @@
 //
 // No tensor cores: the path is an FFT at ~9 flop/B executed, bound by HBM and the
 // FP32/shared-memory pipes, not a dense contraction.
-#include <cuda_runtime.h>
-#include <cstdio>
-#include <cstring>
-#include <cstdint>
-#include <atomic>
-#include <vector>
-#include <algorithm>
-
-#include "fft_core.cuh"
-#include "fft_wpf.cuh"
-#include "tables.hpp"
-#include "../../include/glb_shim.h"
-
-using namespace glb;
+#include "gram_common.cuh"
 
 // ------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
-static std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_launches{0};
+int g_kernel_pref = 0;               // 0 auto, 1 general, 2 ring, 3 warp-per-frame
 static int g_force_generic = 0;     // tests: run the general kernel where the ring kernel would be chosen
 
 extern "C" const char *glb_last_error(void) { return g_err; }
 extern "C" void glb_set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
 extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load(); }
 extern "C" void glb_force_generic_kernel(int on) { g_force_generic = on; }
-
-#define CU(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
-               __FILE__, __LINE__);                                                           \
-      return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? GLB_ENODEV      \
-             : (e_ == cudaErrorMemoryAllocation ? GLB_ENOMEM : GLB_ECUDA);                    \
-    }                                                                                         \
-  } while (0)
+extern "C" void glb_set_kernel_preference(int pref) { g_kernel_pref = pref; }
 
 // ------------------------------------------------------------------------- plumbing
 extern "C" int glb_device_count(int *count) {
@@ -169,1023 +150,6 @@ extern "C" int glb_tables_destroy(void *tp) {
   return GLB_OK;
 }
 
-// ------------------------------------------------------------------------- gram kernel
-struct KParams {
-  const float *samples;
-  long long origin, count;
-  const float *tapers;
-  int ntapers;
-  const float *means;         // pre-computed block means (general geometry), or nullptr
-  long long means_first_block;
-  int fused_mean;             // 1: block means are computed inside the kernel (regular geometry)
-  int qs;                     // regular geometry: hop = 2T << qs
-  float inv_hop_mean;         // 1 / hop
-  int hop, n_ov, cblk;        // cblk = ceil(n_ov / hop)
-  float inv_hop;
-  float ra9mb_a;
-  int limiter;
-  float lim_scale;            // taper_scale^0.9
-  float spec_scale;           // 1 / (2 taper_scale)
-  long long first_frame, nframes;
-  int frames_per_group;
-  float *rows;
-  long long row_stride;
-  int rows_db;
-  float2 *spectrum;
-  const float2 *tw, *vtab, *roots;
-};
-
-#ifndef GLB_REG_TARGET
-#define GLB_REG_TARGET 80
-#endif
-#ifndef GLB_STREAM_STORE
-#define GLB_STREAM_STORE 1
-#endif
-
-template <int M> struct Geo {
-  static constexpr int N = 2 * M;
-  static constexpr int T = M / kPoints;
-  static constexpr int G = (T >= 128) ? 1 : 128 / T;   // frame groups per CTA
-  static constexpr int THREADS = G * T;
-  static constexpr int NW = (T + 31) / 32;             // warps per group
-  // frames are staged in shared memory by TMA bulk copies, one frame ahead, when the
-  // staging buffer still leaves room for >= 2 CTAs per SM
-  static constexpr bool STAGE = (M <= 4096);           // (used by the multitaper variant only)
-  // twiddles kept in registers across frames instead of per-frame table loads
-  static constexpr bool RT = (M <= 2048);
-  static constexpr size_t BUF_BYTES = (size_t) BufSize<M>::value * sizeof(float2);      // multiple of 16
-  static constexpr size_t RED_BYTES = 16 * NW * sizeof(float) + 16 * sizeof(float);     // partial sums + means
-  // per frame group: FFT buffer | [staging buffer] | reduction scratch | mbarrier
-  static __host__ __device__ constexpr size_t stage_bytes(bool multi) { return (STAGE && multi) ? (size_t) N * sizeof(float) : 0; }
-  static __host__ __device__ constexpr size_t group_bytes(bool multi) { return ((BUF_BYTES + stage_bytes(multi) + RED_BYTES + 16 + 15) / 16) * 16; }
-  static __host__ __device__ constexpr size_t smem_bytes(bool multi) { return (size_t) G * group_bytes(multi); }
-  // CTAs per SM the register allocation is tuned for (~GLB_REG_TARGET registers per thread)
-  static constexpr int MINB_ = 65536 / (THREADS * (THREADS >= 512 ? 64 : GLB_REG_TARGET));
-  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
-};
-
-// Barrier over the frame groups of a CTA.  (Tried and dropped, B200: mapping a 4-warp group onto
-// one SM sub-partition with its own named barrier -- no gain over the CTA-wide barrier.)
-template <int M> __device__ __forceinline__ void group_sync(int) { __syncthreads(); }
-
-// ---- mbarrier / TMA bulk-copy helpers (1-D cp.async.bulk global -> shared) ----
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
-// The taper table is the one global array every frame re-reads; with ~28 KB of L1 left beside the
-// shared-memory carve-out it stays resident only if its lines are the last to go and the row
-// stores do not allocate.
-#ifndef GLB_L1_POLICY
-#define GLB_L1_POLICY 1
-#endif
-__device__ __forceinline__ float2 ld_taper(const float2 *p) {
-#if GLB_L1_POLICY
-  float2 r;
-  asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-  return r;
-#else
-  return __ldg(p);
-#endif
-}
-
-// frame f can be fetched by one bulk copy: entirely inside the staged samples, no zero
-// history, 16-byte aligned
-__device__ __forceinline__ bool frame_bulk_ok(const KParams &p, long long f, int n) {
-  const long long s0 = f * (long long) p.hop - p.n_ov;
-  const long long rel = s0 - p.origin;
-  return (s0 >= 0) && (rel >= 0) && (rel + n <= p.count) && ((rel & 3) == 0);
-}
-
-// Raw samples of one frame: x[q] = (y[2m], y[2m+1]), m = t + T q; zeros before the stream.
-template <int M>
-__device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KParams &p, long long f, const float *stage,
-                                         bool staged) {
-  constexpr int T = M / kPoints, N = 2 * M;
-  if (staged) {
-    const float2 *s2 = reinterpret_cast<const float2 *>(stage);
-#pragma unroll
-    for (int q = 0; q < kPoints; q++) x[q] = s2[t + T * q];
-    return;
-  }
-  const long long s0 = f * (long long) p.hop - p.n_ov;
-  const long long rel = s0 - p.origin;
-  if ((s0 >= 0) && (rel >= 0) && (rel + N <= p.count) && ((rel & 1) == 0)) {
-    const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
-#pragma unroll
-    for (int q = 0; q < kPoints; q++) x[q] = ldg2(src + t + T * q);
-    return;
-  }
-#pragma unroll
-  for (int q = 0; q < kPoints; q++) {
-    float y[2];
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const long long s = s0 + 2 * (t + T * q) + e;
-      const long long r = s - p.origin;
-      y[e] = (s >= 0 && r >= 0 && r < p.count) ? __ldg(p.samples + r) : 0.f;
-    }
-    x[q] = make_float2(y[0], y[1]);
-  }
-}
-
-// Block-mean removal inside the kernel (prepare_audio, fft.c:86-96) for the regular
-// geometry hop = 2T << QS, n_ov a multiple of hop: the frame is NB = 16 >> QS whole hop
-// blocks, block b = registers q with (q >> QS) == b.  Every thread sums its share of each
-// block, warps reduce by shuffle, the group combines through shared memory.  A block gets
-// the same summation tree in every frame it appears in, so its mean is bit-identical
-// across frames (and across time shards).  Zero history sums to a zero mean.
-template <int M, int QS>
-__device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, float *red, float inv_hop, int g) {
-  constexpr int T = M / kPoints, NW = (T + 31) / 32, NB = kPoints >> QS;
-  constexpr int W = T < 32 ? T : 32;      // lanes of a warp that belong to this group
-  float bs[NB];
-#pragma unroll
-  for (int b = 0; b < NB; b++) {
-    float s = 0.f;
-#pragma unroll
-    for (int q = b << QS; q < (b + 1) << QS; q++) s += x[q].x + x[q].y;
-#pragma unroll
-    for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    bs[b] = s;
-  }
-  if (NW > 1) {
-    const int w = t >> 5;
-    if ((t & 31) == 0) {
-#pragma unroll
-      for (int b = 0; b < NB; b++) red[b * NW + w] = bs[b];
-    }
-    group_sync<M>(g);
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-      float s = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < NW; w2++) s += red[b * NW + w2];
-      bs[b] = s;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < kPoints; q++) {
-    const float m = bs[q >> QS] * inv_hop;
-    x[q].x -= m;
-    x[q].y -= m;
-  }
-}
-
-template <int M>
-__device__ __forceinline__ void remove_block_means_qs(float2 (&x)[kPoints], int t, float *red, const KParams &p, int g) {
-  switch (p.qs) {
-    case 4: remove_block_means<M, 4>(x, t, red, p.inv_hop_mean, g); break;
-    case 3: remove_block_means<M, 3>(x, t, red, p.inv_hop_mean, g); break;
-    case 2: remove_block_means<M, 2>(x, t, red, p.inv_hop_mean, g); break;
-    case 1: remove_block_means<M, 1>(x, t, red, p.inv_hop_mean, g); break;
-    default: remove_block_means<M, 0>(x, t, red, p.inv_hop_mean, g); break;
-  }
-}
-
-// pre-computed block means, any geometry: block of frame sample i is
-// f - cblk + floor((i + cblk*hop - n_ov) / hop); samples before the stream keep 0
-template <int M>
-__device__ __forceinline__ void remove_table_means(float2 (&x)[kPoints], int t, const KParams &p, long long f) {
-  constexpr int T = M / kPoints;
-  const long long s0 = f * (long long) p.hop - p.n_ov;
-  const float *mu = p.means + (f - p.cblk - p.means_first_block);
-  const float off = (float) (p.cblk * p.hop - p.n_ov) + 0.5f;
-#pragma unroll
-  for (int q = 0; q < kPoints; q++) {
-    const int i = 2 * (t + T * q);
-    if (s0 + i >= 0) x[q].x -= __ldg(mu + (int) (((float) i + off) * p.inv_hop));
-    if (s0 + i + 1 >= 0) x[q].y -= __ldg(mu + (int) (((float) (i + 1) + off) * p.inv_hop));
-  }
-}
-
-// RA9MB -> taper -> limiter (fft.c:127-156); the common case is the bare multiply
-template <int M, bool PLAIN>
-__device__ __forceinline__ void apply_taper(float2 (&v)[kPoints], const float2 (&x)[kPoints], int t, const KParams &p,
-                                            const float *tap) {
-  constexpr int T = M / kPoints;
-  const float2 *w2 = reinterpret_cast<const float2 *>(tap);
-  if (PLAIN || (p.ra9mb_a <= 0.f && p.limiter == 0)) {
-#pragma unroll
-    for (int q = 0; q < kPoints; q++) {
-      const float2 w = ld_taper(w2 + t + T * q);
-      v[q] = mul2(x[q], w);
-    }
-    return;
-  }
-#pragma unroll
-  for (int q = 0; q < kPoints; q++) {
-    const float2 w = ldg2(w2 + t + T * q);
-    float y[2] = {x[q].x, x[q].y};
-    const float ww[2] = {w.x, w.y};
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      if (p.ra9mb_a > 0.f) y[e] = y[e] / (p.ra9mb_a + y[e] * y[e]);
-      y[e] *= ww[e];
-      if (p.limiter == 1) {
-        const float m = p.lim_scale * powf(fabsf(y[e]), 0.1f);
-        y[e] = (y[e] > 0.f) ? m : -m;
-      }
-    }
-    v[q] = make_float2(y[0], y[1]);
-  }
-}
-
-template <int M, int P, bool RT> struct MidPasses {
-  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr, int g) {
-    if constexpr (P < Plan<M>::NP - 1) {
-      pass_load<M>(v, t, buf);
-      if constexpr (RT) {
-        pass_compute_rt<M, P>(v, tr);
-        group_sync<M>(g);               // every thread has read before anyone overwrites
-        pass_scatter<M, P>(v, t, buf);
-      } else {
-        group_sync<M>(g);
-        pass_store<M, P>(v, t, buf, tw);
-      }
-      group_sync<M>(g);
-      MidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, g);
-    }
-  }
-};
-
-// MULTI: multitaper (K' tapers per frame, frame staged in shared memory by TMA one frame
-// ahead and re-read per taper).  PLAIN: no RA9MB / limiter code in the kernel.
-template <int M, bool MULTI, bool PLAIN>
-__global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(const KParams p) {
-  using GeoM = Geo<M>;
-  constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
-  constexpr bool STAGE = GeoM::STAGE && MULTI;
-  constexpr bool RT = GeoM::RT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int g = threadIdx.x / T;
-  const int t = threadIdx.x % T;
-  unsigned char *gbase = smem_raw + (size_t) g * GeoM::group_bytes(MULTI);
-  float2 *buf = reinterpret_cast<float2 *>(gbase);
-  float *stage = reinterpret_cast<float *>(gbase + GeoM::BUF_BYTES);
-  float *red = reinterpret_cast<float *>(gbase + GeoM::BUF_BYTES + GeoM::stage_bytes(MULTI));
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + GeoM::BUF_BYTES + GeoM::stage_bytes(MULTI) + GeoM::RED_BYTES);
-  const long long gid = (long long) blockIdx.x * G + g;
-  const long long fb = gid * p.frames_per_group;
-  unsigned phase = 0;
-
-  TwRegs tr;
-  if constexpr (RT) load_tw_regs<M>(tr, t, p.tw, p.vtab);
-
-  if (STAGE) {
-    if (t == 0) {
-      mbar_init(mbar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (t == 0 && fb < p.nframes && frame_bulk_ok(p, p.first_frame + fb, N)) {
-      const long long f0 = p.first_frame + fb;
-      mbar_expect_tx(mbar, N * 4);
-      tma_load_1d(stage, p.samples + (f0 * (long long) p.hop - p.n_ov - p.origin), N * 4, mbar);
-    }
-  }
-
-  for (int it = 0; it < p.frames_per_group; ++it) {
-    const long long fl = fb + it;
-    const bool active = fl < p.nframes;
-    const long long f = p.first_frame + fl;
-    const bool staged = STAGE && active && frame_bulk_ok(p, f, N);
-    const bool next_there = (it + 1 < p.frames_per_group) && (fl + 1 < p.nframes);
-    const bool next_staged = STAGE && next_there && frame_bulk_ok(p, f + 1, N);
-    if (staged) {
-      mbar_wait(mbar, phase);
-      phase ^= 1;
-    }
-    if (!STAGE && next_there) {
-      // pull the next frame's new hop block towards L2 while this frame is computed
-      const long long nb = (f + 1) * (long long) p.hop - p.origin;       // first new sample, buffer index
-      for (int i = t * 32; i < p.hop; i += T * 32)
-        if (nb + i >= 0 && nb + i < p.count) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.samples + nb + i));
-    }
-    float acc[17];
-    if (MULTI) {
-#pragma unroll
-      for (int i = 0; i < 17; i++) acc[i] = 0.f;
-    }
-    const int ntap = MULTI ? p.ntapers : 1;
-    for (int j = 0; j < ntap; ++j) {
-      float2 v[kPoints];
-      {
-        float2 x[kPoints];
-        // Control flow around the warp shuffles / barriers of the mean removal depends only
-        // on j (uniform over the CTA), never on a group's own frame: groups of one warp or
-        // CTA can sit on different kinds of frames.
-        if (MULTI && STAGE && j > 0) {
-          // multitaper: tapers after the first read the cleaned copy kept in the staging buffer
-          const float2 *s2 = reinterpret_cast<const float2 *>(stage);
-#pragma unroll
-          for (int q = 0; q < kPoints; q++) x[q] = s2[t + T * q];
-        } else {
-          if (active) {
-            load_raw<M>(x, t, p, f, stage, staged);
-          } else {
-#pragma unroll
-            for (int q = 0; q < kPoints; q++) x[q] = make_float2(0.f, 0.f);
-          }
-          if (p.fused_mean) remove_block_means_qs<M>(x, t, red, p, g);
-          else if (p.means != nullptr && active) remove_table_means<M>(x, t, p, f);
-          if (MULTI && STAGE && ntap > 1) {
-            float2 *s2 = reinterpret_cast<float2 *>(stage);
-#pragma unroll
-            for (int q = 0; q < kPoints; q++) s2[t + T * q] = x[q];     // own elements only: no hazard
-          }
-        }
-        apply_taper<M, PLAIN>(v, x, t, p, p.tapers + (size_t) j * N);
-      }
-      if constexpr (RT) {
-        pass_compute_rt<M, 0>(v, tr);
-        group_sync<M>(g);              // (A) the previous transform's last pass has been read by all
-        pass_scatter<M, 0>(v, t, buf);
-      } else {
-        group_sync<M>(g);
-        pass_store<M, 0>(v, t, buf, p.tw);
-      }
-      if (STAGE && next_staged && j == ntap - 1 && t == 0) {
-        // past barrier (A) everyone is done reading the staging buffer: fetch the next frame
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(mbar, N * 4);
-        tma_load_1d(stage, p.samples + ((f + 1) * (long long) p.hop - p.n_ov - p.origin), N * 4, mbar);
-      }
-      group_sync<M>(g);
-      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
-      auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
-      float *row = (!MULTI && active && p.rows) ? p.rows + fl * p.row_stride : nullptr;
-      float2 *sp = (!MULTI && active && p.spectrum) ? p.spectrum + fl * (long long) (M + 1) : nullptr;
-      const bool db = p.rows_db != 0;
-      const float ss = p.spec_scale;
-      auto sink_single = [&](int slot, float2 a, bool cj) {
-        const int bin = slot_bin<M>(t, slot);
-        if (row) {
-          float y = norm2(a);
-          if (db) y = 10.f * log10f(y);
-          row[bin] = y;
-        }
-        if (sp) sp[bin] = make_float2(a.x * ss, cj ? -a.y * ss : a.y * ss);
-      };
-      if constexpr (RT) {
-        last_pass_rt<M>(v, t, buf, p.tw, tr);
-        if (MULTI) emit_bins_rt<M>(v, t, tr, sink_multi);
-        else emit_bins_rt<M>(v, t, tr, sink_single);
-      } else {
-        last_pass<M>(v, t, buf, p.tw);
-        if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
-        else emit_bins<M>(v, t, p.vtab, sink_single);
-      }
-      // no barrier here: (A) of the next transform orders these reads before its stores
-    }
-    if (MULTI && active && p.rows) {
-      float *row = p.rows + fl * p.row_stride;
-      const bool db = p.rows_db != 0;
-#pragma unroll
-      for (int slot = 0; slot < 17; slot++) {
-        if (slot < 16 || t == 0) {
-          float y = acc[slot];
-          if (db) y = 10.f * log10f(y);
-          row[slot_bin<M>(t, slot)] = y;
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------- ring kernel
-// The fast path for the regular geometry (hop = 2T << QS, N - hop a multiple of hop: 0, 50,
-// 75, 87.5, 93.75 % overlap; no RA9MB / limiter).  A frame is NB = 16 >> QS whole hop blocks.
-// Each frame group keeps the last NB + 1 blocks of its run in a shared-memory ring that is
-// filled by TMA bulk copies (cp.async.bulk + mbarrier), always one block ahead of the FFT,
-// so every sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM
-// latency hides behind the previous frame's transform.  Block means (sub_mean) are computed
-// once per block when it lands and kept beside the ring.
-#ifndef GLB_MEAN_AHEAD
-#define GLB_MEAN_AHEAD 0  // 1: the next block's mean is formed before the last barrier of the current transform
-                          //    (measured 4 % slower: the block has to land 40 % of a frame earlier)
-#endif
-#ifndef GLB_RING_EXTRA
-#define GLB_RING_EXTRA 0  // 1: one spare slot, the next block is requested at the top of a frame;
-#endif                    // 0: NB slots, requested after barrier (A) into the oldest block's slot
-struct RingLayout {
-  int slots;            // NB + GLB_RING_EXTRA
-  size_t ring_off, red_off, mu_off, mbar_off, group_bytes;
-};
-
-template <int M>
-__host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
-  RingLayout L;
-  L.slots = nb + GLB_RING_EXTRA;
-  L.ring_off = Geo<M>::BUF_BYTES;
-  L.red_off = L.ring_off + (size_t) L.slots * hop * sizeof(float);
-  L.mu_off = L.red_off + (size_t) 18 * Geo<M>::NW * sizeof(float);
-  L.mbar_off = ((L.mu_off + 18 * sizeof(float) + 7) / 8) * 8;
-  L.group_bytes = ((L.mbar_off + 18 * sizeof(unsigned long long) + 15) / 16) * 16;
-  return L;
-}
-
-// mean of one ring block: every thread sums its (1 << qs) float2 entries, warps reduce by
-// shuffle, the group combines through `red` (one barrier).  The summation tree of a block is
-// the same wherever the block sits in a frame: its mean is bit-identical in every frame, group
-// and time shard.  Must be called by all threads of the CTA (contains a block barrier).
-template <int M>
-__device__ __forceinline__ float ring_block_partial(const float *blk, int qs, int t, float *red) {
-  constexpr int T = M / kPoints, NW = (T + 31) / 32, W = T < 32 ? T : 32;
-  const float2 *b2 = reinterpret_cast<const float2 *>(blk);
-  float s = 0.f;
-  for (int i = 0; i < (1 << qs); i++) {
-    const float2 a = b2[t + T * i];
-    s += a.x + a.y;
-  }
-#pragma unroll
-  for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (NW > 1 && (t & 31) == 0) red[t >> 5] = s;
-  return s;
-}
-// after a block barrier that follows ring_block_partial()
-template <int M>
-__device__ __forceinline__ float ring_block_total(float s_warp, const float *red, float inv_hop) {
-  constexpr int T = M / kPoints, NW = (T + 31) / 32;
-  float s = s_warp;
-  if (NW > 1) {
-    s = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; w++) s += red[w];
-  }
-  return s * inv_hop;
-}
-template <int M>
-__device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
-  constexpr int T = M / kPoints, NW = (T + 31) / 32;
-  const float s = ring_block_partial<M>(blk, qs, t, red);
-  if (NW > 1) __syncthreads();
-  return ring_block_total<M>(s, red, inv_hop);
-}
-
-// Top of a frame: the NB blocks of the frame from the ring into registers, block means removed.
-// `new_mean`: the newest block has just landed and its mean is not known yet; it is summed from
-// the registers just loaded (same order as ring_block_partial, so the mean of a block is the
-// same bits wherever it is formed), combined across the warps of the group through `red` with
-// one block barrier, and left in mu_new / mu[slot_newest].  The loads of the other blocks are
-// in flight across that barrier.
-template <int M, int QS>
-__device__ __forceinline__ void ring_fetch(float2 (&x)[kPoints], int t, const float *ring, int hop, int slot_oldest,
-                                           int slots, float *mu, float &mu_new, bool sub, bool new_mean, float *red,
-                                           float inv_hop) {
-  constexpr int T = M / kPoints, NB = kPoints >> QS, NW = (T + 31) / 32, W = T < 32 ? T : 32;
-  int sidx = slot_oldest;
-  int slot_of[NB];
-#pragma unroll
-  for (int b = 0; b < NB; b++) {
-    const float2 *bp = reinterpret_cast<const float2 *>(ring + (size_t) sidx * hop);
-    slot_of[b] = sidx;
-#pragma unroll
-    for (int i = 0; i < (1 << QS); i++) x[(b << QS) + i] = bp[t + T * i];
-    sidx = (sidx + 1 == slots) ? 0 : sidx + 1;
-  }
-  if (!sub) return;
-  if (new_mean) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < (1 << QS); i++) {
-      const float2 a = x[((NB - 1) << QS) + i];
-      s += a.x + a.y;
-    }
-#pragma unroll
-    for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (NW > 1) {
-      if ((t & 31) == 0) red[t >> 5] = s;
-      __syncthreads();
-    }
-    mu_new = ring_block_total<M>(s, red, inv_hop);
-    if (t == 0) mu[slot_of[NB - 1]] = mu_new;
-  }
-#pragma unroll
-  for (int b = 0; b < NB; b++) {
-    const float m = (b == NB - 1) ? mu_new : mu[slot_of[b]];
-#pragma unroll
-    for (int i = 0; i < (1 << QS); i++) x[(b << QS) + i] = sub2(x[(b << QS) + i], bc(m));
-  }
-}
-
-// One PSD row out of the registers (slot numbering of fft_core.cuh): slot 2 rp is bin k, slot
-// 2 rp + 1 is bin M - k, k = t + rp 2T except for the upper four pairs of thread 0; base pointers
-// plus immediates.  Thread 0 also owns bin M/2.
-__device__ __forceinline__ void st_row(float *p, float y) {
-#if GLB_L1_POLICY
-  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(y) : "memory");
-#elif GLB_STREAM_STORE
-  __stcs(p, y);
-#else
-  *p = y;
-#endif
-}
-template <int M>
-__device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[17]) {
-  constexpr int T = M / kPoints;
-  const int kh = khi<M>(t) - 8 * T;
-  float *ra = row + t, *rb = row + (M - t), *rah = row + kh, *rbh = row + (M - kh);
-#pragma unroll
-  for (int rp = 0; rp < 8; rp++) {
-    st_row((rp < 4 ? ra : rah) + rp * 2 * T, yv[2 * rp]);
-    st_row((rp < 4 ? rb : rbh) - rp * 2 * T, yv[2 * rp + 1]);
-  }
-  if (t == 0) st_row(row + M / 2, yv[16]);
-}
-
-// mid passes of the ring kernel; `hook` runs before the last block barrier ahead of the final pass
-template <int M, int P, bool RT> struct RingMidPasses {
-  template <class H>
-  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr, H &&hook) {
-    if constexpr (P < Plan<M>::NP - 1) {
-      pass_load<M>(v, t, buf);
-      if constexpr (RT) {
-        pass_compute_rt<M, P>(v, tr);
-        __syncthreads();                // every thread has read before anyone overwrites
-        pass_scatter<M, P>(v, t, buf);
-      } else {
-        __syncthreads();
-        pass_store<M, P>(v, t, buf, tw);
-      }
-      if constexpr (P == Plan<M>::NP - 2) hook();
-      __syncthreads();
-      RingMidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, hook);
-    }
-  }
-};
-
-template <int M, bool MULTI>
-__global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kernel(const KParams p) {
-  using GeoM = Geo<M>;
-  constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
-  constexpr bool RT = GeoM::RT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int g = threadIdx.x / T;
-  const int t = threadIdx.x % T;
-  const int hop = p.hop, qs = p.qs, nb = kPoints >> qs;          // nb blocks per frame
-  const RingLayout L = ring_layout<M>(hop, nb);
-  const int slots = L.slots;
-  unsigned char *gbase = smem_raw + (size_t) g * L.group_bytes;
-  float2 *buf = reinterpret_cast<float2 *>(gbase);
-  float *ring = reinterpret_cast<float *>(gbase + L.ring_off);
-  float *red = reinterpret_cast<float *>(gbase + L.red_off);
-  float *mu = reinterpret_cast<float *>(gbase + L.mu_off);
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + L.mbar_off);
-  const long long gid = (long long) blockIdx.x * G + g;
-  const long long fb = gid * p.frames_per_group;
-  const bool group_active = fb < p.nframes;
-  const long long f_first = p.first_frame + fb;
-  const long long b0 = f_first - (nb - 1);                       // oldest block of the first frame
-  const bool sub = p.fused_mean != 0;
-  const unsigned blk_bytes = (unsigned) hop * 4u;
-  unsigned phase_bits = 0;                                       // one parity bit per ring slot
-
-  TwRegs tr;
-  if constexpr (RT) load_tw_regs<M>(tr, t, p.tw, p.vtab);
-
-  if (t == 0) {
-    for (int sl = 0; sl < slots; sl++) mbar_init(&mbar[sl], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // prologue: the nb blocks of the first frame (zeros before the stream start, fft.c:103-108)
-  for (int lb = 0; lb < nb; lb++) {
-    const long long blk = b0 + lb;
-    if (group_active) {
-      if (blk < 0) {
-        float2 *z = reinterpret_cast<float2 *>(ring + (size_t) lb * hop);
-        for (int i = 0; i < (1 << qs); i++) z[t + T * i] = make_float2(0.f, 0.f);
-      } else if (t == 0) {
-        mbar_expect_tx(&mbar[lb], blk_bytes);
-        tma_load_1d(ring + (size_t) lb * hop, p.samples + (blk * hop - p.origin), blk_bytes, &mbar[lb]);
-      }
-    }
-  }
-  float mu_new = 0.f;
-  for (int lb = 0; lb < nb; lb++) {
-    const long long blk = b0 + lb;
-    if (group_active && blk >= 0) {
-      mbar_wait(&mbar[lb], 0);
-      phase_bits ^= 1u << lb;
-    }
-    if (sub) {
-      __syncthreads();                                           // zero fill visible to all (uniform: groups differ in blk)
-      const float m = ring_block_mean<M>(ring + (size_t) lb * hop, qs, t, red + lb * GeoM::NW, p.inv_hop_mean);
-      mu_new = (blk < 0) ? 0.f : m;
-      if (t == 0) mu[lb] = mu_new;
-    }
-  }
-  __syncthreads();                                               // zero fill and mu[] visible
-
-  int slot_new = nb - 1;                                         // slot of the newest block of frame `it`
-  for (int it = 0; it < p.frames_per_group; ++it) {
-    const long long fl = fb + it;
-    const bool active = fl < p.nframes;
-    const long long f = p.first_frame + fl;
-    const bool next_there = (it + 1 < p.frames_per_group) && (fl + 1 < p.nframes);
-    const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
-#if !GLB_MEAN_AHEAD
-    if (it > 0 && active) {
-      // block f was requested one frame ago
-      mbar_wait(&mbar[slot_new], (phase_bits >> slot_new) & 1u);
-      phase_bits ^= 1u << slot_new;
-    }
-#endif
-    auto request_next = [&]() {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&mbar[slot_next], blk_bytes);
-      tma_load_1d(ring + (size_t) slot_next * hop, p.samples + ((f + 1) * (long long) hop - p.origin), blk_bytes, &mbar[slot_next]);
-    };
-    // spare slot: slot_next held block f - nb, whose last readers passed a block barrier in frame f - 1
-    if (GLB_RING_EXTRA && next_there && t == 0) request_next();
-    // slot of block f - nb + 1: next to the spare slot, or (tight ring) the slot block f + 1 will take
-    const int slot_oldest = GLB_RING_EXTRA ? ((slot_next + 1 == slots) ? 0 : slot_next + 1) : slot_next;
-    float acc[17];
-    if (MULTI) {
-#pragma unroll
-      for (int i = 0; i < 17; i++) acc[i] = 0.f;
-    }
-    const int ntap = MULTI ? p.ntapers : 1;
-    float mu_next = 0.f;
-    for (int j = 0; j < ntap; ++j) {
-      float2 v[kPoints];
-      {
-        float2 x[kPoints];
-        // (mean-ahead variant: the mean is already in mu_new)
-        const bool nm = !GLB_MEAN_AHEAD && it > 0 && j == 0;
-        float *redn = red + slot_new * GeoM::NW;
-        switch (qs) {
-          case 4: ring_fetch<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-          case 3: ring_fetch<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-          case 2: ring_fetch<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-          case 1: ring_fetch<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-          default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-        }
-        apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
-      }
-      // Block f + 1 was requested after barrier (A) of this frame's last taper; before the last
-      // block barrier of the transform every thread waits for it and leaves its share of the
-      // block sum in `red`, so the mean is there after that barrier: the next frame starts
-      // without a barrier of its own and without waiting for DRAM.
-      const bool last_tap = (j == ntap - 1);
-      float s_warp = 0.f;
-      auto land_next = [&]() {
-        if (GLB_MEAN_AHEAD && last_tap && next_there) {
-          mbar_wait(&mbar[slot_next], (phase_bits >> slot_next) & 1u);
-          phase_bits ^= 1u << slot_next;
-          if (sub) s_warp = ring_block_partial<M>(ring + (size_t) slot_next * hop, qs, t, red);
-        }
-      };
-      if constexpr (RT) {
-        pass_compute_rt<M, 0>(v, tr);
-        __syncthreads();               // (A) the previous transform's last pass has been read by all
-        pass_scatter<M, 0>(v, t, buf);
-      } else {
-        __syncthreads();
-        pass_store<M, 0>(v, t, buf, p.tw);
-      }
-      // tight ring: past (A) of the last taper nobody reads the oldest block any more
-      if (!GLB_RING_EXTRA && next_there && last_tap && t == 0) request_next();
-      if constexpr (Plan<M>::NP == 2) land_next();
-      __syncthreads();
-      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, land_next);
-      if (GLB_MEAN_AHEAD && last_tap && next_there && sub) {
-        mu_next = ring_block_total<M>(s_warp, red, p.inv_hop_mean);
-        if (t == 0) mu[slot_next] = mu_next;
-      }
-      float *row = p.rows + fl * p.row_stride;
-      const bool db = p.rows_db != 0;
-      float yv[17];
-      yv[16] = 1.f;                     // only thread 0 has a 17th bin
-      auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
-      auto sink_single = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
-      const bool w0 = t < 32;           // warp-uniform: only the warp that holds thread 0 pays for its re-ordering
-      if constexpr (RT) {
-        last_pass_rt<M>(v, t, buf, p.tw, tr);
-        if (MULTI) {
-          if (w0) emit_bins_rt<M, true>(v, t, tr, sink_multi);
-          else emit_bins_rt<M, false>(v, t, tr, sink_multi);
-        } else {
-          if (w0) emit_bins_rt<M, true>(v, t, tr, sink_single);
-          else emit_bins_rt<M, false>(v, t, tr, sink_single);
-        }
-      } else {
-        last_pass<M>(v, t, buf, p.tw);
-        if (MULTI) {
-          if (w0) emit_bins<M, true>(v, t, p.vtab, sink_multi);
-          else emit_bins<M, false>(v, t, p.vtab, sink_multi);
-        } else {
-          if (w0) emit_bins<M, true>(v, t, p.vtab, sink_single);
-          else emit_bins<M, false>(v, t, p.vtab, sink_single);
-        }
-      }
-      if (!MULTI) {
-        // the row leaves the registers here: one store per bin, streaming (written once, never
-        // re-read by this kernel); the dB conversion is a single uniform branch per frame
-        if (db) {
-#pragma unroll
-          for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
-        }
-        if (active) store_row<M>(row, t, yv);
-      }
-    }
-    if (MULTI && active) {
-      float *row = p.rows + fl * p.row_stride;
-      const bool db = p.rows_db != 0;
-#pragma unroll
-      for (int slot = 0; slot < 17; slot++) {
-        if (slot < 16 || t == 0) {
-          float y = acc[slot];
-          if (db) y = 10.f * log10f(y);
-          row[slot_bin<M>(t, slot)] = y;
-        }
-      }
-    }
-    slot_new = slot_next;
-    if (GLB_MEAN_AHEAD) mu_new = mu_next;
-  }
-}
-
-// ------------------------------------------------------------------------- warp-per-frame kernel
-// Periodogram fast path for N = 512..4096: a frame never leaves its warp (fft_wpf.cuh), so the
-// kernel has no block barrier at all.  Warps walk contiguous runs of INTERIOR frames (no zero
-// history, fully inside the staged samples, 8-byte aligned); the few edge frames of a
-// recording are launched through the general kernel by the host code below.
-#ifndef GLB_WPF_MINB
-#define GLB_WPF_MINB 5
-#endif
-constexpr int kWpfWarps = 2;          // warps per CTA (independent of each other)
-
-// block-mean removal inside one lane group: hop = 2T << QW; block b = registers q with (q >> QW) == b
-template <int M, int QW>
-__device__ __forceinline__ void wpf_remove_means(float2 (&x)[kWP], float inv_hop) {
-  constexpr int T = Wpf<M>::T, NB = kWP >> QW;
-#pragma unroll
-  for (int b = 0; b < NB; b++) {
-    float s = 0.f;
-#pragma unroll
-    for (int q = b << QW; q < (b + 1) << QW; q++) s += x[q].x + x[q].y;
-#pragma unroll
-    for (int o = T / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float m = s * inv_hop;
-#pragma unroll
-    for (int q = b << QW; q < (b + 1) << QW; q++) {
-      x[q].x -= m;
-      x[q].y -= m;
-    }
-  }
-}
-
-template <int M>
-__global__ void __launch_bounds__(32 * kWpfWarps, GLB_WPF_MINB) gram_wpf_kernel(const KParams p) {
-  constexpr int T = Wpf<M>::T, N = 2 * M, FPW = 32 / T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane / T, t = lane % T;
-  float2 *tile = reinterpret_cast<float2 *>(smem_raw) + (size_t) (warp * FPW + g) * (Wpf<M>::TILE + 2);
-  const long long gid = ((long long) blockIdx.x * kWpfWarps + warp) * FPW + g;
-  const long long fb = gid * p.frames_per_group;
-
-  WpfRegs rg;
-  wpf_load_regs<M>(rg, t, p.roots, p.vtab);
-  const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers) + t;
-  const bool db = p.rows_db != 0;
-
-  for (int it = 0; it < p.frames_per_group; ++it) {
-    const long long fl = fb + it;
-    const bool active = fl < p.nframes;
-    // inactive tail iterations recompute the group's last frame without storing (keeps the
-    // warp converged for the shuffles and __syncwarp below)
-    const long long fe = active ? fl : (p.nframes - 1);
-    const long long f = p.first_frame + fe;
-    const float2 *src = reinterpret_cast<const float2 *>(p.samples + (f * (long long) p.hop - p.n_ov - p.origin)) + t;
-    float2 v[kWP];
-#pragma unroll
-    for (int q = 0; q < kWP; q++) v[q] = ldg2(src + T * q);
-    if (fl + 1 < p.nframes && it + 1 < p.frames_per_group) {
-      // pull the next frame's new hop block towards L2 behind this frame's arithmetic
-      const float *nx = p.samples + ((f + 1) * (long long) p.hop - p.origin);
-      for (int i = t * 32; i < p.hop; i += T * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
-    }
-    if (p.fused_mean) {
-      switch (p.qs) {
-        case 6: wpf_remove_means<M, 6>(v, p.inv_hop_mean); break;
-        case 5: wpf_remove_means<M, 5>(v, p.inv_hop_mean); break;
-        case 4: wpf_remove_means<M, 4>(v, p.inv_hop_mean); break;
-        case 3: wpf_remove_means<M, 3>(v, p.inv_hop_mean); break;
-        default: wpf_remove_means<M, 2>(v, p.inv_hop_mean); break;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < kWP; q++) {
-      const float2 w = ldg2(w2 + T * q);
-      v[q].x *= w.x;
-      v[q].y *= w.y;
-    }
-    wpf_pass_a<M>(v);
-    __syncwarp();                      // the previous frame's gathers are done
-    wpf_scatter<M>(v, t, tile);
-    __syncwarp();
-    wpf_gather<M>(v, t, tile);
-    wpf_pass_b<M>(v, t, rg);
-    float *row = p.rows + fe * p.row_stride;
-    wpf_emit<M>(v, t, rg, [&](int, int bin, float2 a, bool) {
-      float y = norm2(a);
-      if (db) y = 10.f * log10f(y);
-      if (active) row[bin] = y;
-    });
-  }
-}
-
-template <int M>
-static int launch_wpf(const KParams &kp, cudaStream_t st) {
-  int dev = 0, sms = 0;
-  CU(cudaGetDevice(&dev));
-  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  constexpr int FPW = 32 / Wpf<M>::T;
-  const size_t smem = (size_t) kWpfWarps * FPW * (Wpf<M>::TILE + 2) * sizeof(float2);
-  static thread_local int occ_cache[64];
-  int &occ = occ_cache[dev & 63];
-  if (occ == 0) {
-    CU(cudaFuncSetAttribute(gram_wpf_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gram_wpf_kernel<M>, 32 * kWpfWarps, smem));
-    if (occ < 1) occ = 1;
-  }
-  long long groups = (long long) sms * occ * kWpfWarps * FPW;
-  if (groups > kp.nframes) groups = kp.nframes;
-  if (groups < 1) groups = 1;
-  KParams k = kp;
-  k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
-  const long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-  const int ctas = (int) ((used + kWpfWarps * FPW - 1) / (kWpfWarps * FPW));
-  gram_wpf_kernel<M><<<ctas, 32 * kWpfWarps, smem, st>>>(k);
-  CU(cudaGetLastError());
-  g_launches++;
-  return GLB_OK;
-}
-
-// which kernel family serves a launch (tests / experiments can pin one)
-static int g_kernel_pref = 0;        // 0 auto, 1 general, 2 ring, 3 warp-per-frame
-extern "C" void glb_set_kernel_preference(int pref) { g_kernel_pref = pref; }
-
-template <int M>
-static int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st, int allow) {
-  using GeoM = Geo<M>;
-  int dev = 0, sms = 0;
-  CU(cudaGetDevice(&dev));
-  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const bool plain = multi || (kp.ra9mb_a <= 0.f && kp.limiter == 0);
-  // ---- fastest path (N <= 4096 periodograms): warp-per-frame kernel on the interior frames
-  if constexpr (M >= 256 && M <= 2048) {
-    constexpr int unitw = 2 * Wpf<M>::T;
-    int qw = -1;
-    for (int s2 = 2; s2 <= 6; s2++)
-      if (kp.hop == (unitw << s2)) qw = s2;
-    const bool mean_ok = !kp.fused_mean || (qw >= 0 && (kp.n_ov % kp.hop) == 0);
-    const bool pref_ok = (allow & 4) != 0;
-    if (pref_ok && !multi && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && mean_ok &&
-        (kp.hop % 2) == 0 && ((kp.n_ov + kp.origin) % 2) == 0 && ((reinterpret_cast<uintptr_t>(kp.samples) & 7) == 0)) {
-      // interior frames: f*hop - n_ov >= max(origin, 0) and the frame ends inside the staged samples
-      const long long lo_s = kp.origin > 0 ? kp.origin : 0;
-      long long f_lo = (lo_s + kp.n_ov + kp.hop - 1) / kp.hop;
-      long long f_hi = (kp.origin + kp.count - kp.hop) / kp.hop + 1;       // exclusive: (f+1)*hop <= origin+count
-      if (f_lo < kp.first_frame) f_lo = kp.first_frame;
-      if (f_hi > kp.first_frame + kp.nframes) f_hi = kp.first_frame + kp.nframes;
-      if (f_hi > f_lo) {
-        KParams kw = kp;
-        kw.qs = qw;
-        kw.first_frame = f_lo;
-        kw.nframes = f_hi - f_lo;
-        kw.rows = kp.rows + (f_lo - kp.first_frame) * kp.row_stride;
-        int rc = launch_wpf<M>(kw, st);
-        if (rc != GLB_OK) return rc;
-        // edge frames before / after the interior run go through the kernels below
-        KParams ke = kp;
-        if (f_lo > kp.first_frame) {
-          ke.nframes = f_lo - kp.first_frame;
-          rc = launch_gram_m<M>(ke, multi, groups_hint, st, 1);
-          if (rc != GLB_OK) return rc;
-        }
-        if (f_hi < kp.first_frame + kp.nframes) {
-          ke = kp;
-          ke.first_frame = f_hi;
-          ke.nframes = kp.first_frame + kp.nframes - f_hi;
-          ke.rows = kp.rows + (f_hi - kp.first_frame) * kp.row_stride;
-          rc = launch_gram_m<M>(ke, multi, groups_hint, st, 1);
-          if (rc != GLB_OK) return rc;
-        }
-        return GLB_OK;
-      }
-    }
-  }
-  // ---- fast path: regular geometry, rows only, 16-byte aligned blocks -> TMA ring kernel
-  {
-    const int unit = 2 * GeoM::T;
-    int qs = -1;
-    for (int s2 = 0; s2 <= 4; s2++)
-      if (kp.hop == (unit << s2)) qs = s2;
-    const bool regular = qs >= 0 && (kp.n_ov % kp.hop) == 0 && (kp.hop % 4) == 0 && (kp.origin % 4) == 0 &&
-                         ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0);
-    if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && (allow & 2) != 0) {
-      const int nb = kPoints >> qs;
-      const RingLayout L = ring_layout<M>(kp.hop, nb);
-      const size_t smem = (size_t) GeoM::G * L.group_bytes;
-      if (smem <= 227 * 1024) {
-        auto rk = multi ? gram_ring_kernel<M, true> : gram_ring_kernel<M, false>;
-        static thread_local int occ_ring[2][5][64];
-        int &occ = occ_ring[multi ? 1 : 0][qs][dev & 63];
-        if (occ == 0) {
-          // opt in to the device maximum once: the ring size (hence the launch's smem) varies with the overlap
-          CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk, GeoM::THREADS, smem));
-          if (occ < 1) occ = -1;
-        }
-        // big frames: the ring must not cost more residency than it saves in traffic
-        int occ_generic_bound = (int) ((227 * 1024) / GeoM::smem_bytes(false));
-        const bool worth = occ >= 2 || (occ >= 1 && occ_generic_bound <= 1) || GeoM::THREADS >= 1024 || g_kernel_pref == 2;
-        if (occ >= 1 && worth) {
-          long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
-          if (groups > kp.nframes) groups = kp.nframes;
-          if (groups < 1) groups = 1;
-          KParams k = kp;
-          k.qs = qs;
-          k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
-          long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-          int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
-          rk<<<ctas, GeoM::THREADS, smem, st>>>(k);
-          CU(cudaGetLastError());
-          g_launches++;
-          return GLB_OK;
-        }
-      }
-    }
-  }
-  const int variant = multi ? 2 : (plain ? 1 : 0);
-  auto kern = multi ? gram_kernel<M, true, true> : (plain ? gram_kernel<M, false, true> : gram_kernel<M, false, false>);
-  // the staging buffer is only carved out for the multitaper variant
-  const size_t smem = GeoM::smem_bytes(multi);
-  // per (device, variant): opt in to the dynamic shared memory once, cache the occupancy
-  static thread_local int occ_cache[3][64];
-  int &occ = occ_cache[variant][dev & 63];
-  if (occ == 0) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GeoM::THREADS, smem));
-    if (occ < 1) occ = 1;
-  }
-  // resident grid: every CTA slot of the chip holds G frame groups, each walking a
-  // contiguous run of frames (keeps the overlapped samples of consecutive frames in L1/L2)
-  long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
-  if (groups > kp.nframes) groups = kp.nframes;
-  if (groups < 1) groups = 1;
-  KParams k = kp;
-  k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
-  long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-  int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
-  // regular geometry for the fused block means: hop = 2T << qs, n_ov a multiple of hop
-  k.fused_mean = 0;
-  k.qs = 0;
-  if (kp.fused_mean) {
-    const int unit = 2 * GeoM::T;
-    int qs = -1;
-    for (int s2 = 0; s2 <= 4; s2++)
-      if (kp.hop == (unit << s2)) qs = s2;
-    if (qs >= 0 && (k.n_ov % kp.hop) == 0) {
-      k.fused_mean = 1;
-      k.qs = qs;
-    } else {
-      glb_set_error("glb_launch_gram: fused block means need hop = (N/16) << s, s = 0..4");
-      return GLB_EINVAL;
-    }
-  }
-  kern<<<ctas, GeoM::THREADS, smem, st>>>(k);
-  CU(cudaGetLastError());
-  g_launches++;
-  return GLB_OK;
-}
-
 extern "C" int glb_gram_fused_mean_ok(int n, int hop) {
   if (!glb_fft_supported(n) || hop < 1 || hop > n) return 0;
   const int unit = n / 16;            // 2T
@@ -1251,19 +215,12 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   int allow = 3;
   if (g_force_generic || g_kernel_pref == 1) allow = 1;
   else if (g_kernel_pref == 3) allow = 7;
-  switch (a->n / 2) {
-    case 16: return launch_gram_m<16>(k, multi, a->groups_hint, st, allow);
-    case 32: return launch_gram_m<32>(k, multi, a->groups_hint, st, allow);
-    case 64: return launch_gram_m<64>(k, multi, a->groups_hint, st, allow);
-    case 128: return launch_gram_m<128>(k, multi, a->groups_hint, st, allow);
-    case 256: return launch_gram_m<256>(k, multi, a->groups_hint, st, allow);
-    case 512: return launch_gram_m<512>(k, multi, a->groups_hint, st, allow);
-    case 1024: return launch_gram_m<1024>(k, multi, a->groups_hint, st, allow);
-    case 2048: return launch_gram_m<2048>(k, multi, a->groups_hint, st, allow);
-    case 4096: return launch_gram_m<4096>(k, multi, a->groups_hint, st, allow);
-    case 8192: return launch_gram_m<8192>(k, multi, a->groups_hint, st, allow);
-    case 16384: return launch_gram_m<16384>(k, multi, a->groups_hint, st, allow);
-  }
+  const int m = a->n / 2;
+  int rc = glb_gram_part_0(m, k, multi, a->groups_hint, st, allow);
+  if (rc == -1) rc = glb_gram_part_1(m, k, multi, a->groups_hint, st, allow);
+  if (rc == -1) rc = glb_gram_part_2(m, k, multi, a->groups_hint, st, allow);
+  if (rc == -1) rc = glb_gram_part_3(m, k, multi, a->groups_hint, st, allow);
+  if (rc != -1) return rc;
   return GLB_EINVAL;
 }
 
