@@ -247,9 +247,28 @@ template <int M> GLB_HD int ld_index(int t, int q) {
   else return pad(t + T * q);
 }
 
-// pass_store<M,P>: twiddle (P > 0), radix-R butterflies on the 16 register points
-// and Stockham store: butterfly j = t + u*T (u < 16/R), k = j mod Ns, output r' goes
-// to entry (j - k) * R + k + r' * Ns.
+// Where the outputs of pass P go (Stockham): butterfly j = t + u T, k = j mod Ns, output r' is
+// entry (j - k) R + k + r' Ns of the next pass; in buffer terms a per-thread base plus r' times a
+// compile-time stride, for each of the three layouts (first pass, pass feeding the last, other).
+template <int M, int P> GLB_HD int scatter_base(int t, int u) {
+  constexpr int T = M / kPoints;
+  constexpr int R = PlanRadix<M, P>::R, Ns = PlanRadix<M, P>::Ns;
+  const int j = t + u * T;
+  const int k = j & (Ns - 1);
+  if constexpr (P == 0 && R == 16) return 17 * j;
+  else if constexpr (LastLayout<M>::value && P == Plan<M>::NP - 2) return last_phys(k, (j - k) / Ns);
+  else if constexpr (Ns % 16 == 0) return pad((j - k) * R + k);
+  else return (j - k) * R + k;                      // unpadded natural index: use scatter_index()
+}
+template <int M, int P> GLB_HD int scatter_index(int base, int r) {
+  constexpr int R = PlanRadix<M, P>::R, Ns = PlanRadix<M, P>::Ns;
+  if constexpr (P == 0 && R == 16) return base + r;
+  else if constexpr (LastLayout<M>::value && P == Plan<M>::NP - 2) return base + r * 9 * Ns;
+  else if constexpr (Ns % 16 == 0) return base + r * (Ns + Ns / 16);
+  else return pad(base + r * Ns);
+}
+
+// pass_store<M,P>: twiddle (P > 0), radix-R butterflies on the 16 register points and Stockham store
 template <int M, int P>
 GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
   constexpr int T = M / kPoints;
@@ -266,24 +285,9 @@ GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
       for (int r = 1; r < R; r++) v[u + r * S] = cmul(v[u + r * S], twp[(r - 1) * Ns]);
     }
     Dft<R, S>::run(v + u);
-    if constexpr (P == 0 && R == 16) {
-      // 16 consecutive entries 16j..16j+15 -> padded 17j..17j+15 (64-bit stores: lanes 17 entries apart)
-      float2 *dst = buf + 17 * j;
+    const int base = scatter_base<M, P>(t, u);
 #pragma unroll
-      for (int r = 0; r < 16; r++) dst[r] = v[u + r * S];
-    } else if constexpr (LastLayout<M>::value && P == Plan<M>::NP - 2) {
-      const int base = last_phys(k, (j - k) / Ns);
-#pragma unroll
-      for (int r = 0; r < R; r++) buf[base + r * 9 * Ns] = v[u + r * S];
-    } else if constexpr (Ns % 16 == 0) {
-      const int base = pad((j - k) * R + k);
-#pragma unroll
-      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 16)] = v[u + r * S];
-    } else {
-      const int base = (j - k) * R + k;
-#pragma unroll
-      for (int r = 0; r < R; r++) buf[pad(base + r * Ns)] = v[u + r * S];
-    }
+    for (int r = 0; r < R; r++) buf[scatter_index<M, P>(base, r)] = v[u + r * S];
   }
 }
 
@@ -470,29 +474,36 @@ GLB_HD void pass_compute_rt(float2 *v, const TwRegs &tr, H &&loaded = H()) {
 
 template <int M, int P>
 GLB_HD void pass_scatter(const float2 *v, int t, float2 *buf) {
-  constexpr int T = M / kPoints;
-  constexpr int R = PlanRadix<M, P>::R, Ns = PlanRadix<M, P>::Ns, S = kPoints / R;
+  constexpr int R = PlanRadix<M, P>::R, S = kPoints / R;
 #pragma unroll
   for (int u = 0; u < S; u++) {
-    const int j = t + u * T;
-    const int k = j & (Ns - 1);
-    if constexpr (P == 0 && R == 16) {
-      float2 *dst = buf + 17 * j;
+    const int base = scatter_base<M, P>(t, u);
 #pragma unroll
-      for (int r = 0; r < 16; r++) dst[r] = v[u + r * S];
-    } else if constexpr (LastLayout<M>::value && P == Plan<M>::NP - 2) {
-      const int base = last_phys(k, (j - k) / Ns);
+    for (int r = 0; r < R; r++) buf[scatter_index<M, P>(base, r)] = v[u + r * S];
+  }
+}
+
+// Two frames at once: the buffer holds float4 entries (frame A's value, frame B's value) at the
+// same entry indices, so every exchange is a 128-bit access (quarter-warps of 8 lanes: the
+// layouts above stay conflict free, 17 j, 9 k and consecutive entries all being distinct mod 8).
+template <int M, int P>
+GLB_HD void pass_scatter2(const float2 *va, const float2 *vb, int t, float4 *buf) {
+  constexpr int R = PlanRadix<M, P>::R, S = kPoints / R;
 #pragma unroll
-      for (int r = 0; r < R; r++) buf[base + r * 9 * Ns] = v[u + r * S];
-    } else if constexpr (Ns % 16 == 0) {
-      const int base = pad((j - k) * R + k);
+  for (int u = 0; u < S; u++) {
+    const int base = scatter_base<M, P>(t, u);
 #pragma unroll
-      for (int r = 0; r < R; r++) buf[base + r * (Ns + Ns / 16)] = v[u + r * S];
-    } else {
-      const int base = (j - k) * R + k;
+    for (int r = 0; r < R; r++)
+      buf[scatter_index<M, P>(base, r)] = make_float4(va[u + r * S].x, va[u + r * S].y, vb[u + r * S].x, vb[u + r * S].y);
+  }
+}
+template <int M>
+GLB_HD void pass_load2(float2 *va, float2 *vb, int t, const float4 *buf) {
 #pragma unroll
-      for (int r = 0; r < R; r++) buf[pad(base + r * Ns)] = v[u + r * S];
-    }
+  for (int q = 0; q < kPoints; q++) {
+    const float4 e = buf[ld_index<M>(t, q)];
+    va[q] = make_float2(e.x, e.y);
+    vb[q] = make_float2(e.z, e.w);
   }
 }
 
@@ -525,33 +536,9 @@ GLB_HD float2 w16_mulc(float2 q, int e) {
   }
 }
 
-// last pass with register twiddles; on return v[r'] = Z[jA + r' 2T], v[8 + r'] = Z[jB + r' 2T]
+// butterflies of the last pass on loaded inputs (v[0..7] butterfly A = t, v[8..15] butterfly B)
 template <int M>
-GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, const TwRegs &tr) {
-  constexpr int T = M / kPoints, NP = Plan<M>::NP, Ns = 2 * T;
-  const int jA = t;
-  const int jB = (t == 0) ? T : 2 * T - t;
-  if constexpr (LastLayout<M>::value) {
-    const int bA = last_phys(jA, 0), bB = last_phys(jB, 0);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      v[r] = buf[bA + r];
-      v[8 + r] = buf[bB + r];
-    }
-  } else if constexpr (Ns % 16 == 0) {
-    const int bA = pad(jA), bB = pad(jB);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      v[r] = buf[bA + r * (Ns + Ns / 16)];
-      v[8 + r] = buf[bB + r * (Ns + Ns / 16)];
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      v[r] = buf[pad(jA + r * Ns)];
-      v[8 + r] = buf[pad(jB + r * Ns)];
-    }
-  }
+GLB_HD void last_pass_compute_rt(float2 *v, int t, const TwRegs &tr) {
   const Tw3 w1 = tr.last[0], w2 = tr.last[1], w3 = tr.last[2], w4 = tr.last[3];
   // A: x_r w_a^r, w_a^(4+b) applied as w_a^4 then w_a^b
 #pragma unroll
@@ -585,6 +572,47 @@ GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, 
 #pragma unroll
   for (int r = 0; r < 8; r++) v[8 + r] = y[(r + 1) & 7];
 }
+
+// buffer index of input r of butterfly j of the last pass
+template <int M> GLB_HD int last_index(int j, int r) {
+  constexpr int T = M / kPoints, Ns = 2 * T;
+  if constexpr (LastLayout<M>::value) return last_phys(j, r);
+  else if constexpr (Ns % 16 == 0) return pad(j) + r * (Ns + Ns / 16);
+  else return pad(j + r * Ns);
+}
+template <int M>
+GLB_HD void last_pass_load(float2 *v, int t, const float2 *buf) {
+  constexpr int T = M / kPoints;
+  const int jA = t;
+  const int jB = (t == 0) ? T : 2 * T - t;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    v[r] = buf[last_index<M>(jA, r)];
+    v[8 + r] = buf[last_index<M>(jB, r)];
+  }
+}
+template <int M>
+GLB_HD void last_pass_load2(float2 *va, float2 *vb, int t, const float4 *buf) {
+  constexpr int T = M / kPoints;
+  const int jA = t;
+  const int jB = (t == 0) ? T : 2 * T - t;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const float4 a = buf[last_index<M>(jA, r)], b = buf[last_index<M>(jB, r)];
+    va[r] = make_float2(a.x, a.y);
+    vb[r] = make_float2(a.z, a.w);
+    va[8 + r] = make_float2(b.x, b.y);
+    vb[8 + r] = make_float2(b.z, b.w);
+  }
+}
+
+// last pass with register twiddles; on return v[r'] = Z[jA + r' 2T], v[8 + r'] = Z[jB + r' 2T]
+template <int M>
+GLB_HD void last_pass_rt(float2 *v, int t, const float2 *buf, const float2 *tw, const TwRegs &tr) {
+  last_pass_load<M>(v, t, buf);
+  last_pass_compute_rt<M>(v, t, tr);
+}
+
 
 // ------------------------------------------------------------------ bins of the final pass
 // After the last pass thread t >= 1 holds butterflies A = t and B = 2T - t: pair rp (0..7) is

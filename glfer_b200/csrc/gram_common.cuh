@@ -843,6 +843,228 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kerne
   }
 }
 
+// mid passes of the pair kernel (both frames through each pass, float4 exchange)
+template <int M, int P> struct PairMidPasses {
+  static __device__ __forceinline__ void run(float2 (&va)[kPoints], float2 (&vb)[kPoints], int t, float4 *buf, const TwRegs &tr) {
+    if constexpr (P < Plan<M>::NP - 1) {
+      pass_load2<M>(va, vb, t, buf);
+      pass_compute_rt<M, P>(va, tr);
+      pass_compute_rt<M, P>(vb, tr);
+      __syncthreads();                  // every thread has read before anyone overwrites
+      pass_scatter2<M, P>(va, vb, t, buf);
+      __syncthreads();
+      PairMidPasses<M, P + 1>::run(va, vb, t, buf, tr);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------- pair kernel
+// Periodogram fast path for 50 % and 75 % overlap (register-twiddle plans): every thread carries
+// the same 16 points of TWO consecutive frames f, f + 1 through the transform.  The two frames
+// share the taper loads and all but one of their ring blocks, the exchange buffer holds float4
+// entries (frame A's value, frame B's value) so every shared-memory access is 128 bits, and the
+// five block barriers, the loop bookkeeping and the address arithmetic are paid once per pair.
+// The two independent butterfly streams also give the scheduler twice the ILP per warp.
+// Ring: the NB + 1 blocks of the pair; after barrier (A) the two oldest slots are handed to one
+// bulk-copy transaction (two copies, one mbarrier) for the blocks of the next pair.
+template <int M, int QS> struct PairGeo {
+  static constexpr int T = M / kPoints, NB = kPoints >> QS, SLOTS = NB + 1, NW = (T + 31) / 32;
+  static constexpr int HOP = (2 * T) << QS;                          // samples per block
+  static constexpr int G = Geo<M>::G, THREADS = Geo<M>::THREADS;
+  static constexpr size_t BUF_BYTES = (size_t) BufSize<M>::value * sizeof(float4);
+  static constexpr size_t RING_OFF = BUF_BYTES;
+  static constexpr size_t RED_OFF = RING_OFF + (size_t) SLOTS * HOP * sizeof(float);
+  static constexpr size_t MU_OFF = RED_OFF + (((size_t) (NB + 1) * NW * sizeof(float) + 15) / 16) * 16;
+  static constexpr size_t MBAR_OFF = MU_OFF + (((size_t) SLOTS * sizeof(float) + 15) / 16) * 16;
+  static constexpr size_t GROUP_BYTES = MBAR_OFF + 16;
+  static constexpr size_t SMEM = (size_t) G * GROUP_BYTES;
+  static constexpr int MINB_ = 65536 / (THREADS * 168);
+  static constexpr int MINB = MINB_ < 1 ? 1 : MINB_;
+};
+
+template <int M, int QS>
+__global__ void __launch_bounds__(Geo<M>::THREADS, (PairGeo<M, QS>::MINB)) gram_pair_kernel(const KParams p) {
+  using PG = PairGeo<M, QS>;
+  constexpr int T = PG::T, G = PG::G, N = 2 * M, NB = PG::NB, SLOTS = PG::SLOTS, NW = PG::NW, HOP = PG::HOP;
+  constexpr int BQ = 1 << QS;                                        // float2 entries per thread and block
+  constexpr int W = T < 32 ? T : 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int g = threadIdx.x / T;
+  const int t = threadIdx.x % T;
+  unsigned char *gbase = smem_raw + (size_t) g * PG::GROUP_BYTES;
+  float4 *buf = reinterpret_cast<float4 *>(gbase);
+  float *ring = reinterpret_cast<float *>(gbase + PG::RING_OFF);
+  float *red = reinterpret_cast<float *>(gbase + PG::RED_OFF);
+  float *mu = reinterpret_cast<float *>(gbase + PG::MU_OFF);
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + PG::MBAR_OFF);
+  const long long gid = (long long) blockIdx.x * G + g;
+  const long long fb = gid * p.frames_per_group;                    // frames_per_group is even
+  const bool group_active = fb < p.nframes;
+  const long long f_first = p.first_frame + fb;
+  const bool sub = p.fused_mean != 0;
+  constexpr unsigned blk_bytes = (unsigned) HOP * 4u;
+  unsigned phase = 0;
+
+  TwRegs tr;
+  load_tw_regs<M>(tr, t, p.tw, p.vtab);
+
+  if (t == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // prologue: blocks f_first - NB + 1 .. f_first + 1 into slots 0..NB (zeros before the stream
+  // start, fft.c:103-108, and for a block past the last frame of the launch)
+  {
+    const long long b0 = f_first - (NB - 1);
+    const bool b_there = fb + 1 < p.nframes;                         // frame B of the first pair exists
+    unsigned bytes = 0;
+#pragma unroll
+    for (int lb = 0; lb <= NB; lb++) {
+      const long long blk = b0 + lb;
+      const bool want = group_active && blk >= 0 && (lb < NB || b_there);
+      if (!want) {
+        float2 *z = reinterpret_cast<float2 *>(ring + (size_t) lb * HOP);
+#pragma unroll
+        for (int i = 0; i < BQ; i++) z[t + T * i] = make_float2(0.f, 0.f);
+      } else {
+        bytes += blk_bytes;
+      }
+    }
+    if (bytes != 0) {
+      if (t == 0) {
+        mbar_expect_tx(mbar, bytes);
+#pragma unroll
+        for (int lb = 0; lb <= NB; lb++) {
+          const long long blk = b0 + lb;
+          if (blk >= 0 && (lb < NB || b_there))
+            tma_load_1d(ring + (size_t) lb * HOP, p.samples + (blk * HOP - p.origin), blk_bytes, mbar);
+        }
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    }
+    __syncthreads();                                                 // zero fill visible
+    // means of the NB - 1 oldest blocks; the two newest are summed from registers in the loop
+    if (sub) {
+#pragma unroll
+      for (int lb = 0; lb < NB - 1; lb++) {
+        const float m = ring_block_mean<M>(ring + (size_t) lb * HOP, QS, t, red + lb * NW, p.inv_hop_mean);
+        if (t == 0) mu[lb] = m;
+      }
+      __syncthreads();
+    }
+  }
+
+  int s0 = 0;                                                        // slot of the oldest block of the pair
+  bool pending = false;                                              // a bulk copy for this pair is in flight
+  for (int it = 0; it < p.frames_per_group; it += 2) {
+    const long long fl = fb + it;
+    const bool active_a = fl < p.nframes, active_b = fl + 1 < p.nframes;
+    const long long f = p.first_frame + fl;
+    if (pending) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+    }
+    int slot_of[NB + 1];
+#pragma unroll
+    for (int lb = 0; lb <= NB; lb++) slot_of[lb] = (s0 + lb) % SLOTS;
+
+    float2 va[kPoints], vb[kPoints];
+    {
+      // the NB + 1 blocks of the pair: frame A is x[0..15], frame B is x[BQ..BQ+15]
+      float2 x[kPoints + BQ];
+#pragma unroll
+      for (int lb = 0; lb <= NB; lb++) {
+        const float2 *bp = reinterpret_cast<const float2 *>(ring + (size_t) slot_of[lb] * HOP);
+#pragma unroll
+        for (int i = 0; i < BQ; i++) x[lb * BQ + i] = bp[t + T * i];
+      }
+      float m[NB + 1];
+#pragma unroll
+      for (int lb = 0; lb <= NB; lb++) m[lb] = 0.f;
+      if (sub) {
+        // the two newest blocks: sums from the registers just loaded, in the order of
+        // ring_block_partial (a block's mean is the same bits wherever it is formed)
+        float sn[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < BQ; i++) {
+            const float2 c = x[(NB - 1 + e) * BQ + i];
+            a += c.x + c.y;
+          }
+#pragma unroll
+          for (int o = W / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          sn[e] = a;
+        }
+        if (NW > 1) {
+          if ((t & 31) == 0) {
+            red[t >> 5] = sn[0];
+            red[NW + (t >> 5)] = sn[1];
+          }
+          __syncthreads();
+        }
+        m[NB - 1] = ring_block_total<M>(sn[0], red, p.inv_hop_mean);
+        m[NB] = ring_block_total<M>(sn[1], red + NW, p.inv_hop_mean);
+#pragma unroll
+        for (int lb = 0; lb < NB - 1; lb++) m[lb] = mu[slot_of[lb]];
+        if (t == 0) {
+          mu[slot_of[NB - 1]] = m[NB - 1];
+          mu[slot_of[NB]] = m[NB];
+        }
+      }
+      const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers);
+#pragma unroll
+      for (int q = 0; q < kPoints; q++) {
+        const float2 w = ld_taper(w2 + t + T * q);
+        va[q] = mul2(sub2(x[q], bc(m[q >> QS])), w);
+        vb[q] = mul2(sub2(x[q + BQ], bc(m[(q >> QS) + 1])), w);
+      }
+    }
+    pass_compute_rt<M, 0>(va, tr);
+    pass_compute_rt<M, 0>(vb, tr);
+    __syncthreads();                   // (A) the previous pair's last pass and this pair's ring reads are done
+    pass_scatter2<M, 0>(va, vb, t, buf);
+    {
+      // the two oldest slots take the newest blocks of the next pair
+      const bool next_a = (it + 2 < p.frames_per_group) && (fl + 2 < p.nframes);
+      const bool next_b = next_a && (fl + 3 < p.nframes);
+      pending = next_a;
+      if (next_a && t == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, next_b ? 2 * blk_bytes : blk_bytes);
+        tma_load_1d(ring + (size_t) slot_of[0] * HOP, p.samples + ((f + 2) * (long long) HOP - p.origin), blk_bytes, mbar);
+        if (next_b)
+          tma_load_1d(ring + (size_t) slot_of[1] * HOP, p.samples + ((f + 3) * (long long) HOP - p.origin), blk_bytes, mbar);
+      }
+    }
+    __syncthreads();
+    PairMidPasses<M, 1>::run(va, vb, t, buf, tr);
+    last_pass_load2<M>(va, vb, t, buf);
+    const bool db = p.rows_db != 0;
+    const bool w0 = t < 32;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      float2 *v = e == 0 ? va : vb;
+      last_pass_compute_rt<M>(v, t, tr);
+      float yv[17];
+      yv[16] = 1.f;
+      auto sink = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
+      if (w0) emit_bins_rt<M, true>(v, t, tr, sink);
+      else emit_bins_rt<M, false>(v, t, tr, sink);
+      if (db) {
+#pragma unroll
+        for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
+      }
+      if (e == 0 ? active_a : active_b) store_row<M>(p.rows + (fl + e) * p.row_stride, t, yv);
+    }
+    s0 = (s0 + 2) % SLOTS;
+  }
+}
+
 // ------------------------------------------------------------------------- warp-per-frame kernel
 // Periodogram fast path for N = 512..4096: a frame never leaves its warp (fft_wpf.cuh), so the
 // kernel has no block barrier at all.  Warps walk contiguous runs of INTERIOR frames (no zero
@@ -1013,7 +1235,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
       }
     }
   }
-  // ---- fast path: regular geometry, rows only, 16-byte aligned blocks -> TMA ring kernel
+  // ---- fast path: regular geometry, rows only, 16-byte aligned blocks -> TMA ring / pair kernel
   {
     const int unit = 2 * GeoM::T;
     int qs = -1;
@@ -1021,6 +1243,38 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
       if (kp.hop == (unit << s2)) qs = s2;
     const bool regular = qs >= 0 && (kp.n_ov % kp.hop) == 0 && (kp.hop % 4) == 0 && (kp.origin % 4) == 0 &&
                          ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0);
+    if constexpr (GeoM::RT && M >= 256) {
+      // 50 % / 75 % overlap periodograms: two frames per thread (selectable family: measured
+      // 0.431 ms vs 0.422 ms for the ring kernel on the metric workload, 3 CTAs/SM vs 6)
+      if (regular && !multi && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr &&
+          (allow & 8) != 0 && (qs == 3 || qs == 2) && kp.nframes >= 2) {
+        void (*pk)(const KParams) = qs == 3 ? gram_pair_kernel<M, 3> : gram_pair_kernel<M, 2>;
+        const size_t smem = qs == 3 ? PairGeo<M, 3>::SMEM : PairGeo<M, 2>::SMEM;
+        static thread_local int occ_pair[2][64];
+        int &occ = occ_pair[qs - 2][dev & 63];
+        if (occ == 0) {
+          CU(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, GeoM::THREADS, smem));
+          if (occ < 1) occ = -1;
+        }
+        if (occ >= 1) {
+          long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
+          if (groups > (kp.nframes + 1) / 2) groups = (kp.nframes + 1) / 2;
+          if (groups < 1) groups = 1;
+          KParams k = kp;
+          k.qs = qs;
+          long long fpg = (kp.nframes + groups - 1) / groups;
+          fpg += fpg & 1;                                            // whole pairs per group
+          k.frames_per_group = (int) fpg;
+          long long used = (kp.nframes + fpg - 1) / fpg;
+          int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
+          pk<<<ctas, GeoM::THREADS, smem, st>>>(k);
+          CU(cudaGetLastError());
+          g_launches++;
+          return GLB_OK;
+        }
+      }
+    }
     if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && (allow & 2) != 0) {
       const int nb = kPoints >> qs;
       const RingLayout L = ring_layout<M>(kp.hop, nb);
@@ -1041,7 +1295,8 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
         }
         // big frames: the ring must not cost more residency than it saves in traffic
         int occ_generic_bound = (int) ((227 * 1024) / GeoM::smem_bytes(false));
-        const bool worth = occ >= 2 || (occ >= 1 && occ_generic_bound <= 1) || GeoM::THREADS >= 1024 || g_kernel_pref == 2;
+        // (N = 16384: one 512-thread CTA per SM with the ring still beats two without, 2.39 vs 2.55 ms)
+        const bool worth = occ >= 2 || (occ >= 1 && occ_generic_bound <= 1) || GeoM::THREADS >= 512 || g_kernel_pref == 2;
         if (occ >= 1 && worth) {
           long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
           if (groups > kp.nframes) groups = kp.nframes;

@@ -212,9 +212,10 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   // (automatic = ring then general: measured on B200 the ring kernel is the fastest family at
   // N = 4096, 0.726 ms vs 0.746 ms for warp-per-frame, whose 67 KB of straight-line code per
   // frame stalls on instruction fetch; warp-per-frame stays selectable for experiments)
-  int allow = 3;
+  int allow = 3;                                  // 1 general, 2 ring, 4 warp-per-frame, 8 pair
   if (g_force_generic || g_kernel_pref == 1) allow = 1;
   else if (g_kernel_pref == 3) allow = 7;
+  else if (g_kernel_pref == 4) allow = 11;
   const int m = a->n / 2;
   int rc = glb_gram_part_0(m, k, multi, a->groups_hint, st, allow);
   if (rc == -1) rc = glb_gram_part_1(m, k, multi, a->groups_hint, st, allow);

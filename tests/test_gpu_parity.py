@@ -104,9 +104,10 @@ def test_every_fft_size(gpu_api, n):
 
 
 def test_every_kernel_family_on_regular_geometries(gpu_api):
-    """Three kernel families serve the same launches: general (1), TMA ring (2), warp-per-frame
-    (3; N <= 4096 periodograms, edge frames through the general kernel).  Each must match the
-    oracle; the automatic choice is whatever is fastest."""
+    """Four kernel families serve the same launches: general (1), TMA ring (2), warp-per-frame
+    (3; N <= 4096 periodograms, edge frames through the general kernel) and two-frames-per-thread
+    (4; 50 % / 75 % overlap periodograms, N = 512..4096).  Each must match the oracle; the
+    automatic choice is whatever is fastest."""
     x = stream(150000, seed=4)
     try:
         for kw in (dict(n=4096, window_type=0, overlap=0.5, sub_mean=True), dict(n=1024, window_type=7, overlap=0.75, sub_mean=True),
@@ -118,7 +119,7 @@ def test_every_kernel_family_on_regular_geometries(gpu_api):
                 ref = O.multitaper(x, kw["n"], kw["overlap"], kw["mtm_w"], kw["mtm_kmax"], True)
             else:
                 ref = O.periodogram(x, kw["n"], kw["window_type"], kw["overlap"], kw["sub_mean"])
-            for pref in (1, 2, 3, 0):
+            for pref in (1, 2, 3, 4, 0):
                 gpu_api.set_kernel_preference(pref)
                 got = gpu_api.GramPlan(**kw).run(x)["psd"]
                 if kw.get("scale_db"):
@@ -126,6 +127,24 @@ def test_every_kernel_family_on_regular_geometries(gpu_api):
                     assert np.max(np.abs(got - 10 * np.log10(ref.astype(np.float64)))[big]) < 0.01, (pref, kw)
                 else:
                     assert_psd_close(got, ref, f"family {pref} {kw}")
+    finally:
+        gpu_api.set_kernel_preference(0)
+
+
+def test_pair_kernel_ragged_runs(gpu_api):
+    """The two-frames-per-thread family on runs whose length is odd, shorter than one pair per
+    group, or not a multiple of the group count: the unpaired last frame and the blocks past the
+    end of the recording must not leak into the rows."""
+    try:
+        for n, ov in ((4096, 0.5), (2048, 0.75), (512, 0.5)):
+            hop = O.hop_size(n, ov)
+            for nframes in (2, 3, 5, 31, 298, 299):
+                x = stream(nframes * hop - 7, seed=nframes)
+                ref = O.periodogram(x, n, 0, ov, True)
+                gpu_api.set_kernel_preference(4)
+                got = gpu_api.GramPlan(n=n, window_type=0, overlap=ov, sub_mean=True).run(x)["psd"]
+                assert got.shape == ref.shape
+                assert_psd_close(got, ref, f"pair N={n} ov={ov} frames={nframes}")
     finally:
         gpu_api.set_kernel_preference(0)
 
