@@ -212,8 +212,9 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   // (automatic = ring then general: measured on B200 the ring kernel is the fastest family at
   // N = 4096, 0.726 ms vs 0.746 ms for warp-per-frame, whose 67 KB of straight-line code per
   // frame stalls on instruction fetch; warp-per-frame stays selectable for experiments)
-  int allow = 3;                                  // 1 general, 2 ring, 4 warp-per-frame, 8 pair
+  int allow = 19;                                 // 1 general, 2 ring, 4 warp-per-frame, 8 pair, 16 TMEM stash
   if (g_force_generic || g_kernel_pref == 1) allow = 1;
+  else if (g_kernel_pref == 2) allow = 3;
   else if (g_kernel_pref == 3) allow = 7;
   else if (g_kernel_pref == 4) allow = 11;
   const int m = a->n / 2;
