@@ -292,6 +292,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = api.kernel_launches() - launches0
+    family = api.last_kernel_family()
     dev_s = max_over_ranks(sum(step_ms) * 1e-3)
     gram_s = sum(gram_ms) * 1e-3 / len(gram_ms)
     value = world * nf * args.steps / dev_s          # all ranks do nf (+-1) frames per step
@@ -328,7 +329,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     traffic = None          # DRAM read+write bytes of the kernel per launch, from the committed ncu capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
         if tj.get("workload") == args.workload and not args.seconds:
             traffic = tj["traffic_bytes_per_launch"]
@@ -342,7 +343,7 @@ def main():
             "data": "synthetic QRSS/DFCW multi-tone + noise (int16-quantised, /32768), 20 s block tiled to length",
             "config": config, "samples_per_sec": value * hop,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "gram_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": family,
                          "kernel_ms": 1e3 * gram_s, "algorithmic_bytes_per_launch": alg_bytes,
                          "fp32_flops_per_launch": nf * ntap * 5 * n * int(np.log2(n)),
                          "fp32_tflops_5nlogn": nf * ntap * 5 * n * np.log2(n) / gram_s / 1e12},

@@ -159,6 +159,15 @@ def kernel_launches() -> int:
     return int(lib().glfer_b200_kernel_launches())
 
 
+KERNEL_FAMILIES = {0: "none", 1: "gram_kernel (general)", 2: "gram_ring_kernel (TMA ring)", 3: "gram_wpf_kernel (warp per frame)",
+                   4: "gram_pair_kernel (two frames per thread)"}
+
+
+def last_kernel_family() -> str:
+    """Family of the last spectrogram kernel the library launched."""
+    return KERNEL_FAMILIES.get(int(lib().glb_last_kernel_family()), "?")
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 

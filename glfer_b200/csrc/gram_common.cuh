@@ -20,7 +20,8 @@ using namespace glb;
 
 // shared state of the library (defined in gram_kernels.cu)
 extern std::atomic<unsigned long long> g_launches;
-extern int g_kernel_pref;            // 0 auto, 1 general, 2 ring, 3 warp-per-frame
+extern int g_kernel_pref;            // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
+extern int g_last_family;            // family of the last spectrogram kernel launched (same numbering)
 extern "C" void glb_set_error(const char *msg);
 
 #define CU(call)                                                                              \
@@ -858,259 +859,6 @@ template <int M, int P> struct PairMidPasses {
   }
 };
 
-// ------------------------------------------------------------------------- TMEM-stash kernel
-// Periodogram fast path for 50 % / 75 % overlap on 128-thread CTAs (N <= 4096).  Thread t reads
-// the same positions t + T i of every hop block and the same 16 taper values in every frame, so
-// both are thread-private state -- and Blackwell's tensor memory (256 KB per SM, idle in an FP32
-// FFT) is a per-lane scratch of exactly that kind: thread t owns TMEM lane t (tcgen05.ld/st,
-// 32x32b shape).  Each CTA allocates 64 columns:
-//   columns  0..31   the thread's 16 taper pairs, written once
-//   columns 32..61   the mean-removed samples of the NB - 1 older blocks of the frame (circular)
-// Per frame only the newest block is read from shared memory; it is stashed (mean removed) for the
-// NB - 1 frames that will need it again.  The shared-memory ring shrinks to two landing slots
-// whatever the overlap, the bulk copy of block f + 2 is issued during frame f (two frames of
-// slack instead of one), there is no global load left in the frame loop, and the L1TEX data
-// pipe -- the busiest unit of the ring kernel -- loses the taper and old-block wavefronts
-// (192 of ~1030 per frame at 50 % overlap).
-#define GLB_TMEM_LD(NV, addr, v, off)                                                                     \
-  tmem_ld_##NV((addr), &(v)[off])
-__device__ __forceinline__ void tmem_ld_8(unsigned addr, unsigned *v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(addr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_8(unsigned addr, const unsigned *v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// NF float2 values <-> 2 NF consecutive columns of the thread's lane, in chunks of 8 columns
-template <int NF>
-__device__ __forceinline__ void tmem_load_f2(unsigned addr, float2 *dst) {
-  static_assert(NF % 4 == 0, "chunks of 8 columns");
-  unsigned w[2 * NF];
-#pragma unroll
-  for (int c = 0; c < 2 * NF; c += 8) tmem_ld_8(addr + c, w + c);
-  tmem_wait_ld();
-#pragma unroll
-  for (int i = 0; i < NF; i++) dst[i] = make_float2(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
-}
-template <int NF>
-__device__ __forceinline__ void tmem_store_f2(unsigned addr, const float2 *src) {
-  static_assert(NF % 4 == 0, "chunks of 8 columns");
-  unsigned w[2 * NF];
-#pragma unroll
-  for (int i = 0; i < NF; i++) {
-    w[2 * i] = __float_as_uint(src[i].x);
-    w[2 * i + 1] = __float_as_uint(src[i].y);
-  }
-#pragma unroll
-  for (int c = 0; c < 2 * NF; c += 8) tmem_st_8(addr + c, w + c);
-}
-
-template <int M, int QS> struct TmemGeo {
-  static constexpr int T = M / kPoints, NB = kPoints >> QS, BQ = 1 << QS, NW = (T + 31) / 32;
-  static constexpr int HOP = (2 * T) << QS;
-  static constexpr int G = Geo<M>::G, THREADS = Geo<M>::THREADS;
-  static constexpr int OLD = kPoints - BQ;                           // float2 per thread in the stash
-  static constexpr size_t RING_OFF = Geo<M>::BUF_BYTES;
-  static constexpr size_t RED_OFF = RING_OFF + (size_t) 2 * HOP * sizeof(float);
-  static constexpr size_t MBAR_OFF = RED_OFF + (((size_t) NW * sizeof(float) + 15) / 16) * 16;
-  static constexpr size_t GROUP_BYTES = MBAR_OFF + 16;
-  static constexpr size_t SMEM = (size_t) G * GROUP_BYTES + 16;      // + the TMEM base address word
-  static constexpr int MINB_ = 65536 / (THREADS * GLB_REG_TARGET);
-  static constexpr int MINB = MINB_ < 1 ? 1 : MINB_;
-};
-
-template <int M, int QS>
-__global__ void __launch_bounds__(Geo<M>::THREADS, (TmemGeo<M, QS>::MINB)) gram_tmem_kernel(const KParams p) {
-  using TG = TmemGeo<M, QS>;
-  static_assert(TG::THREADS == 128, "one TMEM lane per thread: 128-thread CTAs");
-  static_assert(QS == 2 || QS == 3, "50 % and 75 % overlap");
-  constexpr int T = TG::T, G = TG::G, N = 2 * M, NB = TG::NB, BQ = TG::BQ, NW = TG::NW, HOP = TG::HOP, OLD = TG::OLD;
-  constexpr int W = T < 32 ? T : 32;
-  constexpr unsigned kColsTaper = 0, kColsStash = 32, kCols = 64;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int g = threadIdx.x / T;
-  const int t = threadIdx.x % T;
-  unsigned char *gbase = smem_raw + (size_t) g * TG::GROUP_BYTES;
-  float2 *buf = reinterpret_cast<float2 *>(gbase);
-  float *ring = reinterpret_cast<float *>(gbase + TG::RING_OFF);
-  float *red = reinterpret_cast<float *>(gbase + TG::RED_OFF);
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + TG::MBAR_OFF);   // one per landing slot
-  unsigned *tslot = reinterpret_cast<unsigned *>(smem_raw + (size_t) G * TG::GROUP_BYTES);
-  const long long gid = (long long) blockIdx.x * G + g;
-  const long long fb = gid * p.frames_per_group;
-  const bool group_active = fb < p.nframes;
-  const long long f_first = p.first_frame + fb;
-  const bool sub = p.fused_mean != 0;
-  constexpr unsigned blk_bytes = (unsigned) HOP * 4u;
-
-  // ---- tensor memory: 64 columns for the CTA, lane = thread index
-  if (threadIdx.x < 32) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tslot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (t == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const unsigned tbase = *tslot + ((unsigned) (threadIdx.x & ~31) << 16);   // this warp's 32 lanes
-  {
-    float2 w[kPoints];
-    const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers);
-#pragma unroll
-    for (int q = 0; q < kPoints; q++) w[q] = ldg2(w2 + t + T * q);
-    tmem_store_f2<kPoints>(tbase + kColsTaper, w);
-    tmem_wait_st();
-  }
-
-  TwRegs tr;
-  load_tw_regs<M>(tr, t, p.tw, p.vtab);
-
-  // ---- prologue: the NB - 1 older blocks of the first frame, one at a time through slot 0
-  // (zeros before the stream start, fft.c:103-108), mean removed, into the stash; stash position
-  // of the j-th block of the group's run is j mod (NB - 1)
-  unsigned ph0 = 0, ph1 = 0;                                         // parities of the two landing slots
-  const long long b0 = f_first - (NB - 1);
-  for (int j = 0; j < NB - 1; j++) {
-    const long long blk = b0 + j;
-    const bool there = group_active && blk >= 0;
-    if (there) {
-      if (t == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&mbar[0], blk_bytes);
-        tma_load_1d(ring, p.samples + (blk * HOP - p.origin), blk_bytes, &mbar[0]);
-      }
-      mbar_wait(&mbar[0], ph0);
-      ph0 ^= 1;
-    }
-    float2 xo[BQ];
-    const float2 *bp = reinterpret_cast<const float2 *>(ring);
-#pragma unroll
-    for (int i = 0; i < BQ; i++) xo[i] = there ? bp[t + T * i] : make_float2(0.f, 0.f);
-    if (sub) {
-      // all threads of the CTA take part (block barrier inside); the sum of a missing block is 0
-      float a = 0.f;
-#pragma unroll
-      for (int i = 0; i < BQ; i++) a += xo[i].x + xo[i].y;
-#pragma unroll
-      for (int o = W / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (NW > 1) {
-        if ((t & 31) == 0) red[t >> 5] = a;
-        __syncthreads();
-      }
-      const float m = ring_block_total<M>(a, red, p.inv_hop_mean);
-#pragma unroll
-      for (int i = 0; i < BQ; i++) xo[i] = sub2(xo[i], bc(m));
-    }
-    tmem_store_f2<BQ>(tbase + kColsStash + (unsigned) (j % (NB - 1)) * 2 * BQ, xo);
-    __syncthreads();                                                 // slot 0 and `red` are free again
-  }
-  tmem_wait_st();
-  // blocks of frames 0 and 1 of the run into the two landing slots
-  if (group_active && t == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&mbar[0], blk_bytes);
-    tma_load_1d(ring, p.samples + (f_first * HOP - p.origin), blk_bytes, &mbar[0]);
-    if (p.frames_per_group > 1 && fb + 1 < p.nframes) {
-      mbar_expect_tx(&mbar[1], blk_bytes);
-      tma_load_1d(ring + HOP, p.samples + ((f_first + 1) * HOP - p.origin), blk_bytes, &mbar[1]);
-    }
-  }
-
-  for (int it = 0; it < p.frames_per_group; ++it) {
-    const long long fl = fb + it;
-    const bool active = fl < p.nframes;
-    const long long f = p.first_frame + fl;
-    const int slot = it & 1;
-    const float *blk = ring + (size_t) slot * HOP;
-    float2 v[kPoints];
-    {
-      float2 x[kPoints];
-      // older blocks from the stash (issued first: they are in flight across the mean barrier)
-      unsigned wold[NB > 1 ? 2 * OLD : 2];
-#pragma unroll
-      for (int lb = 0; lb < NB - 1; lb++) {
-        const unsigned pos = (unsigned) ((it + lb) % (NB - 1));
-#pragma unroll
-        for (int c = 0; c < 2 * BQ; c += 8) tmem_ld_8(tbase + kColsStash + pos * 2 * BQ + c, wold + lb * 2 * BQ + c);
-      }
-      if (active) {
-        mbar_wait(&mbar[slot], slot ? ph1 : ph0);
-        if (slot) ph1 ^= 1; else ph0 ^= 1;
-      }
-      float2 xn[BQ];
-      const float2 *bp = reinterpret_cast<const float2 *>(blk);
-#pragma unroll
-      for (int i = 0; i < BQ; i++) xn[i] = bp[t + T * i];
-      if (sub) {
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < BQ; i++) a += xn[i].x + xn[i].y;
-#pragma unroll
-        for (int o = W / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (NW > 1) {
-          if ((t & 31) == 0) red[t >> 5] = a;
-          __syncthreads();
-        }
-        const float m = ring_block_total<M>(a, red, p.inv_hop_mean);
-#pragma unroll
-        for (int i = 0; i < BQ; i++) xn[i] = sub2(xn[i], bc(m));
-      }
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < OLD; i++) x[i] = make_float2(__uint_as_float(wold[2 * i]), __uint_as_float(wold[2 * i + 1]));
-#pragma unroll
-      for (int i = 0; i < BQ; i++) x[OLD + i] = xn[i];
-      // the newest block takes the place of the oldest one in the stash
-      if (NB > 1) tmem_store_f2<BQ>(tbase + kColsStash + (unsigned) (it % (NB - 1)) * 2 * BQ, xn);
-      // taper from tensor memory, 4 pairs at a time
-#pragma unroll
-      for (int q = 0; q < kPoints; q += 4) {
-        float2 w[4];
-        tmem_load_f2<4>(tbase + kColsTaper + 2 * q, w);
-#pragma unroll
-        for (int i = 0; i < 4; i++) v[q + i] = mul2(x[q + i], w[i]);
-      }
-    }
-    pass_compute_rt<M, 0>(v, tr);
-    __syncthreads();                   // (A) the previous transform's last pass and this frame's slot have been read by all
-    pass_scatter<M, 0>(v, t, buf);
-    // the slot just consumed takes block f + 2
-    if (t == 0 && it + 2 < p.frames_per_group && fl + 2 < p.nframes) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&mbar[slot], blk_bytes);
-      tma_load_1d(ring + (size_t) slot * HOP, p.samples + ((f + 2) * (long long) HOP - p.origin), blk_bytes, &mbar[slot]);
-    }
-    __syncthreads();
-    MidPasses<M, 1, true>::run(v, t, buf, p.tw, tr, g);
-    last_pass_rt<M>(v, t, buf, p.tw, tr);
-    float yv[17];
-    yv[16] = 1.f;
-    auto sink = [&](int s_, float2 a, bool) { yv[s_] = norm2(a); };
-    if (t < 32) emit_bins_rt<M, true>(v, t, tr, sink);
-    else emit_bins_rt<M, false>(v, t, tr, sink);
-    if (p.rows_db != 0) {
-#pragma unroll
-      for (int s_ = 0; s_ < 17; s_++) yv[s_] = 10.f * log10f(yv[s_]);
-    }
-    if (active) store_row<M>(p.rows + fl * p.row_stride, t, yv);
-  }
-
-  tmem_wait_st();
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(*tslot) : "memory");
-}
-
 // ------------------------------------------------------------------------- pair kernel
 // Periodogram fast path for 50 % and 75 % overlap (register-twiddle plans): every thread carries
 // the same 16 points of TWO consecutive frames f, f + 1 through the transform.  The two frames
@@ -1433,6 +1181,7 @@ inline int launch_wpf(const KParams &kp, cudaStream_t st) {
   gram_wpf_kernel<M><<<ctas, 32 * kWpfWarps, smem, st>>>(k);
   CU(cudaGetLastError());
   g_launches++;
+  g_last_family = 3;
   return GLB_OK;
 }
 
@@ -1496,36 +1245,6 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
       if (kp.hop == (unit << s2)) qs = s2;
     const bool regular = qs >= 0 && (kp.n_ov % kp.hop) == 0 && (kp.hop % 4) == 0 && (kp.origin % 4) == 0 &&
                          ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0);
-    if constexpr (GeoM::RT && GeoM::THREADS == 128 && M >= 64) {
-      // 50 % / 75 % overlap periodograms: taper and older blocks in tensor memory
-      if (regular && !multi && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr &&
-          (allow & 16) != 0 && (qs == 3 || qs == 2)) {
-        void (*tk)(const KParams) = qs == 3 ? gram_tmem_kernel<M, 3> : gram_tmem_kernel<M, 2>;
-        const size_t smem = qs == 3 ? TmemGeo<M, 3>::SMEM : TmemGeo<M, 2>::SMEM;
-        static thread_local int occ_tm[2][64];
-        int &occ = occ_tm[qs - 2][dev & 63];
-        if (occ == 0) {
-          CU(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, GeoM::THREADS, smem));
-          if (occ > 8) occ = 8;                                      // 8 x 64 of the 512 TMEM columns
-          if (occ < 1) occ = -1;
-        }
-        if (occ >= 1) {
-          long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GeoM::G;
-          if (groups > kp.nframes) groups = kp.nframes;
-          if (groups < 1) groups = 1;
-          KParams k = kp;
-          k.qs = qs;
-          k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
-          long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-          int ctas = (int) ((used + GeoM::G - 1) / GeoM::G);
-          tk<<<ctas, GeoM::THREADS, smem, st>>>(k);
-          CU(cudaGetLastError());
-          g_launches++;
-          return GLB_OK;
-        }
-      }
-    }
     if constexpr (GeoM::RT && M >= 256) {
       // 50 % / 75 % overlap periodograms: two frames per thread (selectable family: measured
       // 0.431 ms vs 0.422 ms for the ring kernel on the metric workload, 3 CTAs/SM vs 6)
@@ -1554,6 +1273,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
           pk<<<ctas, GeoM::THREADS, smem, st>>>(k);
           CU(cudaGetLastError());
           g_launches++;
+          g_last_family = 4;
           return GLB_OK;
         }
       }
@@ -1592,6 +1312,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
           rk<<<ctas, GeoM::THREADS, smem, st>>>(k);
           CU(cudaGetLastError());
           g_launches++;
+          g_last_family = 2;
           return GLB_OK;
         }
       }
@@ -1637,6 +1358,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
   kern<<<ctas, GeoM::THREADS, smem, st>>>(k);
   CU(cudaGetLastError());
   g_launches++;
+  g_last_family = 1;
   return GLB_OK;
 }
 

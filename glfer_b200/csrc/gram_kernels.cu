@@ -23,7 +23,8 @@
 // ------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-int g_kernel_pref = 0;               // 0 auto, 1 general, 2 ring, 3 warp-per-frame
+int g_kernel_pref = 0;               // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
+int g_last_family = 0;
 static int g_force_generic = 0;     // tests: run the general kernel where the ring kernel would be chosen
 
 extern "C" const char *glb_last_error(void) { return g_err; }
@@ -31,6 +32,7 @@ extern "C" void glb_set_error(const char *msg) { snprintf(g_err, sizeof g_err, "
 extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load(); }
 extern "C" void glb_force_generic_kernel(int on) { g_force_generic = on; }
 extern "C" void glb_set_kernel_preference(int pref) { g_kernel_pref = pref; }
+extern "C" int glb_last_kernel_family(void) { return g_last_family; }
 
 // ------------------------------------------------------------------------- plumbing
 extern "C" int glb_device_count(int *count) {
@@ -212,9 +214,8 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   // (automatic = ring then general: measured on B200 the ring kernel is the fastest family at
   // N = 4096, 0.726 ms vs 0.746 ms for warp-per-frame, whose 67 KB of straight-line code per
   // frame stalls on instruction fetch; warp-per-frame stays selectable for experiments)
-  int allow = 19;                                 // 1 general, 2 ring, 4 warp-per-frame, 8 pair, 16 TMEM stash
+  int allow = 3;                                  // 1 general, 2 ring, 4 warp-per-frame, 8 pair
   if (g_force_generic || g_kernel_pref == 1) allow = 1;
-  else if (g_kernel_pref == 2) allow = 3;
   else if (g_kernel_pref == 3) allow = 7;
   else if (g_kernel_pref == 4) allow = 11;
   const int m = a->n / 2;

@@ -152,6 +152,8 @@ int glb_launch_levels(const float *rows, long long stride, int nbins, long long 
 
 /* counters */
 unsigned long long glb_kernel_launches(void);
+/* family of the last spectrogram kernel launched: 1 general, 2 TMA ring, 3 warp-per-frame, 4 two frames per thread */
+int glb_last_kernel_family(void);
 
 #ifdef __cplusplus
 }
