@@ -629,11 +629,18 @@ template <int M, int P, bool RT> struct RingMidPasses {
 
 // QSC >= 0: the overlap is a compile-time constant (hop = 2T << QSC): ring geometry and slot
 // addresses fold into immediates; QSC = -1 reads it from the parameters (any regular overlap).
+// N = 16384 (512 threads, one CTA per SM because of its 138 KB of shared memory): the periodogram
+// variant may use 128 registers, enough to keep the twiddles of its two mid passes in registers
+template <int M, bool MULTI> struct RingGeo {
+  static constexpr bool BIG = (M == 8192) && !MULTI;
+  static constexpr bool RT = Geo<M>::RT || BIG;
+  static constexpr int MINB = BIG ? 1 : Geo<M>::MINB;
+};
 template <int M, bool MULTI, int QSC>
-__global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_ring_kernel(const KParams p) {
+__global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gram_ring_kernel(const KParams p) {
   using GeoM = Geo<M>;
   constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
-  constexpr bool RT = GeoM::RT;
+  constexpr bool RT = RingGeo<M, MULTI>::RT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int g = threadIdx.x / T;
   const int t = threadIdx.x % T;

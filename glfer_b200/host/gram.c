@@ -19,7 +19,9 @@
 #include <string.h>
 #include "glb_host.h"
 
+#ifndef NSLOT
 #define NSLOT 2
+#endif
 
 typedef struct {
   void *stream;
@@ -489,7 +491,10 @@ static long long chunk_frames(const glfer_gram_plan *p)
 {
   /* ~32 MiB of new samples per chunk: large enough to run the copy engines and the
      kernel at full rate, small enough that two slots overlap well */
-  long long f = (32LL << 20) / ((long long) p->hop * 4);
+  long long mib = 32;
+  const char *e = getenv("GLFER_B200_CHUNK_MIB");            /* experiments */
+  if (e && atoi(e) > 0) mib = atoi(e);
+  long long f = (mib << 20) / ((long long) p->hop * 4);
   if (f < 64) f = 64;
   const long long min_avg = 16LL * p->cfg.avg_depth;
   if (p->cfg.avg_mode != GLFER_NO_AVG && f < min_avg) f = min_avg;

@@ -124,6 +124,7 @@ int main(int argc, char **argv) {
   if (full) rc |= check<4096>(9);
   if (full) rc |= check<4096>(28, true);
   if (full) rc |= check<8192>(10);
+  if (full) rc |= check<8192>(29, true);
   if (full) rc |= check<16384>(11);
   return rc;
 }
