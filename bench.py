@@ -50,6 +50,8 @@ WORKLOADS = {
            dict(n=16384, window_type=0, overlap=0.5, sub_mean=True), 3 * 3600),
     "c5": ("multitaper N=32768 K'=16 (mtm_k=15) NW=8 50% ovl, 1 h @ 48 kHz per GPU",
            dict(n=32768, mode=1, overlap=0.5, sub_mean=True, mtm_w=8.0, mtm_kmax=15), 3600),
+    "lmp": ("LMP detector (lmp.c) N=4096 rectangular 50% ovl, ring of 4 frames, 1 h @ 48 kHz",
+            dict(n=4096, mode=3, overlap=0.5, sub_mean=True, lmp_av=4), 3600),
 }
 
 
@@ -133,6 +135,10 @@ def _ref_worker(args):
         for _ in range(reps):
             if kw.get("mode", 0) == 1:
                 dt, nf = R.time_mtm(x, kw["n"], kw["overlap"], kw["mtm_w"], kw["mtm_kmax"], kw.get("sub_mean", True))
+            elif kw.get("mode", 0) == 3:
+                t0 = time.perf_counter()
+                nf = R.lmp(x, kw["n"], kw["overlap"], kw["lmp_av"], kw.get("sub_mean", True), kind="f32").shape[0]
+                dt = time.perf_counter() - t0
             else:
                 dt, nf = R.time_periodogram(x, kw["n"], kw["window_type"], kw["overlap"], kw.get("sub_mean", True))
             t += dt
@@ -143,6 +149,8 @@ def _ref_worker(args):
             t0 = time.perf_counter()
             if kw.get("mode", 0) == 1:
                 rows = O.multitaper(x, kw["n"], kw["overlap"], kw["mtm_w"], kw["mtm_kmax"], kw.get("sub_mean", True))
+            elif kw.get("mode", 0) == 3:
+                rows = O.lmp(x, kw["n"], kw["overlap"], kw["lmp_av"], kw.get("sub_mean", True))
             else:
                 rows = O.periodogram(x, kw["n"], kw["window_type"], kw["overlap"], kw.get("sub_mean", True))
             t += time.perf_counter() - t0
@@ -265,7 +273,8 @@ def main():
     # this rank's shard of the (world x seconds) recording
     nframes_total = world * seconds * FS // hop
     first, nf = shard.frame_range(nframes_total, world, rank)
-    lo, hi = shard.sample_span(n, hop, first, nf, sub_mean=kw.get("sub_mean", True), avg_depth=kw.get("avg_depth", 0) if kw.get("avg_mode") else 0)
+    ring = kw.get("lmp_av", 0) if kw.get("mode", 0) == 3 else (kw.get("avg_depth", 0) if kw.get("avg_mode") else 0)
+    lo, hi = shard.sample_span(n, hop, first, nf, sub_mean=kw.get("sub_mean", True), avg_depth=ring)
     nsamp = hi - lo
     x_host = api.pinned_empty((nsamp,), np.float32)
     x_host[:] = synth.tiled_stream(nsamp, fs=FS, block_s=20.0, seed=0x5EED + rank)

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GLFER_B200_LIB") or os.path.join(HERE, "libglfer_b200.so")
 
 MODE_FFT, MODE_MTM = 0, 1
+MODE_LMP = 3                           # glfer.h:45 MODE_LMP
 NO_AVG, AVG_SUMAVG, AVG_PLAIN, AVG_SUMEXTREME = 0, 1, 2, 3
 HANNING, BLACKMAN, GAUSSIAN, WELCH, BARTLETT, RECTANGULAR, HAMMING, KAISER = range(8)
 
@@ -28,7 +29,7 @@ class GramConfig(C.Structure):
                 ("a", C.c_float), ("limiter", C.c_int), ("sub_mean", C.c_int), ("mtm_w", C.c_float),
                 ("mtm_kmax", C.c_int), ("avg_mode", C.c_int), ("avg_depth", C.c_int), ("avg_minbin", C.c_int),
                 ("avg_maxbin", C.c_int), ("avg_max0", C.c_int), ("avg_peakbin_init", C.c_int),
-                ("scale_db", C.c_int), ("device", C.c_int)]
+                ("scale_db", C.c_int), ("device", C.c_int), ("lmp_av", C.c_int)]
 
 
 class FftParams(C.Structure):          # include/fft.h (reference fft.h:51-63)
@@ -41,6 +42,11 @@ class FftParams(C.Structure):          # include/fft.h (reference fft.h:51-63)
 class MtmParams(C.Structure):          # include/mtm.h (reference mtm.h:36-44)
     _fields_ = [("fft", FftParams), ("window", C.POINTER(C.POINTER(C.c_double))), ("sig", C.POINTER(C.c_double)),
                 ("w", C.c_float), ("kmax", C.c_int)]
+
+
+class LmpParams(C.Structure):          # include/lmp.h (reference lmp.h:37-46)
+    _fields_ = [("fft", FftParams), ("avg", C.c_int), ("window", C.POINTER(C.POINTER(C.c_double))),
+                ("sig", C.POINTER(C.c_double)), ("w", C.c_float), ("kmax", C.c_int)]
 
 
 class AvgData(C.Structure):            # include/avg.h (reference avg.h:28-36)
@@ -200,9 +206,9 @@ _PINNED: dict = {}
 
 def make_config(n=1024, window_type=KAISER, overlap=0.0, mode=MODE_FFT, sub_mean=True, a=0.0, limiter=0,
                 mtm_w=4.0, mtm_kmax=7, avg_mode=NO_AVG, avg_depth=4, avg_minbin=0, avg_maxbin=0, avg_max0=0,
-                avg_peakbin_init=0, scale_db=False, device=0) -> GramConfig:
+                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4) -> GramConfig:
     return GramConfig(mode, n, window_type, overlap, a, limiter, int(sub_mean), mtm_w, mtm_kmax, avg_mode, avg_depth,
-                      avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device)
+                      avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device, lmp_av)
 
 
 class GramPlan:

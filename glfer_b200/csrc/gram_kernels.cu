@@ -607,6 +607,61 @@ extern "C" int glb_launch_peak_carry(const int *cand, int *peakbin, long long nf
   return GLB_OK;
 }
 
+// ------------------------------------------------------------------------- LMP statistic
+// lmp_do, lmp.c:131-160: one thread per (frame, bin); the nl rows of the ring are read twice
+// (mean, then variance) in slot order and stay in L1/L2.  Double arithmetic throughout, as the
+// reference (my, sy, v_hat are doubles); IEEE sqrt and division, so inf / NaN appear exactly
+// where the reference produces them (v_hat = 0).
+__global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd, long long psd_first_frame, long long psd_stride,
+                                                  int ring_rows, int nbins, long long first_frame, long long nframes, int nl,
+                                                  int rows_db, float *__restrict__ out, long long out_stride) {
+  const int bin = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bin >= nbins) return;
+  const double c0 = -sqrt((double) nl / 2.0), c1 = 2.0 * sqrt(2.0 * (double) nl);
+  for (long long fi = blockIdx.y; fi < nframes; fi += gridDim.y) {
+    const long long f = first_frame + fi;
+    auto row = [&](int j) -> float {
+      if (ring_rows > 0) return psd[(long long) j * psd_stride + bin];
+      const long long d = ((f - j) % nl + nl) % nl;   // frames since slot j was last written
+      const long long g = f - d;                      // latest frame <= f in slot j (< 0: never written)
+      return g >= 0 ? psd[(g - psd_first_frame) * psd_stride + bin] : 0.f;
+    };
+    double my = 0.0;
+    for (int j = 0; j < nl; j++) my += (double) row(j);
+    my /= nl;
+    double sy = 0.0;
+    for (int j = 0; j < nl; j++) {
+      const double d = (double) row(j) - my;
+      sy += d * d;
+    }
+    sy /= (nl - 1);
+    double v = my * my - sy;
+    if (v < 0.0) v = 0.0;
+    v = 0.5 * (my - sqrt(v));
+    float o = (float) (c0 + (nl * my) / (c1 * v));
+    if ((double) o <= 1.0e-3) o = 1e-3f;
+    if (bin == 0) o = 1e-3f;
+    if (rows_db) o = 10.f * log10f(o);
+    out[fi * out_stride + bin] = o;
+  }
+}
+
+extern "C" int glb_launch_lmp(const float *psd, long long psd_first_frame, long long psd_stride, int psd_ring_rows, int nbins,
+                              long long first_frame, long long nframes, int nl, int rows_db, float *out, long long out_stride,
+                              void *stream) {
+  if (nframes <= 0) return GLB_OK;
+  if (!psd || !out || nl < 2 || nbins < 1 || first_frame < 0) {
+    glb_set_error("glb_launch_lmp: invalid arguments (nl >= 2)");
+    return GLB_EINVAL;
+  }
+  dim3 grid((nbins + 255) / 256, (unsigned) std::min<long long>(nframes, 32768));
+  lmp_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(psd, psd_first_frame, psd_stride, psd_ring_rows, nbins, first_frame, nframes, nl,
+                                                      rows_db, out, out_stride);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
 // ------------------------------------------------------------------------- half-complex PSD
 // fft_psd (fft.c:203-226) for a spectrum that did not come from gram_kernel (callers that
 // fill outbuf themselves).  phase = atan2(Re, Im), the reference's argument order.

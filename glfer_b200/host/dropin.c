@@ -85,6 +85,7 @@ typedef struct engine {
   float *d_ring;             /* [depth][width] last PSD rows */
   double *d_avg, *d_ret, *d_var;
   int *d_cand;
+  float *d_lmp;              /* LMP engines: the statistic row (ring = d_ring [depth][width]) */
 } engine;
 
 static engine *g_engines;
@@ -115,7 +116,7 @@ static void drop_engine(const void *key)
     if (e->stream) glb_stream_sync(e->stream);
     glb_free(e->d_frame); glb_free(e->d_tapers); glb_free(e->d_psd); glb_free(e->d_spec);
     glb_free(e->d_hc); glb_free(e->d_phase); glb_free(e->d_ring); glb_free(e->d_avg);
-    glb_free(e->d_ret); glb_free(e->d_var); glb_free(e->d_cand);
+    glb_free(e->d_ret); glb_free(e->d_var); glb_free(e->d_cand); glb_free(e->d_lmp);
     glb_host_free(e->h_psd); glb_host_free(e->h_spec);
     glb_tables_destroy(e->tables);
     glb_stream_destroy(e->stream);
@@ -389,6 +390,56 @@ void mtm_close(mtm_params_t *params)
   if (params->window) nr_free_dmatrix(params->window, 1, 0);
   params->window = NULL;
   free(params->sig); params->sig = NULL;
+}
+
+/* ------------------------------------------------------------------ lmp.h */
+void lmp_init(lmp_params_t *params)
+{
+  const int n = params->fft.n, nl = params->avg;
+  if (nl < 2) { fprintf(stderr, "libglfer_b200: lmp avg %d < 2 (lmp.c:145 divides by avg - 1)\n", nl); exit(-1); }
+  params->fft.inbuf_audio = calloc(n, sizeof(float));
+  params->fft.inbuf_fft = calloc(n, sizeof(float));
+  params->fft.outbuf = params->fft.inbuf_fft;    /* lmp.c:75 */
+  params->fft.sub_mean = glb_autoscale();        /* lmp.c:80 */
+  if (!params->fft.inbuf_audio || !params->fft.inbuf_fft) { glb_set_error("out of memory"); glb_fatal("lmp_init"); }
+  const float scale = (float) (1.0 / (2.0 * sqrt((double) n)));
+  float *scaled = malloc(sizeof(float) * n);
+  for (int i = 0; i < n; i++) scaled[i] = scale;          /* the frame goes into the FFT as it is (lmp.c:112-114) */
+  engine *e = make_estimator(params, n, 1, scaled, scale);
+  free(scaled);
+  e->width = n / 2 + 1;
+  e->depth = nl;
+  e->frames = 0;
+  MUST(glb_malloc((void **) &e->d_ring, sizeof(float) * (size_t) nl * e->width), "malloc");
+  MUST(glb_malloc((void **) &e->d_lmp, sizeof(float) * e->width), "malloc");
+  MUST(glb_memset(e->d_ring, 0, sizeof(float) * (size_t) nl * e->width, e->stream), "memset");   /* lmp.c:88-93 */
+}
+
+void lmp_do(float *audio_buf, float *psd_buf, float *phase_buf, lmp_params_t *params)
+{
+  (void) phase_buf;                              /* never written by the reference either */
+  engine *e = find_engine(params);
+  if (!e || !e->d_lmp) { glb_set_error("lmp_do on parameters that did not go through lmp_init"); glb_fatal("lmp_do"); }
+  const int n = params->fft.n, bins = n / 2 + 1;
+  prepare_audio(audio_buf, &params->fft);
+  run_frame(e, params->fft.inbuf_audio, 0.0f, 0, 1);
+  spectrum_to_halfcomplex(e->h_spec, n, params->fft.outbuf);       /* the in-place FFT of lmp.c:119 */
+  const int slot = (int) (e->frames % e->depth);                   /* j_l, lmp.c:124 */
+  MUST(glb_memcpy_d2d(e->d_ring + (size_t) slot * bins, e->d_psd, sizeof(float) * bins, e->stream), "d2d");
+  MUST(glb_launch_lmp(e->d_ring, 0, bins, e->depth, bins, e->frames, 1, e->depth, 0, e->d_lmp, bins, e->stream), "launch");
+  MUST(glb_memcpy_d2h(e->h_psd, e->d_lmp, sizeof(float) * bins, e->stream), "d2h");
+  MUST(glb_stream_sync(e->stream), "sync");
+  memcpy(psd_buf, e->h_psd, sizeof(float) * bins);
+  e->fresh = 0;                                  /* h_psd no longer holds the PSD of the frame */
+  e->frames++;
+}
+
+void lmp_close(lmp_params_t *params)
+{
+  drop_engine(params);
+  free(params->fft.inbuf_audio); params->fft.inbuf_audio = NULL;
+  free(params->fft.inbuf_fft); params->fft.inbuf_fft = NULL;
+  params->fft.outbuf = NULL;
 }
 
 /* ------------------------------------------------------------------ avg.h */

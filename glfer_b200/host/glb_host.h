@@ -5,6 +5,7 @@
 #include "../../include/fft.h"
 #include "../../include/mtm.h"
 #include "../../include/avg.h"
+#include "../../include/lmp.h"
 #include "../../include/glfer_b200.h"
 #include "../../include/glb_shim.h"
 

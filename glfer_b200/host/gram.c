@@ -128,6 +128,7 @@ void glfer_gram_config_default(glfer_gram_config *c)
   c->avg_minbin = 0;
   c->avg_maxbin = 0;
   c->device = 0;
+  c->lmp_av = 4;               /* glfer.c:252 */
 }
 
 int glb_plan_sub_mean(const glfer_gram_plan *p) { return p->cfg.sub_mean; }
@@ -137,8 +138,9 @@ long long glfer_gram_num_frames(const glfer_gram_plan *p, long long nsamples) { 
 
 static long long halo_frames(const glfer_gram_plan *p, long long first_frame)
 {
-  if (p->cfg.avg_mode == GLFER_NO_AVG) return 0;
-  long long h = p->cfg.avg_depth - 1;
+  long long h = 0;
+  if (p->cfg.mode == GLFER_MODE_LMP) h = p->cfg.lmp_av - 1;          /* the ring of lmp.c:86-93 */
+  else if (p->cfg.avg_mode != GLFER_NO_AVG) h = p->cfg.avg_depth - 1;
   return h < first_frame ? h : first_frame;
 }
 
@@ -195,7 +197,12 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
   if (!cfg || !out) return fail(GLFER_EINVAL, "null argument");
   *out = NULL;
   if (!glb_fft_supported(cfg->n)) return fail(GLFER_EINVAL, "FFT size must be a power of two in 32..32768");
-  if (cfg->mode != GLFER_MODE_FFT && cfg->mode != GLFER_MODE_MTM) return fail(GLFER_EINVAL, "unknown mode");
+  if (cfg->mode != GLFER_MODE_FFT && cfg->mode != GLFER_MODE_MTM && cfg->mode != GLFER_MODE_LMP)
+    return fail(GLFER_EINVAL, "unknown mode");
+  if (cfg->mode == GLFER_MODE_LMP) {
+    if (cfg->lmp_av < 2) return fail(GLFER_EINVAL, "lmp_av must be >= 2 (lmp.c:145 divides by lmp_av - 1)");
+    if (cfg->avg_mode != GLFER_NO_AVG) return fail(GLFER_EINVAL, "frame averaging is not available in LMP mode");
+  }
   const int hop = glb_hop(cfg->n, cfg->overlap);
   if (hop < 1 || hop > cfg->n) return fail(GLFER_EINVAL, "overlap leaves no new samples per block");
   if (cfg->mode == GLFER_MODE_MTM && (cfg->mtm_kmax < 0 || cfg->mtm_kmax > 31))
@@ -222,13 +229,14 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
   p->h_window = malloc(sizeof(float) * n);
   float *scaled = NULL;
   int rc = 0;
-  if (cfg->mode == GLFER_MODE_FFT) {
+  if (cfg->mode == GLFER_MODE_LMP) p->cfg.window_type = RECTANGULAR_WINDOW;     /* source.c:395 */
+  if (cfg->mode == GLFER_MODE_FFT || cfg->mode == GLFER_MODE_LMP) {
     p->ntapers = 1;
-    glb_window_table(n, cfg->window_type, p->h_window);
+    glb_window_table(n, p->cfg.window_type, p->h_window);
     scaled = malloc(sizeof(float) * n);
     for (int i = 0; i < n; i++) {
       /* a rectangular window is NOT applied by the reference (fft.c:146-148): weight 1 */
-      const double w = (cfg->window_type == RECTANGULAR_WINDOW) ? 1.0 : (double) p->h_window[i];
+      const double w = (p->cfg.window_type == RECTANGULAR_WINDOW) ? 1.0 : (double) p->h_window[i];
       scaled[i] = (float) (w * (double) p->taper_scale);
     }
   } else {
@@ -351,7 +359,7 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   g.nframes = nf;
   g.rows = s->d_psd;
   g.row_stride = p->bins;
-  g.rows_db = (c->avg_mode == GLFER_NO_AVG) ? c->scale_db : 0;   /* averaging needs linear PSD */
+  g.rows_db = (c->avg_mode == GLFER_NO_AVG && c->mode != GLFER_MODE_LMP) ? c->scale_db : 0;   /* averaging / LMP need linear PSD */
   g.spectrum = NULL;
   g.tables = p->tables;
   if (s->time_gram) TRY(glb_event_record(s->ev2, s->stream));
@@ -408,6 +416,11 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
     /* with cand_out the caller resolves the carried *peakbin once over the whole run */
     if (!cand_out) TRY(glb_launch_peak_carry(s->d_cand, s->d_peak, nframes, c->avg_peakbin_init, s->stream));
   }
+  if (c->mode == GLFER_MODE_LMP) {
+    /* the rows handed out are the detector statistic over the ring of the last lmp_av PSD rows */
+    TRY(ensure((void **) &s->d_avg, &s->avg_cap, (size_t) nframes * p->bins, sizeof(float)));
+    TRY(glb_launch_lmp(s->d_psd, f0, p->bins, 0, p->bins, first, nframes, c->lmp_av, c->scale_db, s->d_avg, p->bins, s->stream));
+  }
   s->out_first = first;
   s->out_nframes = nframes;
   s->out_halo = halo;
@@ -418,8 +431,10 @@ static int fetch_slot(glfer_gram_plan *p, slot_t *s, float *psd_rows, float *avg
                       int *avg_peakbin, double *avg_variance)
 {
   const size_t nf = (size_t) s->out_nframes;
-  if (psd_rows)
-    TRY(glb_memcpy_d2h(psd_rows, s->d_psd + (size_t) s->out_halo * p->bins, sizeof(float) * nf * p->bins, s->stream));
+  if (psd_rows) {
+    const float *src = (p->cfg.mode == GLFER_MODE_LMP) ? s->d_avg : s->d_psd + (size_t) s->out_halo * p->bins;
+    TRY(glb_memcpy_d2h(psd_rows, src, sizeof(float) * nf * p->bins, s->stream));
+  }
   if (p->cfg.avg_mode != GLFER_NO_AVG) {
     if (avg_rows) TRY(glb_memcpy_d2h(avg_rows, s->d_avg, sizeof(float) * nf * p->bins, s->stream));
     if (avg_ret) TRY(glb_memcpy_d2h(avg_ret, s->d_ret, sizeof(double) * nf, s->stream));
@@ -662,7 +677,8 @@ static int run_display_impl(glfer_gram_plan *p, const float *samples, const shor
     if (rc) break;
     rc = exec_slot(p, s, c0, cn, NULL);
     if (rc) break;
-    const float *d_psd = s->d_psd + (size_t) s->out_halo * p->bins;
+    /* psdbuf of the GUI: the estimator's output row, which in LMP mode is the statistic */
+    const float *d_psd = (p->cfg.mode == GLFER_MODE_LMP) ? s->d_avg : s->d_psd + (size_t) s->out_halo * p->bins;
     const float *d_shown = avg_on ? s->d_avg : d_psd;               /* g_main.c:1192-1201 */
     rc = ensure((void **) &s->d_levels, &s->levels_cap, (size_t) cn * p->bins, 1);
     if (rc == 0 && rgb) rc = ensure((void **) &s->d_rgb, &s->rgb_cap, (size_t) cn * p->bins * 3, 1);

@@ -126,6 +126,16 @@ typedef struct {
 } glb_avg_args;
 
 int glb_launch_avg(const glb_avg_args *a, void *stream);
+/* The per-bin statistic of the LMP estimator (lmp_do, lmp.c:131-160) over rectangular-window PSD
+ * rows resident on the device: for output frame f the ring psdbufl[j], j = 0..nl-1, is the row
+ * of the latest frame g <= f with g % nl == j (zeros when there is none yet, lmp.c:86-93); mean
+ * and variance over the ring in double, in slot order, then the detector formula, stored to
+ * float, 1e-3 where <= 1e-3, bin 0 = 1e-3.
+ * psd_ring_rows > 0: psd is the ring itself (row j at psd + j * psd_stride; per-call interface). */
+int glb_launch_lmp(const float *psd, long long psd_first_frame, long long psd_stride, int psd_ring_rows, int nbins,
+                   long long first_frame, long long nframes, int nl, int rows_db, float *out, long long out_stride,
+                   void *stream);
+
 /* peakbin[f] = peak_cand[f] >= 0 ? peak_cand[f] : peakbin[f-1], peakbin[-1] = init */
 int glb_launch_peak_carry(const int *peak_cand, int *peakbin, long long nframes, int init, void *stream);
 

@@ -33,6 +33,7 @@ extern "C" {
 /* estimator mode: values of the reference's mode enum (glfer.h:47) */
 #define GLFER_MODE_FFT 0
 #define GLFER_MODE_MTM 1
+#define GLFER_MODE_LMP 3   /* MODE_LMP: rectangular periodogram ring -> per-bin detector statistic (lmp.c) */
 /* averaging mode: values of avgmode_t (glfer.h:53-55) */
 #define GLFER_NO_AVG 0
 #define GLFER_AVG_SUMAVG 1
@@ -40,7 +41,7 @@ extern "C" {
 #define GLFER_AVG_SUMEXTREME 3
 
 typedef struct {
-  int mode;            /* GLFER_MODE_FFT | GLFER_MODE_MTM */
+  int mode;            /* GLFER_MODE_FFT | GLFER_MODE_MTM | GLFER_MODE_LMP */
   int n;               /* FFT size (opt.data_block_size): power of two, 32..32768 */
   int window_type;     /* fft.h window enum; ignored for MTM (forced rectangular, source.c:344) */
   float overlap;       /* opt.data_blocks_overlap; hop = (int)(n * (1.0 - overlap)) (fft.c:70) */
@@ -57,6 +58,9 @@ typedef struct {
   int avg_peakbin_init;/* the caller's peakbin before frame 0 */
   int scale_db;        /* 1: rows are 10*log10(value) (g_main.c:1191-1199) */
   int device;          /* CUDA device ordinal */
+  int lmp_av;          /* opt.lmp_av: rows in the LMP ring (>= 2); the "psd" rows of an LMP plan are the
+                          statistic of lmp_do; window forced rectangular (source.c:395), RA9MB / limiter
+                          do not reach the spectrum (lmp.c:112-114); no frame averaging in this mode */
 } glfer_gram_config;
 
 typedef struct glfer_gram_plan glfer_gram_plan;

@@ -196,6 +196,62 @@ def phase_from_spectrum(spec: np.ndarray, n: int) -> np.ndarray:
     return ph
 
 
+# ----------------------------------------------------------------------------- LMP
+def lmp_statistic(psd_rows: np.ndarray, nl: int, first_frame: int = 0, history: np.ndarray | None = None) -> np.ndarray:
+    """The per-bin statistic of lmp_do, lmp.c:131-160, over a sequence of float PSD rows.
+    psdbufl is a ring of nl rows, zero at init (lmp.c:86-93), written at slot j_l = frame mod nl
+    (lmp.c:124,188-190).  Per bin, in double: my = sum_j psdbufl[j] / nl in SLOT order
+    (lmp.c:131-137), sy = sum_j (psdbufl[j] - my)^2 / (nl - 1) (lmp.c:140-146),
+    v_hat = 0.5 (my - sqrt(max(my^2 - sy, 0))) (lmp.c:150-152),
+    out = -sqrt(nl/2) + nl my / (2 sqrt(2 nl) v_hat) stored to float, then 1e-3 where
+    out <= 1e-3 (NaN and inf pass through), out[0] = 1e-3 (lmp.c:154-157).
+    `first_frame` / `history` ([first_frame rows or at least nl-1][bins], the rows before
+    psd_rows[0]) let a shard reproduce the ring of a longer run."""
+    rows = np.asarray(psd_rows, dtype=np.float32)
+    nf, bins = rows.shape
+    ring = np.zeros((nl, bins), dtype=np.float32)
+    if history is not None and first_frame > 0:
+        h = np.asarray(history, dtype=np.float32)
+        for i in range(max(0, len(h) - nl), len(h)):
+            g = first_frame - len(h) + i
+            if g >= 0:
+                ring[g % nl] = h[i]
+    out = np.empty((nf, bins), dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for f in range(nf):
+            ring[(first_frame + f) % nl] = rows[f]
+            my = np.zeros(bins, dtype=np.float64)
+            for j in range(nl):
+                my += ring[j].astype(np.float64)
+            my /= nl
+            sy = np.zeros(bins, dtype=np.float64)
+            for j in range(nl):
+                d = ring[j].astype(np.float64) - my
+                sy += d * d
+            sy /= (nl - 1)
+            v = my * my - sy
+            v = np.where(v < 0.0, 0.0, v)
+            v = 0.5 * (my - np.sqrt(v))
+            o = (-math.sqrt(nl / 2.0) + (nl * my) / (2.0 * math.sqrt(2.0 * nl) * v)).astype(np.float32)
+            o = np.where(o.astype(np.float64) <= 1.0e-3, np.float32(1e-3), o)
+            o[0] = np.float32(1e-3)
+            out[f] = o
+    return out
+
+
+def lmp(samples: np.ndarray, n: int, overlap: float, nl: int, sub_mean: bool = False,
+        first_frame: int = 0, nframes: int | None = None) -> np.ndarray:
+    """lmp_do per hop block (source.c:155-156 -> lmp.c:101-192).  prepare_audio runs with a
+    rectangular window (source.c:395) and its RA9MB / limiter results are overwritten: the FFT
+    input is rebuilt from inbuf_audio (lmp.c:112-114), so only the block-mean removal reaches
+    the spectrum.  Returns float32 rows [nframes][n/2+1]."""
+    total = num_frames(len(samples), n, overlap)
+    if nframes is None:
+        nframes = total - first_frame
+    raw = periodogram(samples, n, RECTANGULAR, overlap, sub_mean, first_frame=0, nframes=first_frame + nframes)
+    return lmp_statistic(raw[first_frame:], nl, first_frame, raw[:first_frame])
+
+
 # ----------------------------------------------------------------------------- DPSS
 def gl_dpss(n: int, w: float, kmax: int):
     """gl_dpss, g-l_dpss.c:288-347: c = pi*w with w = N*W given directly (:295-297);

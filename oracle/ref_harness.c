@@ -1,6 +1,6 @@
 /* Headless driver around the UNMODIFIED reference estimator sources.
  * TEST INFRASTRUCTURE ONLY: compiled by oracle/Makefile together with
- * /root/reference/{fft.c,fft_radix2.c,mtm.c,g-l_dpss.c,avg.c,util.c} into
+ * /root/reference/{fft.c,fft_radix2.c,mtm.c,g-l_dpss.c,avg.c,lmp.c,util.c} into
  * oracle/_ref/libglfer_ref_{f32,f64}.so.  Nothing under oracle/ is linked into,
  * imported by or executed from the product library.
  *
@@ -27,6 +27,7 @@
 #include "fft.h"
 #include "mtm.h"
 #include "avg.h"
+#include "lmp.h"
 #include "g-l_dpss.h"
 
 opt_t opt;
@@ -165,6 +166,45 @@ long refh_mtm(const float *samples, long nsamples, int n, float overlap, int sub
   free(blk);
   free(psd);
   mtm_close(&p);
+  return nframes;
+}
+
+/* LMP spectrogram: the MODE_LMP branch of source.c:155-157, parameters set as change_params
+ * does (source.c:394-400).  lmp.c keeps its ring index in a function-static that no init
+ * resets (lmp.c:102); the harness feeds zero blocks after the run until that index is back at
+ * 0, so that every call starts like a fresh process. */
+long refh_lmp(const float *samples, long nsamples, int n, float overlap, int sub_mean,
+              float a, int limiter, int nl, long max_frames, float *rows)
+{
+  lmp_params_t p;
+  memset(&p, 0, sizeof p);
+  p.fft.n = n;
+  p.fft.window_type = RECTANGULAR_WINDOW;
+  p.fft.overlap = overlap;
+  p.fft.a = a;
+  p.fft.limiter = limiter;
+  p.avg = nl;
+  opt.autoscale = sub_mean;
+  lmp_init(&p);
+  int hop = refh_hop(n, overlap);
+  int bins = n / 2 + 1;
+  long nframes = hop > 0 ? nsamples / hop : 0;
+  if (nframes > max_frames) nframes = max_frames;
+  float *blk = malloc(sizeof(float) * (hop > 0 ? hop : 1));
+  float *psd = malloc(sizeof(float) * bins);
+  glfer.first_buffer = TRUE;
+  for (long f = 0; f < nframes; f++) {
+    memcpy(blk, samples + f * hop, sizeof(float) * hop);
+    lmp_do(blk, rows ? rows + f * bins : psd, NULL, &p);
+    glfer.first_buffer = FALSE;
+  }
+  for (long f = nframes; f % nl != 0; f++) {            /* realign the static ring index */
+    memset(blk, 0, sizeof(float) * hop);
+    lmp_do(blk, psd, NULL, &p);
+  }
+  free(blk);
+  free(psd);
+  lmp_close(&p);
   return nframes;
 }
 

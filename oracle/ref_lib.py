@@ -38,6 +38,8 @@ def lib(kind: str = "f64") -> C.CDLL:
         l.refh_mtm.argtypes = [_fp, C.c_long, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int,
                                C.c_long, _fp]
         l.refh_mtm.restype = C.c_long
+        l.refh_lmp.argtypes = [_fp, C.c_long, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_long, _fp]
+        l.refh_lmp.restype = C.c_long
         l.refh_avg.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_long, C.c_long, C.c_int,
                                _dp, _dp, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), _dp, C.c_int]
         l.refh_floor.argtypes = [_fp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
@@ -95,6 +97,16 @@ def mtm(samples, n, overlap, w, kmax, sub_mean=False, a=0.0, limiter=0, max_fram
     nf = min(len(samples) // h, max_frames)
     rows = np.empty((nf, n // 2 + 1), dtype=np.float32)
     got = lib(kind).refh_mtm(samples, len(samples), n, overlap, int(sub_mean), a, limiter, w, kmax, nf, rows)
+    assert got == nf
+    return rows
+
+
+def lmp(samples, n, overlap, nl, sub_mean=False, a=0.0, limiter=0, max_frames=1 << 40, kind="f64"):
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    h = hop(n, overlap, kind)
+    nf = min(len(samples) // h, max_frames)
+    rows = np.empty((nf, n // 2 + 1), dtype=np.float32)
+    got = lib(kind).refh_lmp(samples, len(samples), n, overlap, int(sub_mean), a, limiter, nl, nf, rows)
     assert got == nf
     return rows
 

@@ -46,6 +46,9 @@ def main():
     tap, lam = R.dpss(1024, 4.0, 7)
     out["c3_lambda"] = lam
     out["c3_tapers"] = tap.astype(np.float32)
+    # LMP (lmp.c): ring of 4 rectangular periodograms at N=1024, 50 %; ring of 7 at N=512, 75 %
+    out["lmp_rows"] = R.lmp(x, 1024, 0.5, 4, True)
+    out["lmp_rows_n512"] = R.lmp(x[:12000], 512, 0.75, 7, False)
     # odd hop (overlap 0.9 -> hop 102 at N=1024), RA9MB and limiter
     out["odd_rows"] = R.periodogram(x[:20000], 1024, 1, 0.9, True)
     out["preop_rows"] = R.periodogram(x[:20000], 1024, 0, 0.5, True, a=0.01, limiter=1)

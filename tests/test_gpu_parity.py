@@ -342,6 +342,71 @@ def test_per_call_mtm_equals_oracle(gpu_api):
     assert_psd_close(np.array(rows), O.multitaper(x, 1024, 0.5, 4.0, 7, True), "per-call MTM")
 
 
+def assert_lmp_close(got, ref, what):
+    """The LMP statistic divides by v_hat = (my - sqrt(my^2 - sy)) / 2, a difference of nearly
+    equal numbers for a steady tone and a square root near 0 for noise: a 1e-6 relative error
+    of the FP32 PSD rows becomes up to ~1e-3 of the statistic (measured with a float32 FFT on
+    the CPU: max 9e-4, median 2e-7).  Bar: 2e-3 relative + 2e-3 absolute (the floor value is
+    1e-3), median below 1e-5, NaN / inf in the same places."""
+    assert got.shape == ref.shape, what
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin), what
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))[fin]
+    mag = np.abs(ref.astype(np.float64))[fin]
+    assert np.all(err <= 2e-3 * mag + 2e-3), (what, float((err / (2e-3 * mag + 2e-3)).max()))
+    assert np.median(err / mag) < 1e-5, what
+
+
+def test_lmp_fixture_kernel_exactness_and_shards(gpu_api):
+    """LMP mode (lmp.c): against the reference fixture; the statistic kernel alone against the
+    oracle formula on the GPU's own PSD rows (IEEE double: identical floats); frame sub-ranges
+    and time shards against the full run (the ring is rebuilt from lmp_av - 1 halo frames)."""
+    for n, ov, nl, sm, key, x in ((1024, 0.5, 4, True, "lmp_rows", XG), (512, 0.75, 7, False, "lmp_rows_n512", XG[:12000])):
+        p = gpu_api.GramPlan(n=n, mode=gpu_api.MODE_LMP, overlap=ov, sub_mean=sm, lmp_av=nl)
+        got = p.run(x)["psd"]
+        assert_lmp_close(got, GOLD[key], f"LMP fixture {key}")
+        raw = gpu_api.GramPlan(n=n, window_type=5, overlap=ov, sub_mean=sm).run(x)["psd"]
+        assert np.array_equal(got.view(np.uint32), O.lmp_statistic(raw, nl).view(np.uint32)), key
+        assert np.all(got[:, 0] == np.float32(1e-3))
+        sub = p.run(x, first_frame=11, nframes=17)["psd"]
+        assert np.array_equal(sub, got[11:28])
+    x = stream(200000, seed=43)
+    kw = dict(n=2048, mode=gpu_api.MODE_LMP, overlap=0.5, sub_mean=True, lmp_av=5)
+    one = gpu_api.run_sharded(x, 1, **kw)
+    assert_lmp_close(one["psd"], O.lmp(x, 2048, 0.5, 5, True), "LMP N=2048")
+    for shards in (2, 4):
+        devs = [g % gpu_api.device_count() for g in range(shards)]
+        assert np.array_equal(one["psd"], gpu_api.run_sharded(x, shards, devices=devs, **kw)["psd"]), shards
+    # RA9MB / limiter never reach the LMP spectrum (lmp.c:112-114)
+    q = gpu_api.GramPlan(n=1024, mode=gpu_api.MODE_LMP, overlap=0.5, sub_mean=True, lmp_av=4, a=0.05, limiter=1)
+    assert np.array_equal(q.run(XG)["psd"], gpu_api.GramPlan(n=1024, mode=gpu_api.MODE_LMP, overlap=0.5, sub_mean=True, lmp_av=4).run(XG)["psd"])
+    with pytest.raises(Exception):
+        gpu_api.GramPlan(n=1024, mode=gpu_api.MODE_LMP, lmp_av=1)
+
+
+def test_per_call_lmp_equals_batch(gpu_api):
+    """lmp_init / lmp_do / lmp_close (lmp.h:49-51) one hop block per call, as source.c:155-156."""
+    lib = gpu_api.lib()
+    x = stream(12000, seed=36)
+    par = gpu_api.LmpParams()
+    par.fft.n, par.fft.window_type, par.fft.overlap, par.avg = 1024, 5, 0.5, 4
+    lib.glfer_b200_set_autoscale(1)
+    lib.lmp_init(C.byref(par))
+    rows = []
+    lib.glfer_b200_set_first_buffer(1)
+    for f in range(len(x) // 512):
+        blk = np.ascontiguousarray(x[f * 512:(f + 1) * 512]).copy()
+        psd = np.empty(513, np.float32)
+        lib.lmp_do(blk.ctypes.data, psd.ctypes.data, None, C.byref(par))
+        rows.append(psd)
+        lib.glfer_b200_set_first_buffer(0)
+    lib.lmp_close(C.byref(par))
+    rows = np.array(rows)
+    assert_lmp_close(rows, O.lmp(x, 1024, 0.5, 4, True), "per-call LMP")
+    batch = gpu_api.GramPlan(n=1024, mode=gpu_api.MODE_LMP, overlap=0.5, sub_mean=True, lmp_av=4).run(x)["psd"]
+    assert_lmp_close(rows, batch, "per-call LMP vs batch")
+
+
 def test_compute_floor(gpu_api):
     lib = gpu_api.lib()
     x = stream(20000, seed=37)

@@ -69,6 +69,17 @@ def test_dpss_and_multitaper_fixture():
     assert rel.max() < 1e-6
 
 
+def test_lmp_fixture_bit_exact():
+    """lmp_do (lmp.c:101-192) restated: identical floats to the unmodified reference."""
+    assert np.array_equal(O.lmp(X, 1024, 0.5, 4, True).view(np.uint32), GOLD["lmp_rows"].view(np.uint32))
+    assert np.array_equal(O.lmp(X[:12000], 512, 0.75, 7, False).view(np.uint32), GOLD["lmp_rows_n512"].view(np.uint32))
+    # bin 0 and the floor are pinned to 1e-3 (lmp.c:155-157)
+    assert np.all(GOLD["lmp_rows"][:, 0] == np.float32(1e-3)) and GOLD["lmp_rows"].min() == np.float32(1e-3)
+    # a shard that starts inside the run reproduces the ring from its nl - 1 frames of history
+    full = O.lmp(X, 1024, 0.5, 4, True)
+    assert np.array_equal(O.lmp(X, 1024, 0.5, 4, True, first_frame=9, nframes=20), full[9:29])
+
+
 def test_avg_fixtures():
     mn, mx = GOLD["c2_band"]
     assert (mn, mx) == O.avg_bins(8000, 4096, 400.0, 1200.0)
@@ -150,6 +161,8 @@ def test_restatement_matches_reference_library():
             a2 = R.avg(mode, rows, 512, 5, 10, 200, max0)
             assert np.allclose(a1[0], a2[0], rtol=1e-12) and np.allclose(a1[1], a2[1], rtol=1e-12)
             assert np.array_equal(a1[2], a2[2])
+    for n, ov, nl, sm in ((1024, 0.5, 4, True), (256, 0.75, 9, False), (2048, 0.0, 2, True)):
+        assert np.array_equal(O.lmp(x, n, ov, nl, sm).view(np.uint32), R.lmp(x, n, ov, nl, sm).view(np.uint32))
     s, f, p, b = R.floor_stats(rows[3])
     s2, f2, p2, b2 = O.compute_floor(rows[3])
     assert s == pytest.approx(s2) and f == pytest.approx(f2, rel=1e-5) and p == pytest.approx(p2) and b == b2
