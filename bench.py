@@ -37,6 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FS = 48000
+_STDOUT_FD = 1
 WORKLOADS = {
     # name: (description, plan kwargs, seconds of signal per rank)
     "metric": ("periodogram N=4096 Hann 50% ovl, 1 h @ 48 kHz per GPU (BASELINE metric config)",
@@ -190,7 +191,39 @@ def cpu_reference_rate(kw, target_s=6.0, cores=None):
 
 
 # ----------------------------------------------------------------------------- main
+def pin_to_gpu_numa_node(local_rank: int):
+    """Run this process (and place the pinned host buffers it allocates next) on the CPUs of the
+    NUMA node the GPU hangs off: with several ranks per box the end-to-end copies otherwise cross
+    the socket interconnect.  Returns the previous affinity (restored for the CPU baseline leg)."""
+    old = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:      # no NVML, no topology information: leave the affinity alone
+        sys.stderr.write(f"bench.py: NUMA pinning skipped ({e})\n")
+    return old
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the real stdout."""
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _STDOUT_FD
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner
+    # under torchrun, for one) is sent to stderr instead
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -245,7 +278,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "frames/s", "cores": base["cores"], "kind": base["kind"],
                                  "sample": base["sample"]},
                 "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -255,6 +288,7 @@ def main():
     if not torch.cuda.is_available() or api.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (libglfer_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    affinity0 = pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -360,11 +394,12 @@ def main():
             "checksum": checksum}
     if not args.no_cpu and world == 1:
         try:
+            os.sched_setaffinity(0, affinity0)           # the baseline uses every core of the box
             cb = cpu_reference_rate(kw, target_s=6.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the GPU line must not be lost to a baseline problem
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
