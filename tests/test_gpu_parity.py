@@ -485,7 +485,7 @@ def test_headless_harness_per_call_and_batch(gpu_api, tmp_path):
     synth.write_wav16(wav, pcm, 8000)
     ref_exe = os.path.join(os.path.dirname(R.path()), "glfer_headless_ref")
     for args in (["-n", "1024", "-w", "0", "-o", "0.5", "-s", "1"], ["-n", "1024", "-m", "mtm", "-k", "7", "-W", "4", "-o", "0.5"],
-                 ["-n", "2048", "-w", "7", "-o", "0.75", "-A", "2", "-d", "4"]):
+                 ["-n", "2048", "-w", "7", "-o", "0.75", "-A", "2", "-d", "4"], ["-n", "1024", "-m", "lmp", "-L", "4", "-o", "0.5"]):
         outs = {}
         for tag, extra in (("percall", []), ("batch", ["-B"])):
             out = str(tmp_path / f"{tag}.f32")
@@ -498,6 +498,8 @@ def test_headless_harness_per_call_and_batch(gpu_api, tmp_path):
         b = outs["batch"].reshape(-1, n // 2 + 1).astype(np.float64)
         if "-A" in args:
             assert np.allclose(a, b, rtol=5e-4, atol=1e-15)
+        elif "lmp" in args:
+            assert_lmp_close(a.astype(np.float32), b.astype(np.float32), "LMP per-call vs batch")
         else:
             assert_psd_close(a, b, "per-call vs batch")
         if os.path.exists(ref_exe):
@@ -506,6 +508,8 @@ def test_headless_harness_per_call_and_batch(gpu_api, tmp_path):
             r = np.fromfile(out, dtype=np.float32).reshape(a.shape).astype(np.float64)
             if "-A" in args:
                 assert np.allclose(a, r, rtol=5e-4, atol=1e-15)
+            elif "lmp" in args:
+                assert_lmp_close(a.astype(np.float32), r.astype(np.float32), "headless LMP product vs reference build")
             else:
                 assert_psd_close(a, r, "headless product vs reference build")
 

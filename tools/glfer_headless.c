@@ -13,7 +13,7 @@
  * changes.  Output: one binary file of float32 rows [frames][N/2+1] (the PSD, or avg[] when
  * averaging is on), plus a one-line summary on stdout.
  *
- *   glfer_headless -f in.wav [-n 1024] [-w 0..7] [-o overlap] [-m fft|mtm] [-k kmax] [-W nw]
+ *   glfer_headless -f in.wav [-n 1024] [-w 0..7] [-o overlap] [-m fft|mtm|lmp] [-k kmax] [-W nw] [-L lmp_av]
  *                  [-A 0..3] [-d depth] [-b minbin:maxbin] [-s 0|1] [-B] -O rows.f32
  *   -B uses the library's batched entry point (glfer_gram_run_wav) instead of the per-block
  *      calls (product build only).
@@ -29,12 +29,14 @@
 #include "fft.h"
 #include "mtm.h"
 #include "avg.h"
+#include "lmp.h"
 opt_t opt;
 glfer_t glfer;
 #else
 #include "fft.h"
 #include "mtm.h"
 #include "avg.h"
+#include "lmp.h"
 #include "glfer_b200.h"
 /* layout-compatible stand-ins for the reference's globals (glfer.h:62-139): the library
    resolves them weakly by name, exactly as fft.c's `extern opt_t opt; extern glfer_t glfer;` */
@@ -58,7 +60,7 @@ opt_t opt;
 glfer_t glfer;
 #define TRUE 1
 #define FALSE 0
-enum { MODE_FFT = 0, MODE_MTM = 1 };
+enum { MODE_FFT = 0, MODE_MTM = 1, MODE_LMP = 3 };      /* glfer.h:45 */
 enum { NO_AVG = 0, AVG_SUMAVG, AVG_PLAIN, AVG_SUMEXTREME };
 #endif
 
@@ -96,17 +98,18 @@ static int wav_next(wav_src *w)
 int main(int argc, char **argv)
 {
   const char *in = NULL, *out = NULL;
-  int n = 1024, window = 7, mode = MODE_FFT, kmax = 7, avgmode = NO_AVG, depth = 4, minbin = -1, maxbin = -1;
+  int n = 1024, window = 7, mode = MODE_FFT, kmax = 7, lmp_av = 4, avgmode = NO_AVG, depth = 4, minbin = -1, maxbin = -1;
   int autoscale = 1, batch = 0;
   float overlap = 0.0f, nw = 4.0f;
   int c;
-  while ((c = getopt(argc, argv, "f:n:w:o:m:k:W:A:d:b:s:O:B")) != -1) {
+  while ((c = getopt(argc, argv, "f:n:w:o:m:k:W:A:d:b:s:O:BL:")) != -1) {
     switch (c) {
     case 'f': in = optarg; break;
     case 'n': n = atoi(optarg); break;
     case 'w': window = atoi(optarg); break;
     case 'o': overlap = (float) atof(optarg); break;
-    case 'm': mode = strcmp(optarg, "mtm") == 0 ? MODE_MTM : MODE_FFT; break;
+    case 'm': mode = strcmp(optarg, "mtm") == 0 ? MODE_MTM : (strcmp(optarg, "lmp") == 0 ? MODE_LMP : MODE_FFT); break;
+    case 'L': lmp_av = atoi(optarg); break;
     case 'k': kmax = atoi(optarg); break;
     case 'W': nw = (float) atof(optarg); break;
     case 'A': avgmode = atoi(optarg); break;
@@ -119,7 +122,7 @@ int main(int argc, char **argv)
     }
   }
   if (!in || !out) {
-    fprintf(stderr, "usage: glfer_headless -f in.wav -O rows.f32 [-n N] [-w win] [-o ovl] [-m fft|mtm] ...\n");
+    fprintf(stderr, "usage: glfer_headless -f in.wav -O rows.f32 [-n N] [-w win] [-o ovl] [-m fft|mtm|lmp] ...\n");
     return 2;
   }
   const int bins = n / 2 + 1;
@@ -132,6 +135,7 @@ int main(int argc, char **argv)
   opt.autoscale = autoscale;
   opt.mtm_w = nw;
   opt.mtm_k = kmax;
+  opt.lmp_av = lmp_av;
   opt.averaging = avgmode;
   opt.avgsamples = depth;
   FILE *fo = fopen(out, "wb");
@@ -144,7 +148,7 @@ int main(int argc, char **argv)
     glfer_gram_config cfg;
     glfer_gram_config_default(&cfg);
     cfg.mode = mode; cfg.n = n; cfg.window_type = window; cfg.overlap = overlap; cfg.sub_mean = autoscale;
-    cfg.mtm_w = nw; cfg.mtm_kmax = kmax; cfg.avg_mode = avgmode; cfg.avg_depth = depth;
+    cfg.mtm_w = nw; cfg.mtm_kmax = kmax; cfg.avg_mode = avgmode; cfg.avg_depth = depth; cfg.lmp_av = lmp_av;
     glfer_wav wav;
     if (glfer_wav_load(in, &wav) != 0) { fprintf(stderr, "%s\n", glfer_b200_last_error()); return 1; }
     const float binsize = (float) wav.sample_rate / (float) n;
@@ -162,7 +166,7 @@ int main(int argc, char **argv)
     glfer_gram_plan_destroy(plan);
     glfer_wav_free(&wav);
     fclose(fo);
-    printf("frames %ld bins %d hop %d mode %s path batch checksum %.9e\n", frames, bins, hop, mode == MODE_MTM ? "mtm" : "fft", checksum);
+    printf("frames %ld bins %d hop %d mode %s path batch checksum %.9e\n", frames, bins, hop, mode == MODE_MTM ? "mtm" : (mode == MODE_LMP ? "lmp" : "fft"), checksum);
     return 0;
   }
 #else
@@ -175,8 +179,10 @@ int main(int argc, char **argv)
   opt.sample_rate = src.rate;
   fft_params_t fft_par;
   mtm_params_t mtm_par;
+  lmp_params_t lmp_par;
   memset(&fft_par, 0, sizeof fft_par);
   memset(&mtm_par, 0, sizeof mtm_par);
+  memset(&lmp_par, 0, sizeof lmp_par);
   avg_data_t avgdata;
   init_avg(&avgdata);
   alloc_avg(&avgdata, n, depth);                        /* source.c:311-312: width N */
@@ -184,6 +190,10 @@ int main(int argc, char **argv)
   if (mode == MODE_FFT) {
     fft_par.n = n; fft_par.window_type = window; fft_par.overlap = overlap; fft_par.a = 0.0f; fft_par.limiter = 0;
     fft_init(&fft_par);
+  } else if (mode == MODE_LMP) {                        /* source.c:394-400 */
+    lmp_par.fft.n = n; lmp_par.fft.window_type = RECTANGULAR_WINDOW; lmp_par.fft.overlap = overlap;
+    lmp_par.fft.a = 0.0f; lmp_par.fft.limiter = 0; lmp_par.avg = lmp_av;
+    lmp_init(&lmp_par);
   } else {
     mtm_par.fft.n = n; mtm_par.fft.window_type = RECTANGULAR_WINDOW; mtm_par.fft.overlap = overlap;
     mtm_par.w = nw; mtm_par.kmax = kmax;
@@ -200,6 +210,8 @@ int main(int argc, char **argv)
     if (mode == MODE_FFT) {
       fft_do(src.buff, &fft_par);
       fft_psd(psdbuf, NULL, &fft_par);
+    } else if (mode == MODE_LMP) {
+      lmp_do(src.buff, psdbuf, NULL, &lmp_par);        /* source.c:155-156 */
     } else {
       mtm_do(src.buff, psdbuf, NULL, &mtm_par);
     }
@@ -219,9 +231,11 @@ int main(int argc, char **argv)
     for (int i = 0; i < bins; i++) checksum += res[i];
     frames++;
   }
-  if (mode == MODE_FFT) fft_close(&fft_par); else mtm_close(&mtm_par);
+  if (mode == MODE_FFT) fft_close(&fft_par);
+  else if (mode == MODE_LMP) lmp_close(&lmp_par);
+  else mtm_close(&mtm_par);
   delete_avg(&avgdata);
   fclose(fo);
-  printf("frames %ld bins %d hop %d mode %s path per-call checksum %.9e\n", frames, bins, hop, mode == MODE_MTM ? "mtm" : "fft", checksum);
+  printf("frames %ld bins %d hop %d mode %s path per-call checksum %.9e\n", frames, bins, hop, mode == MODE_MTM ? "mtm" : (mode == MODE_LMP ? "lmp" : "fft"), checksum);
   return 0;
 }
