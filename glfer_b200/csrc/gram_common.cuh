@@ -634,7 +634,11 @@ template <int M, int P, bool RT> struct RingMidPasses {
 template <int M, bool MULTI> struct RingGeo {
   static constexpr bool BIG = (M == 8192) && !MULTI;
   static constexpr bool RT = Geo<M>::RT || BIG;
-  static constexpr int MINB = BIG ? 1 : Geo<M>::MINB;
+#ifndef GLB_MULTI_MINB
+#define GLB_MULTI_MINB 4          // CTAs per SM the 128-thread multitaper ring kernel is compiled for: 115 registers, no
+                                  // spills (6 / 5 / 4 / 3 CTAs: 3.34 / 3.17 / 3.03 / 3.02 ms on C3); 0 = as the periodogram
+#endif
+  static constexpr int MINB = BIG ? 1 : ((MULTI && GLB_MULTI_MINB > 0 && Geo<M>::THREADS == 128) ? GLB_MULTI_MINB : Geo<M>::MINB);
 };
 template <int M, bool MULTI, int QSC>
 __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gram_ring_kernel(const KParams p) {
@@ -737,26 +741,26 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     }
     const int ntap = MULTI ? p.ntapers : 1;
     float mu_next = 0.f;
+    // the frame's samples, block means removed: fetched once, kept in registers across the tapers
+    // (the multitaper variant is compiled for 4 CTAs per SM and has the registers for it)
+    float2 x[kPoints];
+    // (mean-ahead variant: the mean is already in mu_new)
+    const bool nm = !GLB_MEAN_AHEAD && it > 0;
+    float *redn = red + slot_new * GeoM::NW;
+    if constexpr (QSC >= 0) {
+      ring_fetch<M, (QSC >= 0 ? QSC : 0)>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean);
+    } else {
+      switch (qs) {
+        case 4: ring_fetch<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+        case 3: ring_fetch<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+        case 2: ring_fetch<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+        case 1: ring_fetch<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+        default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+      }
+    }
     for (int j = 0; j < ntap; ++j) {
       float2 v[kPoints];
-      {
-        float2 x[kPoints];
-        // (mean-ahead variant: the mean is already in mu_new)
-        const bool nm = !GLB_MEAN_AHEAD && it > 0 && j == 0;
-        float *redn = red + slot_new * GeoM::NW;
-        if constexpr (QSC >= 0) {
-          ring_fetch<M, (QSC >= 0 ? QSC : 0)>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean);
-        } else {
-          switch (qs) {
-            case 4: ring_fetch<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-            case 3: ring_fetch<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-            case 2: ring_fetch<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-            case 1: ring_fetch<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-            default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-          }
-        }
-        apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
-      }
+      apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
       // Block f + 1 was requested after barrier (A) of this frame's last taper; before the last
       // block barrier of the transform every thread waits for it and leaves its share of the
       // block sum in `red`, so the mean is there after that barrier: the next frame starts
@@ -789,8 +793,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
         __syncthreads();
         pass_store<M, 0>(v, t, buf, p.tw);
       }
-      // tight ring: past (A) of the last taper nobody reads the oldest block any more
-      if (!GLB_RING_EXTRA && next_there && last_tap && t == 0) request_next();
+      // tight ring: the frame is in registers, so past the first (A) nobody reads the ring any more
+      if (!GLB_RING_EXTRA && next_there && j == 0 && t == 0) request_next();
       if constexpr (Plan<M>::NP == 2) land_next();
       __syncthreads();
       RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, gb, gpar, elected, land_next);
