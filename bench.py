@@ -42,6 +42,10 @@ WORKLOADS = {
     # name: (description, plan kwargs, seconds of signal per rank)
     "metric": ("periodogram N=4096 Hann 50% ovl, 1 h @ 48 kHz per GPU (BASELINE metric config)",
                dict(n=4096, window_type=0, overlap=0.5, sub_mean=True), 3600),
+    "c1": ("periodogram N=1024 Hanning 50% ovl (BASELINE configs[0] shape), 1 h @ 48 kHz per GPU",
+           dict(n=1024, window_type=0, overlap=0.5, sub_mean=True), 3600),
+    "n2048": ("periodogram N=2048 Hanning 50% ovl, 1 h @ 48 kHz per GPU",
+              dict(n=2048, window_type=0, overlap=0.5, sub_mean=True), 3600),
     "c2": ("periodogram N=4096 Kaiser 75% ovl + avg.c plain averaging, 1 h @ 48 kHz",
            dict(n=4096, window_type=7, overlap=0.75, sub_mean=True, avg_mode=2, avg_depth=4, avg_minbin=34,
                 avg_maxbin=102), 3600),

@@ -92,9 +92,26 @@ template <int M> struct Geo {
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
 };
 
-// Barrier over the frame groups of a CTA.  (Tried and dropped, B200: mapping a 4-warp group onto
-// one SM sub-partition with its own named barrier -- no gain over the CTA-wide barrier.)
-template <int M> __device__ __forceinline__ void group_sync(int) { __syncthreads(); }
+// Barrier of one frame group (T threads; a CTA of 128 threads holds 128 / T groups): nothing a
+// group touches in shared memory is shared with another group, so groups that fit a warp
+// (N <= 1024) synchronise with a warp-level sync (+3 % at N = 1024); larger groups use the
+// CTA-wide barrier.
+#ifndef GLB_CTA_BARRIER
+#define GLB_CTA_BARRIER 0             // 1 (experiments): every group barrier is a CTA-wide bar.sync
+#endif
+template <int M> __device__ __forceinline__ void group_sync(int g) {
+  constexpr int T = M / kPoints;
+  if constexpr (GLB_CTA_BARRIER) {
+    (void) g;
+    __syncthreads();
+  } else if constexpr (T <= 32) {
+    __syncwarp();                       // a frame group is (part of) one warp: its buffers never leave the warp
+  } else {
+    // (a named barrier per 2-warp group at N = 2048 measured 6 % slower than the CTA-wide one)
+    (void) g;
+    __syncthreads();
+  }
+}
 
 // ---- mbarrier / TMA bulk-copy helpers (1-D cp.async.bulk global -> shared) ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -519,10 +536,10 @@ __device__ __forceinline__ float ring_block_total(float s_warp, const float *red
   return s * inv_hop;
 }
 template <int M>
-__device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop) {
+__device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t, float *red, float inv_hop, int g) {
   constexpr int T = M / kPoints, NW = (T + 31) / 32;
   const float s = ring_block_partial<M>(blk, qs, t, red);
-  if (NW > 1) __syncthreads();
+  if (NW > 1) group_sync<M>(g);
   return ring_block_total<M>(s, red, inv_hop);
 }
 
@@ -535,7 +552,7 @@ __device__ __forceinline__ float ring_block_mean(const float *blk, int qs, int t
 template <int M, int QS>
 __device__ __forceinline__ void ring_fetch(float2 (&x)[kPoints], int t, const float *ring, int hop, int slot_oldest,
                                            int slots, float *mu, float &mu_new, bool sub, bool new_mean, float *red,
-                                           float inv_hop) {
+                                           float inv_hop, int g) {
   constexpr int T = M / kPoints, NB = kPoints >> QS, NW = (T + 31) / 32, W = T < 32 ? T : 32;
   int sidx = slot_oldest;
   int slot_of[NB];
@@ -559,7 +576,7 @@ __device__ __forceinline__ void ring_fetch(float2 (&x)[kPoints], int t, const fl
     for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (NW > 1) {
       if ((t & 31) == 0) red[t >> 5] = s;
-      __syncthreads();
+      group_sync<M>(g);
     }
     mu_new = ring_block_total<M>(s, red, inv_hop);
     if (t == 0) mu[slot_of[NB - 1]] = mu_new;
@@ -603,7 +620,7 @@ __device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[1
 template <int M, int P, bool RT> struct RingMidPasses {
   template <class H>
   static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr,
-                                             unsigned long long *gb, unsigned &gpar, bool elected, H &&hook) {
+                                             unsigned long long *gb, unsigned &gpar, bool elected, int g, H &&hook) {
     if constexpr (P < Plan<M>::NP - 1) {
       pass_load<M>(v, t, buf);
       if constexpr (RT) {
@@ -613,16 +630,16 @@ template <int M, int P, bool RT> struct RingMidPasses {
         gpar ^= 2u;
 #else
         pass_compute_rt<M, P>(v, tr);
-        __syncthreads();                // every thread has read before anyone overwrites
+        group_sync<M>(g);                // every thread has read before anyone overwrites
 #endif
         pass_scatter<M, P>(v, t, buf);
       } else {
-        __syncthreads();
+        group_sync<M>(g);
         pass_store<M, P>(v, t, buf, tw);
       }
       if constexpr (P == Plan<M>::NP - 2) hook();
-      __syncthreads();
-      RingMidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, gb, gpar, elected, hook);
+      group_sync<M>(g);
+      RingMidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, gb, gpar, elected, g, hook);
     }
   }
 };
@@ -680,7 +697,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     mbar_init(&gb[1], GeoM::NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
+  group_sync<M>(g);
 
   // prologue: the nb blocks of the first frame (zeros before the stream start, fft.c:103-108)
   for (int lb = 0; lb < nb; lb++) {
@@ -703,13 +720,13 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       phase_bits ^= 1u << lb;
     }
     if (sub) {
-      __syncthreads();                                           // zero fill visible to all (uniform: groups differ in blk)
-      const float m = ring_block_mean<M>(ring + (size_t) lb * hop, qs, t, red + lb * GeoM::NW, p.inv_hop_mean);
+      group_sync<M>(g);                                           // zero fill visible to all (uniform: groups differ in blk)
+      const float m = ring_block_mean<M>(ring + (size_t) lb * hop, qs, t, red + lb * GeoM::NW, p.inv_hop_mean, g);
       mu_new = (blk < 0) ? 0.f : m;
       if (t == 0) mu[lb] = mu_new;
     }
   }
-  __syncthreads();                                               // zero fill and mu[] visible
+  group_sync<M>(g);                                               // zero fill and mu[] visible
 
   int slot_new = nb - 1;                                         // slot of the newest block of frame `it`
   for (int it = 0; it < p.frames_per_group; ++it) {
@@ -748,14 +765,14 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     const bool nm = !GLB_MEAN_AHEAD && it > 0;
     float *redn = red + slot_new * GeoM::NW;
     if constexpr (QSC >= 0) {
-      ring_fetch<M, (QSC >= 0 ? QSC : 0)>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean);
+      ring_fetch<M, (QSC >= 0 ? QSC : 0)>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g);
     } else {
       switch (qs) {
-        case 4: ring_fetch<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-        case 3: ring_fetch<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-        case 2: ring_fetch<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-        case 1: ring_fetch<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
-        default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean); break;
+        case 4: ring_fetch<M, 4>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g); break;
+        case 3: ring_fetch<M, 3>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g); break;
+        case 2: ring_fetch<M, 2>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g); break;
+        case 1: ring_fetch<M, 1>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g); break;
+        default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g); break;
       }
     }
     for (int j = 0; j < ntap; ++j) {
@@ -786,18 +803,18 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
         gpar ^= 1u;
 #else
         pass_compute_rt<M, 0>(v, tr);
-        __syncthreads();               // (A) the previous transform's last pass has been read by all
+        group_sync<M>(g);               // (A) the previous transform's last pass has been read by all
 #endif
         pass_scatter<M, 0>(v, t, buf);
       } else {
-        __syncthreads();
+        group_sync<M>(g);
         pass_store<M, 0>(v, t, buf, p.tw);
       }
       // tight ring: the frame is in registers, so past the first (A) nobody reads the ring any more
       if (!GLB_RING_EXTRA && next_there && j == 0 && t == 0) request_next();
       if constexpr (Plan<M>::NP == 2) land_next();
-      __syncthreads();
-      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, gb, gpar, elected, land_next);
+      group_sync<M>(g);
+      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, gb, gpar, elected, g, land_next);
       if (GLB_MEAN_AHEAD && last_tap && next_there && sub) {
         mu_next = ring_block_total<M>(s_warp, red, p.inv_hop_mean);
         if (t == 0) mu[slot_next] = mu_next;
@@ -962,7 +979,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (PairGeo<M, QS>::MINB)) gram_
     if (sub) {
 #pragma unroll
       for (int lb = 0; lb < NB - 1; lb++) {
-        const float m = ring_block_mean<M>(ring + (size_t) lb * HOP, QS, t, red + lb * NW, p.inv_hop_mean);
+        const float m = ring_block_mean<M>(ring + (size_t) lb * HOP, QS, t, red + lb * NW, p.inv_hop_mean, g);
         if (t == 0) mu[lb] = m;
       }
       __syncthreads();
