@@ -775,6 +775,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
         default: ring_fetch<M, 0>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g); break;
       }
     }
+    // (requesting the next taper's 16 pairs right after the multiply, to take their L2 latency off
+    // the next transform, measured slower: 32 more live registers -> 3 CTAs/SM or spills)
     for (int j = 0; j < ntap; ++j) {
       float2 v[kPoints];
       apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
