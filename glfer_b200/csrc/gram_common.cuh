@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdint>
 #include <atomic>
@@ -1311,7 +1312,8 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
     if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && (allow & 2) != 0) {
       const int nb = kPoints >> qs;
       const RingLayout L = ring_layout<M>(kp.hop, nb);
-      const size_t smem = (size_t) GeoM::G * L.group_bytes;
+      size_t smem = (size_t) GeoM::G * L.group_bytes;
+      if (const char *e = getenv("GLB_SMEM_PAD_KB")) smem += (size_t) atoi(e) * 1024;     // experiments: cap the CTAs per SM
       if (smem <= 227 * 1024) {
         // 50 % and 75 % overlap have kernels with the ring geometry folded in
         void (*rk)(const KParams) = nullptr;
