@@ -10,7 +10,7 @@ tail -3 $O/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
 python bench.py > $O/bench_metric.json 2> $O/bench_metric.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
-for w in c2 c3 c4 c5; do
+for w in c1 c2 c3 c4 c5 lmp; do
   python bench.py --workload $w --steps 50 --warmup 3 > $O/bench_$w.json 2> $O/bench_$w.err
 done
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
