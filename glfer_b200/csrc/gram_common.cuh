@@ -730,11 +730,14 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   group_sync<M>(g);                                               // zero fill and mu[] visible
 
   int slot_new = nb - 1;                                         // slot of the newest block of frame `it`
-  for (int it = 0; it < p.frames_per_group; ++it) {
-    const long long fl = fb + it;
-    const bool active = fl < p.nframes;
-    const long long f = p.first_frame + fl;
-    const bool next_there = (it + 1 < p.frames_per_group) && (fl + 1 < p.nframes);
+  // loop state carried incrementally (no 64-bit multiplies per frame): frames of this group that
+  // exist, the row to write and the block the next bulk copy reads
+  const int nact = group_active ? (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group) : 0;
+  float *row_ptr = p.rows + fb * p.row_stride;
+  const float *next_src = p.samples + ((f_first + 1) * (long long) hop - p.origin);
+  for (int it = 0; it < p.frames_per_group; ++it, row_ptr += p.row_stride, next_src += hop) {
+    const bool active = it < nact;
+    const bool next_there = it + 1 < nact;
     const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
 #if !GLB_MEAN_AHEAD
     if (it > 0 && active) {
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     auto request_next = [&]() {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&mbar[slot_next], blk_bytes);
-      tma_load_1d(ring + (size_t) slot_next * hop, p.samples + ((f + 1) * (long long) hop - p.origin), blk_bytes, &mbar[slot_next]);
+      tma_load_1d(ring + (size_t) slot_next * hop, next_src, blk_bytes, &mbar[slot_next]);
     };
     // spare slot: slot_next held block f - nb, whose last readers passed a block barrier in frame f - 1
     if (GLB_RING_EXTRA && next_there && t == 0) request_next();
@@ -822,7 +825,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
         mu_next = ring_block_total<M>(s_warp, red, p.inv_hop_mean);
         if (t == 0) mu[slot_next] = mu_next;
       }
-      float *row = p.rows + fl * p.row_stride;
+      float *row = row_ptr;
       const bool db = p.rows_db != 0;
       float yv[17];
       yv[16] = 1.f;                     // only thread 0 has a 17th bin
@@ -859,7 +862,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
     }
     if (MULTI && active) {
-      float *row = p.rows + fl * p.row_stride;
+      float *row = row_ptr;
       const bool db = p.rows_db != 0;
 #pragma unroll
       for (int slot = 0; slot < 17; slot++) {
