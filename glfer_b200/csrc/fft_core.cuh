@@ -455,21 +455,14 @@ GLB_HD void apply_tw_bases(float2 *v, const Tw3 *b) {
 
 // mid pass with register twiddles, split in two so the block barrier can sit between the
 // arithmetic and the stores (warps then wait with their butterflies already done)
-struct NoHook {
-  GLB_HD void operator()(float) const {}
-};
-// `loaded` runs once every value of v has been consumed by a twiddle multiplication, i.e. once the
-// loads that produced v are known to be complete (split-phase barriers arrive there)
-template <int M, int P, class H = NoHook>
-GLB_HD void pass_compute_rt(float2 *v, const TwRegs &tr, H &&loaded = H()) {
+template <int M, int P>
+GLB_HD void pass_compute_rt(float2 *v, const TwRegs &tr) {
   constexpr int R = PlanRadix<M, P>::R, S = kPoints / R, NB = TwBases<R>::n;
-  if constexpr (P > 0) {
 #pragma unroll
-    for (int u = 0; u < S; u++) apply_tw_bases<R, S>(v + u, &tr.mid[P - 1][u * NB]);
+  for (int u = 0; u < S; u++) {
+    if constexpr (P > 0) apply_tw_bases<R, S>(v + u, &tr.mid[P - 1][u * NB]);
+    Dft<R, S>::run(v + u);
   }
-  loaded(v[kPoints - 1].x);          // a value that depends on the last load
-#pragma unroll
-  for (int u = 0; u < S; u++) Dft<R, S>::run(v + u);
 }
 
 template <int M, int P>

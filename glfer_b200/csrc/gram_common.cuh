@@ -139,20 +139,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                : "memory");
 }
 
-// Split-phase barrier of one frame group on a shared-memory mbarrier: every warp arrives once
-// (one elected lane, after the warp has converged) when it is done with the buffer, and waits
-// for the phase only where it is about to overwrite it; the work in between hides the skew
-// between the warps that a bar.sync at one point would expose.
-#ifndef GLB_SPLIT_BAR
-#define GLB_SPLIT_BAR 0   // measured 2-3 % slower than bar.sync (spinning try_wait + elected arrive cost more than the skew they hide)
-#endif
-// `dep`: a register computed from the last shared-memory load that has to be complete (loads of
-// one warp return in order): the arrive cannot be scheduled ahead of it.
-__device__ __forceinline__ void gbar_arrive(unsigned long long *bar, bool elected, float dep) {
-  __syncwarp();
-  if (elected) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "f"(dep) : "memory");
-}
-
 __device__ __forceinline__ float2 ldg2(const float2 *p) { return __ldg(p); }
 // The taper table is the one global array every frame re-reads; with ~28 KB of L1 left beside the
 // shared-memory carve-out it stays resident only if its lines are the last to go and the row
@@ -482,10 +468,6 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 // so every sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM
 // latency hides behind the previous frame's transform.  Block means (sub_mean) are computed
 // once per block when it lands and kept beside the ring.
-#ifndef GLB_MEAN_AHEAD
-#define GLB_MEAN_AHEAD 0  // 1: the next block's mean is formed before the last barrier of the current transform
-                          //    (measured 4 % slower: the block has to land 40 % of a frame earlier)
-#endif
 #ifndef GLB_RING_EXTRA
 #define GLB_RING_EXTRA 0  // 1: one spare slot, the next block is requested at the top of a frame;
 #endif                    // 0: NB slots, requested after barrier (A) into the oldest block's slot
@@ -502,7 +484,7 @@ __host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
   L.red_off = L.ring_off + (size_t) L.slots * hop * sizeof(float);
   L.mu_off = L.red_off + (size_t) 18 * Geo<M>::NW * sizeof(float);
   L.mbar_off = ((L.mu_off + 18 * sizeof(float) + 7) / 8) * 8;
-  L.group_bytes = ((L.mbar_off + 20 * sizeof(unsigned long long) + 15) / 16) * 16;   // 18 ring slots + 2 group barriers
+  L.group_bytes = ((L.mbar_off + 18 * sizeof(unsigned long long) + 15) / 16) * 16;
   return L;
 }
 
@@ -615,38 +597,25 @@ __device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[1
   if (t == 0) st_row(row + M / 2, yv[16]);
 }
 
-// mid passes of the ring kernel; `hook` runs before the last block barrier ahead of the final pass.
-// Register-twiddle plans: the barrier "everyone has read before anyone overwrites" is split-phase
-// (gb[1]: arrive once the loads are consumed, wait after the butterflies).
+// mid passes of the ring kernel
 template <int M, int P, bool RT> struct RingMidPasses {
-  template <class H>
-  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr,
-                                             unsigned long long *gb, unsigned &gpar, bool elected, int g, H &&hook) {
+  static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr, int g) {
     if constexpr (P < Plan<M>::NP - 1) {
       pass_load<M>(v, t, buf);
       if constexpr (RT) {
-#if GLB_SPLIT_BAR
-        pass_compute_rt<M, P>(v, tr, [&](float dep) { gbar_arrive(&gb[1], elected, dep); });
-        mbar_wait(&gb[1], (gpar >> 1) & 1u);
-        gpar ^= 2u;
-#else
         pass_compute_rt<M, P>(v, tr);
         group_sync<M>(g);                // every thread has read before anyone overwrites
-#endif
         pass_scatter<M, P>(v, t, buf);
       } else {
         group_sync<M>(g);
         pass_store<M, P>(v, t, buf, tw);
       }
-      if constexpr (P == Plan<M>::NP - 2) hook();
       group_sync<M>(g);
-      RingMidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, gb, gpar, elected, g, hook);
+      RingMidPasses<M, P + 1, RT>::run(v, t, buf, tw, tr, g);
     }
   }
 };
 
-// QSC >= 0: the overlap is a compile-time constant (hop = 2T << QSC): ring geometry and slot
-// addresses fold into immediates; QSC = -1 reads it from the parameters (any regular overlap).
 // N = 16384 (512 threads, one CTA per SM because of its 138 KB of shared memory): the periodogram
 // variant may use 128 registers, enough to keep the twiddles of its two mid passes in registers
 template <int M, bool MULTI> struct RingGeo {
@@ -689,13 +658,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   TwRegs tr;
   if constexpr (RT) load_tw_regs<M>(tr, t, p.tw, p.vtab);
 
-  unsigned long long *gb = mbar + 18;                            // group barriers: [0] = (A), [1] = mid passes
-  const bool elected = (T >= 32) ? ((t & 31) == 0) : (t == 0);
-  unsigned gpar = 0;                                             // parity bits of gb[0], gb[1]
   if (t == 0) {
     for (int sl = 0; sl < slots; sl++) mbar_init(&mbar[sl], 1);
-    mbar_init(&gb[0], GeoM::NW);
-    mbar_init(&gb[1], GeoM::NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   group_sync<M>(g);
@@ -739,13 +703,11 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     const bool active = it < nact;
     const bool next_there = it + 1 < nact;
     const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
-#if !GLB_MEAN_AHEAD
     if (it > 0 && active) {
       // block f was requested one frame ago
       mbar_wait(&mbar[slot_new], (phase_bits >> slot_new) & 1u);
       phase_bits ^= 1u << slot_new;
     }
-#endif
     auto request_next = [&]() {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&mbar[slot_next], blk_bytes);
@@ -761,12 +723,10 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       for (int i = 0; i < 17; i++) acc[i] = 0.f;
     }
     const int ntap = MULTI ? p.ntapers : 1;
-    float mu_next = 0.f;
     // the frame's samples, block means removed: fetched once, kept in registers across the tapers
     // (the multitaper variant is compiled for 4 CTAs per SM and has the registers for it)
     float2 x[kPoints];
-    // (mean-ahead variant: the mean is already in mu_new)
-    const bool nm = !GLB_MEAN_AHEAD && it > 0;
+    const bool nm = it > 0;            // the newest block has just landed: its mean is formed in ring_fetch
     float *redn = red + slot_new * GeoM::NW;
     if constexpr (QSC >= 0) {
       ring_fetch<M, (QSC >= 0 ? QSC : 0)>(x, t, ring, hop, slot_oldest, slots, mu, mu_new, sub, nm, redn, p.inv_hop_mean, g);
@@ -784,33 +744,9 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     for (int j = 0; j < ntap; ++j) {
       float2 v[kPoints];
       apply_taper<M, true>(v, x, t, p, p.tapers + (size_t) j * N);
-      // Block f + 1 was requested after barrier (A) of this frame's last taper; before the last
-      // block barrier of the transform every thread waits for it and leaves its share of the
-      // block sum in `red`, so the mean is there after that barrier: the next frame starts
-      // without a barrier of its own and without waiting for DRAM.
-      const bool last_tap = (j == ntap - 1);
-      float s_warp = 0.f;
-      auto land_next = [&]() {
-        if (GLB_MEAN_AHEAD && last_tap && next_there) {
-          mbar_wait(&mbar[slot_next], (phase_bits >> slot_next) & 1u);
-          phase_bits ^= 1u << slot_next;
-          if (sub) s_warp = ring_block_partial<M>(ring + (size_t) slot_next * hop, qs, t, red);
-        }
-      };
       if constexpr (RT) {
-#if GLB_SPLIT_BAR
-        // (A) split-phase: a warp arrives once its ring samples are in registers (which is also
-        // after its reads of the previous transform's last pass) and waits only after the
-        // first-pass butterflies, just before it overwrites the buffer; thread 0 may then also
-        // hand the oldest ring slot to the next bulk copy.
-        gbar_arrive(&gb[0], elected, v[kPoints - 1].x);
         pass_compute_rt<M, 0>(v, tr);
-        mbar_wait(&gb[0], gpar & 1u);
-        gpar ^= 1u;
-#else
-        pass_compute_rt<M, 0>(v, tr);
-        group_sync<M>(g);               // (A) the previous transform's last pass has been read by all
-#endif
+        group_sync<M>(g);              // (A) the previous transform's last pass has been read by all
         pass_scatter<M, 0>(v, t, buf);
       } else {
         group_sync<M>(g);
@@ -818,13 +754,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
       // tight ring: the frame is in registers, so past the first (A) nobody reads the ring any more
       if (!GLB_RING_EXTRA && next_there && j == 0 && t == 0) request_next();
-      if constexpr (Plan<M>::NP == 2) land_next();
       group_sync<M>(g);
-      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, gb, gpar, elected, g, land_next);
-      if (GLB_MEAN_AHEAD && last_tap && next_there && sub) {
-        mu_next = ring_block_total<M>(s_warp, red, p.inv_hop_mean);
-        if (t == 0) mu[slot_next] = mu_next;
-      }
+      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
       float *row = row_ptr;
       const bool db = p.rows_db != 0;
       float yv[17];
@@ -874,7 +805,6 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
     }
     slot_new = slot_next;
-    if (GLB_MEAN_AHEAD) mu_new = mu_next;
   }
 }
 
