@@ -202,27 +202,33 @@ __device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KPar
 // block, warps reduce by shuffle, the group combines through shared memory.  A block gets
 // the same summation tree in every frame it appears in, so its mean is bit-identical
 // across frames (and across time shards).  Zero history sums to a zero mean.
+// `reuse` (groups of more than one warp): the warp partial sums of this frame are still in `red`
+// from an earlier taper of the same frame: no summation, no shuffles, no barrier.
 template <int M, int QS>
-__device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, float *red, float inv_hop, int g) {
+__device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, float *red, float inv_hop, int g, bool reuse) {
   constexpr int T = M / kPoints, NW = (T + 31) / 32, NB = kPoints >> QS;
   constexpr int W = T < 32 ? T : 32;      // lanes of a warp that belong to this group
   float bs[NB];
+  if (NW == 1 || !reuse) {
 #pragma unroll
-  for (int b = 0; b < NB; b++) {
-    float s = 0.f;
+    for (int b = 0; b < NB; b++) {
+      float s = 0.f;
 #pragma unroll
-    for (int q = b << QS; q < (b + 1) << QS; q++) s += x[q].x + x[q].y;
+      for (int q = b << QS; q < (b + 1) << QS; q++) s += x[q].x + x[q].y;
 #pragma unroll
-    for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    bs[b] = s;
+      for (int o = W / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      bs[b] = s;
+    }
   }
   if (NW > 1) {
-    const int w = t >> 5;
-    if ((t & 31) == 0) {
+    if (!reuse) {
+      const int w = t >> 5;
+      if ((t & 31) == 0) {
 #pragma unroll
-      for (int b = 0; b < NB; b++) red[b * NW + w] = bs[b];
+        for (int b = 0; b < NB; b++) red[b * NW + w] = bs[b];
+      }
+      group_sync<M>(g);
     }
-    group_sync<M>(g);
 #pragma unroll
     for (int b = 0; b < NB; b++) {
       float s = 0.f;
@@ -240,13 +246,13 @@ __device__ __forceinline__ void remove_block_means(float2 (&x)[kPoints], int t, 
 }
 
 template <int M>
-__device__ __forceinline__ void remove_block_means_qs(float2 (&x)[kPoints], int t, float *red, const KParams &p, int g) {
+__device__ __forceinline__ void remove_block_means_qs(float2 (&x)[kPoints], int t, float *red, const KParams &p, int g, bool reuse) {
   switch (p.qs) {
-    case 4: remove_block_means<M, 4>(x, t, red, p.inv_hop_mean, g); break;
-    case 3: remove_block_means<M, 3>(x, t, red, p.inv_hop_mean, g); break;
-    case 2: remove_block_means<M, 2>(x, t, red, p.inv_hop_mean, g); break;
-    case 1: remove_block_means<M, 1>(x, t, red, p.inv_hop_mean, g); break;
-    default: remove_block_means<M, 0>(x, t, red, p.inv_hop_mean, g); break;
+    case 4: remove_block_means<M, 4>(x, t, red, p.inv_hop_mean, g, reuse); break;
+    case 3: remove_block_means<M, 3>(x, t, red, p.inv_hop_mean, g, reuse); break;
+    case 2: remove_block_means<M, 2>(x, t, red, p.inv_hop_mean, g, reuse); break;
+    case 1: remove_block_means<M, 1>(x, t, red, p.inv_hop_mean, g, reuse); break;
+    default: remove_block_means<M, 0>(x, t, red, p.inv_hop_mean, g, reuse); break;
   }
 }
 
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 #pragma unroll
             for (int q = 0; q < kPoints; q++) x[q] = make_float2(0.f, 0.f);
           }
-          if (p.fused_mean) remove_block_means_qs<M>(x, t, red, p, g);
+          if (p.fused_mean) remove_block_means_qs<M>(x, t, red, p, g, MULTI && j > 0);
           else if (p.means != nullptr && active) remove_table_means<M>(x, t, p, f);
           if (MULTI && STAGE && ntap > 1) {
             float2 *s2 = reinterpret_cast<float2 *>(stage);
