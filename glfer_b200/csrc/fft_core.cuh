@@ -416,6 +416,18 @@ GLB_HD void load_tw_regs(TwRegs &tr, int t, const float2 *tw, const float2 *vtab
   tr.v0hi = make_tw3(vtab[khi<M>(t)]);
 }
 
+// the last pass's bases and the two split factors only (table-twiddle plans load them per
+// transform: 6 loads instead of the 14 twiddles + 8 split factors of the plain table path)
+template <int M>
+GLB_HD void load_last_regs(TwRegs &tr, int t, const float2 *tw, const float2 *vtab) {
+  constexpr int T = M / kPoints, NP = Plan<M>::NP;
+  const float2 *twA = tw + TwOffset<M, NP - 1>::value + t;
+#pragma unroll
+  for (int i = 0; i < 4; i++) tr.last[i] = make_tw3(twA[i * 2 * T]);
+  tr.v0 = make_tw3(vtab[t]);
+  tr.v0hi = make_tw3(vtab[khi<M>(t)]);
+}
+
 // v[u + r S] *= w^r for r = 1..R-1 from the kept bases; w^(4a+b) is applied as two successive
 // multiplications (w^(4a) then w^b): no derived twiddle is ever formed
 template <int R, int S>

@@ -87,7 +87,10 @@ template <int M> struct Geo {
   // per frame group: FFT buffer | [staging buffer] | reduction scratch | mbarrier
   static __host__ __device__ constexpr size_t stage_bytes(bool multi) { return (STAGE && multi) ? (size_t) N * sizeof(float) : 0; }
   static __host__ __device__ constexpr size_t group_bytes(bool multi) { return ((BUF_BYTES + stage_bytes(multi) + RED_BYTES + 16 + 15) / 16) * 16; }
-  static __host__ __device__ constexpr size_t smem_bytes(bool multi) { return (size_t) G * group_bytes(multi); }
+  // table-twiddle plans (N >= 8192) keep the twiddles of their mid passes in shared memory (one
+  // copy per CTA, a few KB: they depend on k = j mod Ns only)
+  static constexpr size_t TWS_BYTES = RT ? 0 : (size_t) TwOffset<M, (Plan<M>::NP > 1 ? Plan<M>::NP - 1 : 0)>::value * sizeof(float2);
+  static __host__ __device__ constexpr size_t smem_bytes(bool multi) { return (size_t) G * group_bytes(multi) + TWS_BYTES; }
   // CTAs per SM the register allocation is tuned for (~GLB_REG_TARGET registers per thread)
   static constexpr int MINB_ = 65536 / (THREADS * (THREADS >= 512 ? 64 : GLB_REG_TARGET));
   static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ > 16 ? 16 : MINB_);
@@ -344,6 +347,16 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 
   TwRegs tr;
   if constexpr (RT) load_tw_regs<M>(tr, t, p.tw, p.vtab);
+  // table-twiddle plans: mid-pass twiddles from shared memory (global loads of 29 twiddles per
+  // thread and transform kept the L1TEX pipe busy and the warps waiting on L2)
+  const float2 *tw_mid = p.tw;
+  if constexpr (!RT) {
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw + (size_t) G * GeoM::group_bytes(MULTI));
+    constexpr int kMid = TwOffset<M, Plan<M>::NP - 1>::value;
+    for (int i = threadIdx.x; i < kMid; i += GeoM::THREADS) tws[i] = p.tw[i];
+    __syncthreads();
+    tw_mid = tws;
+  }
 
   if (STAGE) {
     if (t == 0) {
@@ -425,7 +438,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
         tma_load_1d(stage, p.samples + ((f + 1) * (long long) p.hop - p.n_ov - p.origin), N * 4, mbar);
       }
       group_sync<M>(g);
-      MidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
+      MidPasses<M, 1, RT>::run(v, t, buf, tw_mid, tr, g);
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
       float *row = (!MULTI && active && p.rows) ? p.rows + fl * p.row_stride : nullptr;
       float2 *sp = (!MULTI && active && p.spectrum) ? p.spectrum + fl * (long long) (M + 1) : nullptr;
@@ -445,9 +458,13 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
         if (MULTI) emit_bins_rt<M>(v, t, tr, sink_multi);
         else emit_bins_rt<M>(v, t, tr, sink_single);
       } else {
-        last_pass<M>(v, t, buf, p.tw);
-        if (MULTI) emit_bins<M>(v, t, p.vtab, sink_multi);
-        else emit_bins<M>(v, t, p.vtab, sink_single);
+        // last pass and split from 6 loaded bases, the register-twiddle code path
+        TwRegs tl;
+        load_last_regs<M>(tl, t, p.tw, p.vtab);
+        last_pass_load<M>(v, t, buf);
+        last_pass_compute_rt<M>(v, t, tl);
+        if (MULTI) emit_bins_rt<M>(v, t, tl, sink_multi);
+        else emit_bins_rt<M>(v, t, tl, sink_single);
       }
       // no barrier here: (A) of the next transform orders these reads before its stores
     }
