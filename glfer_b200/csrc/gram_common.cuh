@@ -685,6 +685,14 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     for (int sl = 0; sl < slots; sl++) mbar_init(&mbar[sl], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // table-twiddle plans (one group per CTA): mid-pass twiddles in shared memory, behind the group
+  const float2 *tw_mid = p.tw;
+  if constexpr (!RT) {
+    float2 *tws = reinterpret_cast<float2 *>(smem_raw + (size_t) G * L.group_bytes);
+    constexpr int kMid = TwOffset<M, Plan<M>::NP - 1>::value;
+    for (int i = threadIdx.x; i < kMid; i += GeoM::THREADS) tws[i] = p.tw[i];
+    tw_mid = tws;
+  }
   group_sync<M>(g);
 
   // prologue: the nb blocks of the first frame (zeros before the stream start, fft.c:103-108)
@@ -778,7 +786,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       // tight ring: the frame is in registers, so past the first (A) nobody reads the ring any more
       if (!GLB_RING_EXTRA && next_there && j == 0 && t == 0) request_next();
       group_sync<M>(g);
-      RingMidPasses<M, 1, RT>::run(v, t, buf, p.tw, tr, g);
+      RingMidPasses<M, 1, RT>::run(v, t, buf, tw_mid, tr, g);
       float *row = row_ptr;
       const bool db = p.rows_db != 0;
       float yv[17];
@@ -796,13 +804,17 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
           else emit_bins_rt<M, false>(v, t, tr, sink_single);
         }
       } else {
-        last_pass<M>(v, t, buf, p.tw);
+        // table-twiddle plans: last pass and split from 6 loaded bases, the register-twiddle code path
+        TwRegs tl;
+        load_last_regs<M>(tl, t, p.tw, p.vtab);
+        last_pass_load<M>(v, t, buf);
+        last_pass_compute_rt<M>(v, t, tl);
         if (MULTI) {
-          if (w0) emit_bins<M, true>(v, t, p.vtab, sink_multi);
-          else emit_bins<M, false>(v, t, p.vtab, sink_multi);
+          if (w0) emit_bins_rt<M, true>(v, t, tl, sink_multi);
+          else emit_bins_rt<M, false>(v, t, tl, sink_multi);
         } else {
-          if (w0) emit_bins<M, true>(v, t, p.vtab, sink_single);
-          else emit_bins<M, false>(v, t, p.vtab, sink_single);
+          if (w0) emit_bins_rt<M, true>(v, t, tl, sink_single);
+          else emit_bins_rt<M, false>(v, t, tl, sink_single);
         }
       }
       if (!MULTI) {
@@ -1268,7 +1280,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
     if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && (allow & 2) != 0) {
       const int nb = kPoints >> qs;
       const RingLayout L = ring_layout<M>(kp.hop, nb);
-      size_t smem = (size_t) GeoM::G * L.group_bytes;
+      size_t smem = (size_t) GeoM::G * L.group_bytes + ((multi ? RingGeo<M, true>::RT : RingGeo<M, false>::RT) ? 0 : Geo<M>::TWS_BYTES);
       if (const char *e = getenv("GLB_SMEM_PAD_KB")) smem += (size_t) atoi(e) * 1024;     // experiments: cap the CTAs per SM
       if (smem <= 227 * 1024) {
         // 50 % and 75 % overlap have kernels with the ring geometry folded in
