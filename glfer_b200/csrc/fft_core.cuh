@@ -268,29 +268,6 @@ template <int M, int P> GLB_HD int scatter_index(int base, int r) {
   else return pad(base + r * Ns);
 }
 
-// pass_store<M,P>: twiddle (P > 0), radix-R butterflies on the 16 register points and Stockham store
-template <int M, int P>
-GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
-  constexpr int T = M / kPoints;
-  constexpr int R = PlanRadix<M, P>::R;
-  constexpr int Ns = PlanRadix<M, P>::Ns;
-  constexpr int S = kPoints / R;         // butterflies per thread, and register stride
-#pragma unroll
-  for (int u = 0; u < S; u++) {
-    const int j = t + u * T;
-    const int k = j & (Ns - 1);
-    if (P > 0) {
-      const float2 *twp = tw + TwOffset<M, P>::value + k;
-#pragma unroll
-      for (int r = 1; r < R; r++) v[u + r * S] = cmul(v[u + r * S], twp[(r - 1) * Ns]);
-    }
-    Dft<R, S>::run(v + u);
-    const int base = scatter_base<M, P>(t, u);
-#pragma unroll
-    for (int r = 0; r < R; r++) buf[scatter_index<M, P>(base, r)] = v[u + r * S];
-  }
-}
-
 template <int M>
 GLB_HD void pass_load(float2 *v, int t, const float2 *buf) {
 #pragma unroll
@@ -462,6 +439,40 @@ GLB_HD void apply_tw_bases(float2 *v, const Tw3 *b) {
     v[3 * S] = cmul(v[3 * S], b[2]);
   } else if constexpr (R == 2) {
     v[1 * S] = cmul(v[1 * S], b[0]);
+  }
+}
+
+// pass_store<M,P>: twiddle (P > 0), radix-R butterflies on the 16 register points and Stockham store
+template <int M, int P>
+GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
+  constexpr int T = M / kPoints;
+  constexpr int R = PlanRadix<M, P>::R;
+  constexpr int Ns = PlanRadix<M, P>::Ns;
+  constexpr int S = kPoints / R;         // butterflies per thread, and register stride
+#pragma unroll
+  for (int u = 0; u < S; u++) {
+    const int j = t + u * T;
+    const int k = j & (Ns - 1);
+    if constexpr (P > 0) {
+      // only the base powers are loaded (6 of 15 for radix 16, 4 of 7 for radix 8); the others are
+      // applied as two successive multiplications, as with register twiddles
+      const float2 *twp = tw + TwOffset<M, P>::value + k;
+      constexpr int NB = TwBases<R>::n;
+      Tw3 b[NB > 0 ? NB : 1];
+      if constexpr (R == 16) {
+        const int e[6] = {1, 2, 3, 4, 8, 12};
+#pragma unroll
+        for (int i = 0; i < 6; i++) b[i] = make_tw3(twp[(e[i] - 1) * Ns]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NB; i++) b[i] = make_tw3(twp[i * Ns]);
+      }
+      apply_tw_bases<R, S>(v + u, b);
+    }
+    Dft<R, S>::run(v + u);
+    const int base = scatter_base<M, P>(t, u);
+#pragma unroll
+    for (int r = 0; r < R; r++) buf[scatter_index<M, P>(base, r)] = v[u + r * S];
   }
 }
 
