@@ -486,11 +486,13 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 // ------------------------------------------------------------------------- ring kernel
 // The fast path for the regular geometry (hop = 2T << QS, N - hop a multiple of hop: 0, 50,
 // 75, 87.5, 93.75 % overlap; no RA9MB / limiter).  A frame is NB = 16 >> QS whole hop blocks.
-// Each frame group keeps the last NB + 1 blocks of its run in a shared-memory ring that is
-// filled by TMA bulk copies (cp.async.bulk + mbarrier), always one block ahead of the FFT,
-// so every sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM
-// latency hides behind the previous frame's transform.  Block means (sub_mean) are computed
-// once per block when it lands and kept beside the ring.
+// Each frame group keeps the last NB blocks of its run in a shared-memory ring that is
+// filled by TMA bulk copies (cp.async.bulk + mbarrier), always one block ahead of the FFT
+// (the oldest slot is handed to the next copy as soon as the frame is in registers), so every
+// sample crosses HBM -> SM exactly once, whatever the overlap, and the DRAM latency hides
+// behind the current frame's transform.  The mean of a block (sub_mean) is formed once, from the
+// registers of the frame in which it is the newest block (ring_fetch), and kept beside the ring
+// for the NB - 1 frames that use the block again.
 #ifndef GLB_RING_EXTRA
 #define GLB_RING_EXTRA 0  // 1: one spare slot, the next block is requested at the top of a frame;
 #endif                    // 0: NB slots, requested after barrier (A) into the oldest block's slot
