@@ -36,9 +36,11 @@ def psd_stats(got, ref):
                 median_rel=float(np.median(rel)) if rel.size else 0.0)
 
 
-def assert_psd_close(got, ref, what=""):
+def assert_psd_close(got, ref, what="", min_frac=MIN_FRAC):
+    """min_frac: with block means removed and no overlap the DC bin of every row is pure rounding
+    noise; at N = 32 that is 1 bin in 17, so callers sweeping tiny sizes lower the share."""
     assert np.isfinite(np.asarray(got)).all(), f"{what}: non-finite PSD"
     st = psd_stats(got, ref)
     assert st["ok"], f"{what}: {st}"
-    assert st["frac_1e4"] >= MIN_FRAC, f"{what}: {st}"
+    assert st["frac_1e4"] >= min_frac, f"{what}: {st}"
     return st
