@@ -55,6 +55,8 @@ WORKLOADS = {
            dict(n=16384, window_type=0, overlap=0.5, sub_mean=True), 3 * 3600),
     "c5": ("multitaper N=32768 K'=16 (mtm_k=15) NW=8 50% ovl, 1 h @ 48 kHz per GPU",
            dict(n=32768, mode=1, overlap=0.5, sub_mean=True, mtm_w=8.0, mtm_kmax=15), 3600),
+    "odd": ("periodogram N=4096 Hann 90% ovl (hop 409: irregular geometry, general kernel), 20 min @ 48 kHz",
+            dict(n=4096, window_type=0, overlap=0.9, sub_mean=True), 1200),
     "lmp": ("LMP detector (lmp.c) N=4096 rectangular 50% ovl, ring of 4 frames, 1 h @ 48 kHz",
             dict(n=4096, mode=3, overlap=0.5, sub_mean=True, lmp_av=4), 3600),
 }
