@@ -180,10 +180,17 @@ __device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KPar
   }
   const long long s0 = f * (long long) p.hop - p.n_ov;
   const long long rel = s0 - p.origin;
-  if ((s0 >= 0) && (rel >= 0) && (rel + N <= p.count) && ((rel & 1) == 0)) {
-    const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
+  if ((s0 >= 0) && (rel >= 0) && (rel + N <= p.count)) {
+    if ((rel & 1) == 0) {
+      const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
 #pragma unroll
-    for (int q = 0; q < kPoints; q++) x[q] = ldg2(src + t + T * q);
+      for (int q = 0; q < kPoints; q++) x[q] = ldg2(src + t + T * q);
+    } else {
+      // interior frame at an odd offset (odd hops): pairs straddle the 8-byte alignment
+      const float *src = p.samples + rel + 2 * t;
+#pragma unroll
+      for (int q = 0; q < kPoints; q++) x[q] = make_float2(__ldg(src + 2 * T * q), __ldg(src + 2 * T * q + 1));
+    }
     return;
   }
 #pragma unroll
