@@ -407,6 +407,38 @@ def test_per_call_lmp_equals_batch(gpu_api):
     assert_lmp_close(rows, batch, "per-call LMP vs batch")
 
 
+def test_peak_carry_scan(gpu_api):
+    """glb_launch_peak_carry (the carried *peakbin of avg.c:129-133) straight through the shim:
+    random candidates, long runs of "not written" (-1) across chunk and tile borders, lengths that
+    are not multiples of a tile, nothing written at all."""
+    lib = gpu_api.lib()
+    lib.glb_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.glb_free.argtypes = [C.c_void_p]
+    lib.glb_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.glb_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.glb_launch_peak_carry.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(11)
+    for n, p_valid in ((1, 1.0), (255, 0.5), (257, 0.01), (100003, 0.3), (100003, 0.0005), (300000, 0.0), (168750, 0.9)):
+        cand = np.where(rng.random(n) < p_valid, rng.integers(0, 2049, n), -1).astype(np.int32)
+        if n > 5000:
+            cand[1000:4000] = -1                     # a run longer than several tiles
+        ref = np.empty(n, np.int32)
+        carry = 77
+        for i in range(n):
+            if cand[i] >= 0:
+                carry = cand[i]
+            ref[i] = carry
+        d_c, d_o = C.c_void_p(), C.c_void_p()
+        assert lib.glb_malloc(C.byref(d_c), cand.nbytes) == 0 and lib.glb_malloc(C.byref(d_o), cand.nbytes) == 0
+        assert lib.glb_memcpy_h2d(d_c, cand.ctypes.data, cand.nbytes, None) == 0
+        assert lib.glb_launch_peak_carry(d_c, d_o, n, 77, None) == 0
+        got = np.empty(n, np.int32)
+        assert lib.glb_memcpy_d2h(got.ctypes.data, d_o, got.nbytes, None) == 0
+        lib.glb_free(d_c)
+        lib.glb_free(d_o)
+        assert np.array_equal(got, ref), (n, p_valid)
+
+
 def test_compute_floor(gpu_api):
     lib = gpu_api.lib()
     x = stream(20000, seed=37)
