@@ -29,7 +29,7 @@ class GramConfig(C.Structure):
                 ("a", C.c_float), ("limiter", C.c_int), ("sub_mean", C.c_int), ("mtm_w", C.c_float),
                 ("mtm_kmax", C.c_int), ("avg_mode", C.c_int), ("avg_depth", C.c_int), ("avg_minbin", C.c_int),
                 ("avg_maxbin", C.c_int), ("avg_max0", C.c_int), ("avg_peakbin_init", C.c_int),
-                ("scale_db", C.c_int), ("device", C.c_int), ("lmp_av", C.c_int)]
+                ("scale_db", C.c_int), ("device", C.c_int), ("lmp_av", C.c_int), ("zero_history", C.c_int)]
 
 
 class FftParams(C.Structure):          # include/fft.h (reference fft.h:51-63)
@@ -178,37 +178,40 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def pinned_empty(shape, dtype) -> np.ndarray:
-    """numpy array over pinned host memory from glfer_b200_host_alloc (kept alive by the array)."""
-    dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = lib().glfer_b200_host_alloc(max(n, 1))
-    if not p:
-        raise GlferError("pinned allocation failed: " + last_error())
-    buf = (C.c_char * max(n, 1)).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+class _PinnedBuffer:
+    """Owner of one glfer_b200_host_alloc block; numpy views keep it alive through their base."""
 
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
+    def __init__(self, nbytes: int):
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = lib().glfer_b200_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise GlferError("pinned allocation failed: " + last_error())
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
-        def __del__(self):
-            try:
+    def __del__(self):
+        try:
+            if self.ptr:
                 lib().glfer_b200_host_free(self.ptr)
-            except Exception:
-                pass
-    _PINNED[id(buf)] = (_Owner(p), buf)
-    return arr
+                self.ptr = None
+        except Exception:
+            pass
 
 
-_PINNED: dict = {}
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over pinned host memory from glfer_b200_host_alloc; the memory is freed when the
+    last view of the array is collected (the owner object is the base of every view)."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    owner = _PinnedBuffer(count * dtype.itemsize)
+    raw = np.asarray(owner)                       # base -> owner
+    return raw[:count * dtype.itemsize].view(dtype).reshape(shape)
 
 
 def make_config(n=1024, window_type=KAISER, overlap=0.0, mode=MODE_FFT, sub_mean=True, a=0.0, limiter=0,
                 mtm_w=4.0, mtm_kmax=7, avg_mode=NO_AVG, avg_depth=4, avg_minbin=0, avg_maxbin=0, avg_max0=0,
-                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4) -> GramConfig:
+                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4, zero_history=False) -> GramConfig:
     return GramConfig(mode, n, window_type, overlap, a, limiter, int(sub_mean), mtm_w, mtm_kmax, avg_mode, avg_depth,
-                      avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device, lmp_av)
+                      avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device, lmp_av, int(zero_history))
 
 
 class GramPlan:

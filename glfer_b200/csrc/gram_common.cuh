@@ -53,6 +53,7 @@ struct KParams {
   float inv_hop;
   float ra9mb_a;
   int limiter;
+  int zero_hist;              // 1: the n_ov history samples of every frame are zero (general kernel only)
   float lim_scale;            // taper_scale^0.9
   float spec_scale;           // 1 / (2 taper_scale)
   long long first_frame, nframes;
@@ -164,7 +165,7 @@ __device__ __forceinline__ float2 ld_taper(const float2 *p) {
 __device__ __forceinline__ bool frame_bulk_ok(const KParams &p, long long f, int n) {
   const long long s0 = f * (long long) p.hop - p.n_ov;
   const long long rel = s0 - p.origin;
-  return (s0 >= 0) && (rel >= 0) && (rel + n <= p.count) && ((rel & 3) == 0);
+  return (s0 >= 0) && (rel >= 0) && (rel + n <= p.count) && ((rel & 3) == 0) && !p.zero_hist;
 }
 
 // Raw samples of one frame: x[q] = (y[2m], y[2m+1]), m = t + T q; zeros before the stream.
@@ -180,7 +181,7 @@ __device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KPar
   }
   const long long s0 = f * (long long) p.hop - p.n_ov;
   const long long rel = s0 - p.origin;
-  if ((s0 >= 0) && (rel >= 0) && (rel + N <= p.count)) {
+  if ((s0 >= 0) && (rel >= 0) && (rel + N <= p.count) && !p.zero_hist) {
     if ((rel & 1) == 0) {
       const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel);
 #pragma unroll
@@ -198,9 +199,10 @@ __device__ __forceinline__ void load_raw(float2 (&x)[kPoints], int t, const KPar
     float y[2];
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      const long long s = s0 + 2 * (t + T * q) + e;
+      const int i = 2 * (t + T * q) + e;
+      const long long s = s0 + i;
       const long long r = s - p.origin;
-      y[e] = (s >= 0 && r >= 0 && r < p.count) ? __ldg(p.samples + r) : 0.f;
+      y[e] = (s >= 0 && r >= 0 && r < p.count && !(p.zero_hist && i < p.n_ov)) ? __ldg(p.samples + r) : 0.f;
     }
     x[q] = make_float2(y[0], y[1]);
   }
@@ -277,8 +279,9 @@ __device__ __forceinline__ void remove_table_means(float2 (&x)[kPoints], int t, 
 #pragma unroll
   for (int q = 0; q < kPoints; q++) {
     const int i = 2 * (t + T * q);
-    if (s0 + i >= 0) x[q].x -= __ldg(mu + (int) (((float) i + off) * p.inv_hop));
-    if (s0 + i + 1 >= 0) x[q].y -= __ldg(mu + (int) (((float) (i + 1) + off) * p.inv_hop));
+    const int h0 = p.zero_hist ? p.n_ov : 0;          // zeroed history keeps its zeros
+    if (s0 + i >= 0 && i >= h0) x[q].x -= __ldg(mu + (int) (((float) i + off) * p.inv_hop));
+    if (s0 + i + 1 >= 0 && i + 1 >= h0) x[q].y -= __ldg(mu + (int) (((float) (i + 1) + off) * p.inv_hop));
   }
 }
 
@@ -1251,8 +1254,13 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
     int qs = -1;
     for (int s2 = 0; s2 <= 4; s2++)
       if (kp.hop == (unit << s2)) qs = s2;
+    // the fast paths read whole hop blocks without bounds checks: the staged span must cover every
+    // block of the launch that lies inside the stream (blocks before sample 0 are the zero history)
+    const long long blk_lo = (kp.first_frame - kp.n_ov / kp.hop) * (long long) kp.hop;
+    const long long blk_hi = (kp.first_frame + kp.nframes) * (long long) kp.hop;
+    const bool covered = kp.origin <= (blk_lo > 0 ? blk_lo : 0) && blk_hi <= kp.origin + kp.count;
     const bool regular = qs >= 0 && (kp.n_ov % kp.hop) == 0 && (kp.hop % 4) == 0 && (kp.origin % 4) == 0 &&
-                         ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0);
+                         ((reinterpret_cast<uintptr_t>(kp.samples) & 15) == 0) && covered;
     if constexpr (GeoM::RT && M >= 256) {
       // 50 % / 75 % overlap periodograms: two frames per thread (selectable family: measured
       // 0.431 ms vs 0.422 ms for the ring kernel on the metric workload, 3 CTAs/SM vs 6)

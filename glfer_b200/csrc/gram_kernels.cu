@@ -189,6 +189,7 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   k.inv_hop_mean = (float) (1.0 / (double) a->hop);
   k.ra9mb_a = a->ra9mb_a;
   k.limiter = a->limiter;
+  k.zero_hist = a->zero_history;
   k.lim_scale = (float) pow((double) a->taper_scale, 0.9);
   k.spec_scale = (float) (1.0 / (2.0 * (double) a->taper_scale));
   k.first_frame = a->first_frame;
@@ -215,7 +216,7 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   // N = 4096, 0.726 ms vs 0.746 ms for warp-per-frame, whose 67 KB of straight-line code per
   // frame stalls on instruction fetch; warp-per-frame stays selectable for experiments)
   int allow = 3;                                  // 1 general, 2 ring, 4 warp-per-frame, 8 pair
-  if (g_force_generic || g_kernel_pref == 1) allow = 1;
+  if (g_force_generic || g_kernel_pref == 1 || a->zero_history) allow = 1;     // zeroed history: general kernel only
   else if (g_kernel_pref == 3) allow = 7;
   else if (g_kernel_pref == 4) allow = 11;
   const int m = a->n / 2;
@@ -776,29 +777,26 @@ __global__ void __launch_bounds__(512) floor_stats_kernel(const float *__restric
       __syncthreads();
     }
   }
-  // tail sum (lowest 5 %): partial sums, then one thread adds the partials
+  // tail sum (lowest 5 %): `for (i = N2 * 0.95; i < N2; i++) floor_pwr += tmp_buf[i]` is a float
+  // accumulation in index order (fft.c:271-272); one thread repeats it so the sum rounds the same
   const int start = (int) (nbins * 0.95);
-  float part = 0.f;
-  for (int i = start + tid; i < nbins; i += 512) part += srt[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    part += __shfl_xor_sync(0xffffffffu, part, o);
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
     if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
   }
-  __shared__ float red_s[16];
-  if ((tid & 31) == 0) { red_s[tid >> 5] = part; red_v[tid >> 5] = best; red_i[tid >> 5] = best_i; }
+  if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = best_i; }
   __syncthreads();
   if (tid == 0) {
     float fsum = 0.f, pv = 0.f;
     int pi = 0x7fffffff;
+    for (int i = start; i < nbins; i++) fsum += srt[i];
     for (int w = 0; w < 16; w++) {
-      fsum += red_s[w];
       if (red_v[w] > pv || (red_v[w] == pv && red_i[w] < pi)) { pv = red_v[w]; pi = red_i[w]; }
     }
-    float fl = fsum / 0.05f;
-    fl = fl / (float) nbins;
+    float fl = (float) ((double) fsum / 0.05);          // `floor_pwr /= 0.05`: double division, stored to float
+    fl = fl / (float) nbins;                             // `floor_pwr /= N2`
     float *o = stats + (long long) blockIdx.x * 4;
     o[0] = srt[0];
     o[1] = fl;

@@ -354,6 +354,7 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
      inbuf_fft from inbuf_audio (mtm.c:190-192) */
   g.ra9mb_a = (c->mode == GLFER_MODE_FFT) ? c->a : 0.0f;
   g.limiter = (c->mode == GLFER_MODE_FFT) ? c->limiter : 0;
+  g.zero_history = c->zero_history;
   g.taper_scale = p->taper_scale;
   g.first_frame = f0;
   g.nframes = nf;
@@ -785,6 +786,7 @@ int glfer_gram_run_sharded(const glfer_gram_config *cfg, int ndev, const int *de
   const long long nframes = nsamples / hop;
   shard_job jobs[64];
   pthread_t th[64];
+  int started[64];
   for (int g = 0; g < ndev; g++) {
     shard_job *j = &jobs[g];
     memset(j, 0, sizeof *j);
@@ -797,11 +799,15 @@ int glfer_gram_run_sharded(const glfer_gram_config *cfg, int ndev, const int *de
     j->psd_rows = psd_rows; j->avg_rows = avg_rows; j->avg_ret = avg_ret;
     j->avg_peakbin = avg_peakbin; j->avg_variance = avg_variance;
     j->bins = cfg->n / 2 + 1;
-    pthread_create(&th[g], NULL, shard_main, j);
+    started[g] = pthread_create(&th[g], NULL, shard_main, j) == 0;
+    if (!started[g]) {
+      j->rc = GLFER_ENOMEM;
+      snprintf(j->msg, sizeof j->msg, "pthread_create failed");
+    }
   }
   int rc = 0;
   for (int g = 0; g < ndev; g++) {
-    pthread_join(th[g], NULL);
+    if (started[g]) pthread_join(th[g], NULL);
     if (jobs[g].rc != 0 && rc == 0) {
       rc = jobs[g].rc;
       snprintf(g_msg, sizeof g_msg, "shard %d: %s", g, jobs[g].msg);
@@ -811,10 +817,24 @@ int glfer_gram_run_sharded(const glfer_gram_config *cfg, int ndev, const int *de
      shards g > 0 ran with the sentinel -1 as their initial value, so leading frames that
      never wrote *peakbin are recognisable and inherit the previous shard's last value */
   if (rc == 0 && avg_peakbin && cfg->avg_mode != GLFER_NO_AVG) {
-    for (int g = 1; g < ndev; g++) {
+    for (int g = 1; g < ndev && rc == 0; g++) {
       const long long f0 = jobs[g].first, f1 = f0 + jobs[g].count;
-      for (long long f = f0; f < f1 && avg_peakbin[f] < 0; f++)
-        avg_peakbin[f] = (f > 0) ? avg_peakbin[f - 1] : cfg->avg_peakbin_init;
+      long long k = 0;
+      while (f0 + k < f1 && avg_peakbin[f0 + k] < 0) k++;
+      if (k == 0) continue;
+      const int carried = (f0 > 0) ? avg_peakbin[f0 - 1] : cfg->avg_peakbin_init;
+      for (long long f = f0; f < f0 + k; f++) avg_peakbin[f] = carried;
+      /* SUMAVG: the variance of those frames excluded the sentinel instead of the carried bin
+         (avg.c:279): recompute them with the true value */
+      if (cfg->avg_mode == GLFER_AVG_SUMAVG && avg_variance) {
+        glfer_gram_config c2 = *cfg;
+        c2.device = devices ? devices[g] : g;
+        c2.avg_peakbin_init = carried;
+        glfer_gram_plan *p2 = NULL;
+        rc = glfer_gram_plan_create(&c2, &p2);
+        if (rc == 0) rc = glfer_gram_run(p2, samples, 0, nsamples, f0, k, NULL, NULL, NULL, NULL, avg_variance + f0);
+        glfer_gram_plan_destroy(p2);
+      }
     }
   }
   return rc;

@@ -68,6 +68,7 @@ typedef struct {
   int fused_mean;              /* 1: block means computed inside the kernel (needs glb_gram_fused_mean_ok) */
   float ra9mb_a;               /* > 0: x / (a + x^2) before the taper (fft.c:127-136) */
   int limiter;                 /* 1: sign(v) |v|^0.1 after the taper (fft.c:151-156) */
+  int zero_history;            /* 1: the first n - hop samples of every frame read as 0 (first_buffer stuck TRUE) */
   float taper_scale;           /* the scale folded into tapers (needed by limiter / spectrum output) */
   long long first_frame;
   long long nframes;

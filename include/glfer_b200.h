@@ -61,6 +61,10 @@ typedef struct {
   int lmp_av;          /* opt.lmp_av: rows in the LMP ring (>= 2); the "psd" rows of an LMP plan are the
                           statistic of lmp_do; window forced rectangular (source.c:395), RA9MB / limiter
                           do not reach the spectrum (lmp.c:112-114); no frame averaging in this mode */
+  int zero_history;    /* 1: glfer.first_buffer stays TRUE, i.e. prepare_audio zeroes the N-hop history on EVERY
+                          frame (fft.c:99-108).  That is what the reference GUI does with opt.autoscale == 0:
+                          first_buffer is cleared only inside `if (opt.autoscale)` (g_main.c:1111-1120).
+                          0 (default): TRUE on block 0 only, the sequence a sane caller drives */
 } glfer_gram_config;
 
 typedef struct glfer_gram_plan glfer_gram_plan;

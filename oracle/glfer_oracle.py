@@ -47,6 +47,11 @@ def _seq_sum_f32(x: np.ndarray, axis: int = -1) -> np.ndarray:
     return np.take(np.cumsum(x, axis=axis, dtype=np.float32), -1, axis=axis)
 
 
+def _seq_sum_f64(x: np.ndarray) -> float:
+    """Sequential double accumulation (`double acc; acc += x[i]`)."""
+    return float(np.cumsum(np.asarray(x, dtype=np.float64))[-1]) if len(x) else 0.0
+
+
 def bessel_i0(x: np.ndarray) -> np.ndarray:
     """util.c:222-237: polynomial approximations of I0 (Abramowitz & Stegun 9.8.1 / 9.8.2)."""
     x = np.asarray(x, dtype=np.float64)
@@ -118,7 +123,7 @@ def block_means(samples: np.ndarray, hop: int) -> np.ndarray:
 
 
 def gather_frames(samples: np.ndarray, n: int, overlap: float, sub_mean: bool,
-                  first_frame: int = 0, nframes: int | None = None) -> np.ndarray:
+                  first_frame: int = 0, nframes: int | None = None, zero_history: bool = False) -> np.ndarray:
     """inbuf_audio for frames [first_frame, first_frame+nframes), fft.c:98-113: frame f
     holds stream samples [f*hop - n_ov, f*hop + hop); the history is zero before the
     first block (glfer.first_buffer, fft.c:103-108).  Returns float32 [nframes][n]."""
@@ -135,7 +140,12 @@ def gather_frames(samples: np.ndarray, n: int, overlap: float, sub_mean: bool,
     # by n_ov samples, *also when n_ov > hop* (older history shifts through, fft.c:100-102).
     xp = np.concatenate([np.zeros(n_ov, dtype=np.float32), x])
     idx = (np.arange(first_frame, first_frame + nframes)[:, None] * hop) + np.arange(n)[None, :]
-    return xp[idx]
+    frames = xp[idx]
+    if zero_history:
+        # glfer.first_buffer never cleared (the GUI with opt.autoscale == 0, g_main.c:1111-1120):
+        # fft.c:103-108 zeroes the first n_ov samples of inbuf_audio on every block
+        frames[:, :n_ov] = 0.0
+    return frames
 
 
 def _preops(frames: np.ndarray, window: np.ndarray, window_type: int, a: float, limiter: int) -> np.ndarray:
@@ -173,11 +183,11 @@ def psd_from_spectrum(spec: np.ndarray, n: int) -> np.ndarray:
 
 def periodogram(samples: np.ndarray, n: int, window_type: int, overlap: float, sub_mean: bool = False,
                 a: float = 0.0, limiter: int = 0, first_frame: int = 0, nframes: int | None = None,
-                return_spectrum: bool = False):
+                return_spectrum: bool = False, zero_history: bool = False):
     """fft_do + fft_psd per hop block (source.c:143-144 -> fft.c:190-217).
     Returns float32 rows [nframes][n/2+1] (bin i <-> i*fs/N, DC first)."""
     window = compute_window(n, window_type)
-    frames = gather_frames(samples, n, overlap, sub_mean, first_frame, nframes)
+    frames = gather_frames(samples, n, overlap, sub_mean, first_frame, nframes, zero_history)
     v = _preops(frames, window, window_type, a, limiter)
     spec = np.fft.rfft(v, axis=1)          # forward e^{-2 pi i jk/N}, un-normalised (fft.c:196)
     rows = psd_from_spectrum(spec, n)
@@ -299,6 +309,47 @@ def multitaper(samples: np.ndarray, n: int, overlap: float, w: float, kmax: int,
 
 
 # ------------------------------------------------------------------------- averaging
+def multitaper_ftest(samples: np.ndarray, n: int, overlap: float, w: float, kmax: int, sub_mean: bool = False,
+                     first_frame: int = 0, nframes: int | None = None, tapers=None, lam=None) -> np.ndarray:
+    """Thomson's harmonic F-test as mtm_do computes it into its file-static `ftest` (double /
+    FFTW-layout build; in the float build `mu` is never written).
+      U0[j] = sum_i v[i][j]                                   mtm.c:78-84 (double)
+      sum_U0_sqr = sum_j U0[j]^2                              mtm.c:125-128 (float accumulator)
+      hn[i] = sum_j U0[j] v[i][j] / sum_U0_sqr                mtm.c:130-136 (float accumulator)
+      mu = FFT(inbuf_audio * hn)                              mtm.c:165-171
+      den[i] = sum_j |y_j[i] - mu[i] U0[j]|^2                 mtm.c:204-210 (float accumulator `ftest[i] +=`)
+      ftest[i] = kmax |mu[i]|^2 sum_U0_sqr / den[i]           mtm.c:222-233 (note: kmax = K' - 1)
+    DC uses the real part only (:205-206, :223-224); for even n the Nyquist denominator is never
+    accumulated (the loops stop at (n+1)/2), so ftest[n/2] = num / 0 = inf (nan when num is 0)."""
+    if tapers is None:
+        tapers, lam = gl_dpss(n, w, kmax)
+    frames = gather_frames(samples, n, overlap, sub_mean, first_frame, nframes).astype(np.float64)
+    u0 = np.array([_seq_sum_f64(tapers[j]) for j in range(kmax + 1)])
+    s2 = np.float32(0.0)
+    for j in range(kmax + 1):
+        s2 = np.float32(np.float64(s2) + u0[j] * u0[j])
+    hn = np.zeros(n, dtype=np.float32)
+    for j in range(kmax + 1):
+        hn = (hn.astype(np.float64) + u0[j] * tapers[j]).astype(np.float32)
+    hn = (hn / s2).astype(np.float32)
+    mu = np.fft.rfft(frames * hn.astype(np.float64)[None, :], axis=1)
+    half = (n + 1) // 2
+    den = np.zeros((frames.shape[0], n // 2 + 1), dtype=np.float32)
+    for j in range(kmax + 1):
+        y = np.fft.rfft(frames * tapers[j][None, :], axis=1)
+        d = y - mu * u0[j]
+        t = d.real * d.real + d.imag * d.imag
+        t[:, 0] = d[:, 0].real * d[:, 0].real
+        den[:, :half] = (den[:, :half].astype(np.float64) + t[:, :half]).astype(np.float32)
+    m2 = mu.real * mu.real + mu.imag * mu.imag
+    m2[:, 0] = mu[:, 0].real * mu[:, 0].real
+    if n % 2 == 0:
+        m2[:, n // 2] = 2.0 * mu[:, n // 2].real * mu[:, n // 2].real     # mu[i]^2 + mu[n-i]^2 with i = n/2
+    num = kmax * m2 * np.float64(s2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (num / den.astype(np.float64)).astype(np.float32)
+
+
 def avg_bins(sample_rate: int, n: int, min_band_hz: float, max_band_hz: float):
     """g_main.c:1144-1146: binsize is a float quotient, bins are truncated float quotients."""
     binsize = np.float32(sample_rate) / np.float32(n)

@@ -33,6 +33,11 @@
 opt_t opt;
 glfer_t glfer;
 
+/* 1: glfer.first_buffer stays TRUE for the whole run -- what the GUI does with opt.autoscale == 0,
+ * where main_window_draw never clears it (g_main.c:1111-1120): every frame gets a zeroed history */
+static int g_sticky_first_buffer = 0;
+void refh_set_sticky_first_buffer(int on) { g_sticky_first_buffer = on; }
+
 static double now_s(void)
 {
   struct timespec ts;
@@ -105,7 +110,7 @@ long refh_periodogram(const float *samples, long nsamples, int n, int window_typ
     fft_psd(rows ? rows + f * bins : psd, phase ? phase + f * bins : NULL, &p);
     if (spec)
       for (int i = 0; i < n; i++) spec[f * n + i] = p.outbuf[i];
-    glfer.first_buffer = FALSE;
+    if (!g_sticky_first_buffer) glfer.first_buffer = FALSE;
   }
   free(blk);
   free(psd);
@@ -161,10 +166,43 @@ long refh_mtm(const float *samples, long nsamples, int n, float overlap, int sub
   for (long f = 0; f < nframes; f++) {
     memcpy(blk, samples + f * hop, sizeof(float) * hop);
     mtm_do(blk, rows ? rows + f * bins : psd, NULL, &p);
-    glfer.first_buffer = FALSE;
+    if (!g_sticky_first_buffer) glfer.first_buffer = FALSE;
   }
   free(blk);
   free(psd);
+  mtm_close(&p);
+  return nframes;
+}
+
+/* The same loop, also copying out the harmonic F-test mtm_do leaves in its file-static buffer
+ * after every block (mtm.c:222-233; ref_mtm_unit.c hands the static out).  Meaningful in the
+ * double (FFTW-layout) build only.  ftest: [nframes][n/2+1]. */
+extern const float *refh_mtm_ftest_buffer(void);
+long refh_mtm_ftest(const float *samples, long nsamples, int n, float overlap, int sub_mean,
+                    float w, int kmax, long max_frames, float *rows, float *ftest_rows)
+{
+  mtm_params_t p;
+  memset(&p, 0, sizeof p);
+  p.fft.n = n;
+  p.fft.window_type = RECTANGULAR_WINDOW;
+  p.fft.overlap = overlap;
+  p.w = w;
+  p.kmax = kmax;
+  opt.autoscale = sub_mean;
+  mtm_init(&p);
+  int hop = refh_hop(n, overlap);
+  int bins = n / 2 + 1;
+  long nframes = hop > 0 ? nsamples / hop : 0;
+  if (nframes > max_frames) nframes = max_frames;
+  float *blk = malloc(sizeof(float) * (hop > 0 ? hop : 1));
+  glfer.first_buffer = TRUE;
+  for (long f = 0; f < nframes; f++) {
+    memcpy(blk, samples + f * hop, sizeof(float) * hop);
+    mtm_do(blk, rows + f * bins, NULL, &p);
+    memcpy(ftest_rows + f * bins, refh_mtm_ftest_buffer(), sizeof(float) * bins);
+    if (!g_sticky_first_buffer) glfer.first_buffer = FALSE;
+  }
+  free(blk);
   mtm_close(&p);
   return nframes;
 }
@@ -196,7 +234,7 @@ long refh_lmp(const float *samples, long nsamples, int n, float overlap, int sub
   for (long f = 0; f < nframes; f++) {
     memcpy(blk, samples + f * hop, sizeof(float) * hop);
     lmp_do(blk, rows ? rows + f * bins : psd, NULL, &p);
-    glfer.first_buffer = FALSE;
+    if (!g_sticky_first_buffer) glfer.first_buffer = FALSE;
   }
   for (long f = nframes; f % nl != 0; f++) {            /* realign the static ring index */
     memset(blk, 0, sizeof(float) * hop);
@@ -285,7 +323,7 @@ double refh_time_periodogram(const float *samples, long nsamples, int n, int win
     fft_do(blk, &p);
     fft_psd(psd, NULL, &p);
     acc += psd[(f * 7) % bins];
-    glfer.first_buffer = FALSE;
+    if (!g_sticky_first_buffer) glfer.first_buffer = FALSE;
   }
   double t1 = now_s();
   free(blk);
@@ -320,7 +358,7 @@ double refh_time_mtm(const float *samples, long nsamples, int n, float overlap, 
     memcpy(blk, samples + f * hop, sizeof(float) * hop);
     mtm_do(blk, psd, NULL, &p);
     acc += psd[(f * 7) % bins];
-    glfer.first_buffer = FALSE;
+    if (!g_sticky_first_buffer) glfer.first_buffer = FALSE;
   }
   double t1 = now_s();
   free(blk);

@@ -38,6 +38,8 @@ def lib(kind: str = "f64") -> C.CDLL:
         l.refh_mtm.argtypes = [_fp, C.c_long, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int,
                                C.c_long, _fp]
         l.refh_mtm.restype = C.c_long
+        l.refh_mtm_ftest.argtypes = [_fp, C.c_long, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_long, _fp, _fp]
+        l.refh_mtm_ftest.restype = C.c_long
         l.refh_lmp.argtypes = [_fp, C.c_long, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_long, _fp]
         l.refh_lmp.restype = C.c_long
         l.refh_avg.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_long, C.c_long, C.c_int,
@@ -50,6 +52,8 @@ def lib(kind: str = "f64") -> C.CDLL:
         l.refh_time_mtm.argtypes = [_fp, C.c_long, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int,
                                     C.POINTER(C.c_long), C.POINTER(C.c_double)]
         l.refh_time_mtm.restype = C.c_double
+        l.refh_set_sticky_first_buffer.argtypes = [C.c_int]
+        l.refh_set_sticky_first_buffer.restype = None
         _LIBS[kind] = l
     return _LIBS[kind]
 
@@ -65,16 +69,21 @@ def window(n: int, wtype: int, kind="f64") -> np.ndarray:
 
 
 def periodogram(samples, n, wtype, overlap, sub_mean=False, a=0.0, limiter=0, max_frames=1 << 40, kind="f64",
-                want_spec=False, want_phase=False):
+                want_spec=False, want_phase=False, sticky_first_buffer=False):
+    """sticky_first_buffer: glfer.first_buffer is never cleared (GUI with opt.autoscale == 0)."""
     samples = np.ascontiguousarray(samples, dtype=np.float32)
     h = hop(n, overlap, kind)
     nf = min(len(samples) // h, max_frames)
     rows = np.empty((nf, n // 2 + 1), dtype=np.float32)
     spec = np.empty((nf, n), dtype=np.float64) if want_spec else None
     phase = np.empty((nf, n // 2 + 1), dtype=np.float32) if want_phase else None
-    got = lib(kind).refh_periodogram(samples, len(samples), n, wtype, overlap, int(sub_mean), a, limiter, nf,
-                                     rows.ctypes.data, spec.ctypes.data if want_spec else None,
-                                     phase.ctypes.data if want_phase else None)
+    lib(kind).refh_set_sticky_first_buffer(int(sticky_first_buffer))
+    try:
+        got = lib(kind).refh_periodogram(samples, len(samples), n, wtype, overlap, int(sub_mean), a, limiter, nf,
+                                         rows.ctypes.data, spec.ctypes.data if want_spec else None,
+                                         phase.ctypes.data if want_phase else None)
+    finally:
+        lib(kind).refh_set_sticky_first_buffer(0)
     assert got == nf
     res = [rows]
     if want_spec:
@@ -99,6 +108,18 @@ def mtm(samples, n, overlap, w, kmax, sub_mean=False, a=0.0, limiter=0, max_fram
     got = lib(kind).refh_mtm(samples, len(samples), n, overlap, int(sub_mean), a, limiter, w, kmax, nf, rows)
     assert got == nf
     return rows
+
+
+def mtm_ftest(samples, n, overlap, w, kmax, sub_mean=False, max_frames=1 << 40, kind="f64"):
+    """mtm_do rows plus the harmonic F-test it leaves in its file-static buffer (double build)."""
+    samples = np.ascontiguousarray(samples, dtype=np.float32)
+    h = hop(n, overlap, kind)
+    nf = min(len(samples) // h, max_frames)
+    rows = np.empty((nf, n // 2 + 1), dtype=np.float32)
+    ft = np.empty((nf, n // 2 + 1), dtype=np.float32)
+    got = lib(kind).refh_mtm_ftest(samples, len(samples), n, overlap, int(sub_mean), w, kmax, nf, rows, ft)
+    assert got == nf
+    return rows, ft
 
 
 def lmp(samples, n, overlap, nl, sub_mean=False, a=0.0, limiter=0, max_frames=1 << 40, kind="f64"):

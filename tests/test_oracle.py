@@ -51,6 +51,25 @@ def test_sine_known_answers():
     assert np.array_equal(h, GOLD["kat_sine_hann"]) and np.array_equal(r, GOLD["kat_sine_rect"])
 
 
+def test_round2_fixtures():
+    """zeroed history on every frame (GUI, autoscale off), C4 shape, C5 at both NW, the F-test"""
+    g2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "glfer_ref_f64_r2.npz"))
+    x48 = synth.pcm16_to_float(g2["pcm48"])
+    assert np.array_equal(O.periodogram(X[:20000], 1024, 0, 0.75, False, zero_history=True), g2["zero_hist_rows"])
+    assert np.array_equal(O.periodogram(X[:12000], 512, 7, 0.9, False, zero_history=True), g2["zero_hist_rows_odd"])
+    assert np.array_equal(O.periodogram(x48, 16384, 0, 0.5, True), g2["c4_rows"])
+    p = O.multitaper(X, 4096, 0.5, 4.0, 7, True)
+    assert (np.abs(p - g2["c3_rows_4096"]) / g2["c3_rows_4096"]).max() < 1e-6
+    p = O.multitaper(x48[:3 * 16384], 32768, 0.5, 8.0, 15, True)
+    assert (np.abs(p - g2["c5_rows_nw8"][:3]) / g2["c5_rows_nw8"][:3]).max() < 1e-5
+    # F-test with the fixture's own tapers: bit exact, including the inf at Nyquist (mtm.c:229-233)
+    ft = O.multitaper_ftest(X, 1024, 0.5, 4.0, 7, True, tapers=GOLD["c3_tapers"].astype(np.float64), lam=GOLD["c3_lambda"])
+    ref = g2["c3_ftest_1024"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(ft), fin) and not fin[:, -1].any() and fin[:, :-1].all()
+    assert np.allclose(ft[fin], ref[fin], rtol=2e-4)          # float32 copy of the tapers in the fixture
+
+
 def test_hop_truncation():
     assert O.hop_size(4096, 0.9) == 409            # float overlap, double product, truncated
     assert O.hop_size(1024, 0.5) == 512 and O.hop_size(4096, 0.75) == 1024 and O.hop_size(1024, 0.0) == 1024
