@@ -434,8 +434,10 @@ def compute_floor(psd: np.ndarray):
 def display_levels(psd_rows: np.ndarray, shown_rows: np.ndarray, overlap: float, log_scale: bool, autoscale: bool,
                    max_level_db: float = -20.0, min_level_db: float = -80.0, thr_level: float = 0.0,
                    first_frame: int = 0, agc_state=(0.0, 0.0)):
-    """main_window_draw, g_main.c:1109-1229, without the GTK drawing.  PARITY UNPINNED: g_main.c
-    needs GTK and cannot be built here, so this restatement has no reference run behind it.
+    """main_window_draw, g_main.c:1109-1229, without the GTK drawing.  PINNED (round 2): bit-identical
+    to the reference's own main_window_draw -- g_main.c compiled unmodified with GTK stubbed out,
+    oracle/ref_gui_unit.c -- in every scale / autoscale / threshold / averaging variant
+    (tests/test_oracle.py::test_display_mapping_pinned, fixtures disp_* of glfer_ref_f64_r2.npz).
     Per frame: compute_floor on the PSD row (:1109); AGC with float state and double
     arithmetic (:1111-1124) or fixed levels (:1126-1128); dB range (:1132-1135); per pixel i:
     bin n-1-i, level through the `short` level buffer in the log scales (:68,1193-1195),

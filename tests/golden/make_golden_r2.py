@@ -16,6 +16,24 @@ from glfer_b200 import synth            # noqa: E402
 from oracle import ref_lib as R         # noqa: E402
 
 
+# keyword arguments of oracle.ref_gui.draw_rows (scale_type: glfer.h:43 SCALE_LIN, _LIN_MAX0, _LOG, _LOG_MAX0;
+# averaging: glfer.h:55); the tests rebuild the same cases through the product and the restatement
+DISPLAY_CASES = {
+    "log_auto": dict(scale_type=2, autoscale=True, overlap=0.5),
+    "log_fixed": dict(scale_type=2, autoscale=False, max_level_db=-30.0, min_level_db=-70.0, overlap=0.5),
+    "lin_auto_thr10": dict(scale_type=0, autoscale=True, thr_level=10.0, overlap=0.5),
+    "lin_fixed": dict(scale_type=0, autoscale=False, max_level_db=-30.0, min_level_db=-70.0, overlap=0.5),
+    "log_auto_thr25": dict(scale_type=2, autoscale=True, thr_level=25.0, overlap=0.5),
+    "log_fixed_bad_range": dict(scale_type=2, autoscale=False, max_level_db=-60.0, min_level_db=-40.0, overlap=0.5),
+    "log_plain_avg": dict(scale_type=2, autoscale=True, overlap=0.5, averaging=2, avgsamples=4, sample_rate=8000,
+                          data_block_size=1024),
+    "logmax0_sumavg": dict(scale_type=3, autoscale=True, overlap=0.5, averaging=1, avgsamples=4, sample_rate=8000,
+                           data_block_size=1024),
+    "linmax0_sumextreme": dict(scale_type=1, autoscale=False, max_level_db=0.0, min_level_db=-30.0, overlap=0.5,
+                               averaging=3, avgsamples=6, sample_rate=8000, data_block_size=1024),
+}
+
+
 def main():
     assert R.available("f64"), "run `make -C oracle` first"
     g1 = np.load(os.path.join(HERE, "glfer_ref_f64.npz"))
@@ -38,6 +56,15 @@ def main():
     out["c5_rows_nw4"] = R.mtm(x48, 32768, 0.5, 4.0, 15, True)
     # "all window types swept" at N=32768: the interior frame 2 of each periodogram
     out["win_rows_32768"] = np.stack([R.periodogram(x48, 32768, t, 0.5, True)[2] for t in range(8)])
+    # display mapping: the reference's main_window_draw (g_main.c, compiled with GTK stubbed out) on the
+    # C1 rows of the round-1 fixture; levels = palette index per pixel (pixel i = bin n-1-i), B/W palette
+    from oracle import ref_gui as G
+    rows = g1["c1_rows"]
+    for name, kw in DISPLAY_CASES.items():
+        r = G.draw_rows(rows, **kw)
+        out[f"disp_{name}"] = r["levels"]
+    out["disp_hot_rgb"] = G.draw_rows(rows[:8], scale_type=G.SCALE_LOG, autoscale=True, palette_id=G.HOT)["rgb"]
+    out["palettes"] = np.stack([G.palette(p) for p in range(8)])
     path = os.path.join(HERE, "glfer_ref_f64_r2.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: getattr(v, "shape", None) for k, v in out.items()}, os.path.getsize(path))

@@ -15,9 +15,10 @@ RTOL = 1e-4
 DB_TOL = 0.01
 FLOOR = 1e-6
 MIN_FRAC = 0.995
-# BASELINE configurations (C1..C5 and the metric shape) are held to the stated bar itself: no bin
-# may sit below the floor (so every bin is judged relatively, 0.01 dB), and the share of bins within
-# 1e-4 relative must be what was measured on B200 in round 1/2 (>= 99.99 %)
+# BASELINE configurations (C1..C5 and the metric shape) are held to the stated bar itself: EVERY bin
+# is judged relatively (0.01 dB), with no exemption for bins below the floor (their count is reported:
+# the reference's own rows hold one such bin in C2, a Kaiser side-lobe null), and the share of bins
+# within 1e-4 relative must be what was measured on B200 in round 1/2 (>= 99.99 %)
 STRICT_MIN_FRAC = 0.9999
 
 
@@ -36,6 +37,7 @@ def psd_stats(got, ref):
     ok = np.where(big, ok_big, ok_small)
     frac = float(np.mean(rel <= RTOL)) if rel.size else 1.0
     return dict(ok=bool(ok.all()), nbad=int((~ok).sum()), frac_1e4=frac, nbelow=int((~big).sum()),
+                nbad_relative=int((rel > db_lin).sum()), max_rel=float(rel.max()) if rel.size else 0.0,
                 max_rel_above_floor=float(rel[big].max()) if big.any() else 0.0,
                 median_rel=float(np.median(rel)) if rel.size else 0.0)
 
@@ -51,8 +53,8 @@ def assert_psd_close(got, ref, what="", min_frac=MIN_FRAC):
 
 
 def assert_psd_strict(got, ref, what="", min_frac=STRICT_MIN_FRAC):
-    """The bar for the BASELINE configurations: every bin within 0.01 dB *relative* (a bin below the
-    floor is a failure, not an excuse) and >= min_frac of the bins within 1e-4 relative."""
+    """The bar for the BASELINE configurations: every bin within 0.01 dB *relative* -- bins below the
+    floor get no absolute-error exemption -- and >= min_frac of the bins within 1e-4 relative."""
     st = assert_psd_close(got, ref, what, min_frac)
-    assert st["nbelow"] == 0, f"{what}: {st['nbelow']} bins below the relative-parity floor: {st}"
+    assert st["nbad_relative"] == 0, f"{what}: {st['nbad_relative']} bins beyond 0.01 dB relative: {st}"
     return st

@@ -70,6 +70,49 @@ def test_round2_fixtures():
     assert np.allclose(ft[fin], ref[fin], rtol=2e-4)          # float32 copy of the tapers in the fixture
 
 
+def _display_case(rows, kw, n=513):
+    """the restatement driven with the arguments of one oracle.ref_gui.draw_rows case"""
+    st = kw.get("scale_type", 2)
+    log, max0 = st in (2, 3), st in (1, 3)
+    shown = rows
+    if kw.get("averaging", 0):
+        fs, block = kw["sample_rate"], kw["data_block_size"]
+        binsize = np.float32(fs) / np.float32(block)                       # g_main.c:1144-1146
+        mn, mx = int(np.float32(400.0) / binsize), int(np.float32(1200.0) / binsize)
+        shown = O.update_avg(kw["averaging"], rows, block, kw["avgsamples"], mn, mx, int(max0))[0][:, :n]
+    return O.display_levels(rows, shown, kw.get("overlap", 0.5), log, kw.get("autoscale", True),
+                            kw.get("max_level_db", -20.0), kw.get("min_level_db", -80.0), kw.get("thr_level", 0.0))[0]
+
+
+def test_display_mapping_pinned():
+    """main_window_draw (g_main.c:1072-1281): fixtures produced by the compiled reference GUI unit"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mg2", os.path.join(os.path.dirname(__file__), "golden", "make_golden_r2.py"))
+    mg2 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg2)
+    g2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "glfer_ref_f64_r2.npz"))
+    rows = GOLD["c1_rows"]
+    for name, kw in mg2.DISPLAY_CASES.items():
+        assert np.array_equal(_display_case(rows, kw), g2[f"disp_{name}"]), name
+    # palette look-up: the HOT palette applied to the log/autoscale levels
+    lv = g2["disp_log_auto"][:8]
+    assert np.array_equal(g2["palettes"][3][lv], g2["disp_hot_rgb"])
+    assert np.array_equal(g2["palettes"][4][:, 0], np.arange(256))           # B/W: index = grey level
+
+
+@have_ref
+def test_display_mapping_matches_live_reference_gui_unit():
+    from oracle import ref_gui as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libglfer_ref_gui.so not built")
+    rng = np.random.default_rng(11)
+    rows = (rng.standard_normal((40, 257)) ** 2 * 1e-5).astype(np.float32)
+    rows[:, 30] += 3e-3
+    for kw in (dict(scale_type=2, autoscale=True, overlap=0.75, thr_level=5.0),
+               dict(scale_type=0, autoscale=False, max_level_db=-25.0, min_level_db=-65.0, overlap=0.0)):
+        assert np.array_equal(_display_case(rows, kw, n=257), G.draw_rows(rows, **kw)["levels"])
+
+
 def test_hop_truncation():
     assert O.hop_size(4096, 0.9) == 409            # float overlap, double product, truncated
     assert O.hop_size(1024, 0.5) == 512 and O.hop_size(4096, 0.75) == 1024 and O.hop_size(1024, 0.0) == 1024
