@@ -382,6 +382,24 @@ def main():
                               "h2d_bytes_per_step": int(pcm_host.nbytes), "d2h_bytes_per_step": int(d2h),
                               "ms_per_step": 1e3 * pcm_s / e2e_steps, "api": "glfer_gram_run_pcm16",
                               "rows_identical_to_float_input": bool(float(rows_host[:: max(1, nf // 97)].sum()) == checksum)}
+        # the reference's real end-to-end product is the waterfall: 16-bit PCM of a WAV file in, 8-bit palette
+        # indices out (main_window_draw, g_main.c:1186-1229, fixed display range = autoscale off).  The
+        # spectrogram kernel writes the levels itself: 2 B/sample up, 1 B/bin down, no float row in HBM.
+        if not plan.avg and kw.get("mode", 0) != 3:
+            lev_host = api.pinned_empty((nf, bins), np.uint8)
+            disp = dict(log_scale=True, autoscale=False, max_level_db=-20.0, min_level_db=-80.0, thr_level=0.0,
+                        out={"levels": lev_host})
+            plan.run_display(pcm_host, origin=lo, first_frame=first, nframes=nf, **disp)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan.run_display(pcm_host, origin=lo, first_frame=first, nframes=nf, **disp)
+            barrier()
+            u8_s = max_over_ranks(time.perf_counter() - t0)
+            e2e["pcm16_in_u8_out"] = {"value": world * nf * e2e_steps / u8_s, "unit": "frames/s",
+                                      "h2d_bytes_per_step": int(pcm_host.nbytes), "d2h_bytes_per_step": int(lev_host.nbytes),
+                                      "ms_per_step": 1e3 * u8_s / e2e_steps, "api": "glfer_gram_run_display_pcm16 (fused 8-bit levels)",
+                                      "levels_histogram_nonconstant": bool(lev_host[:: max(1, nf // 97)].min() < lev_host[:: max(1, nf // 97)].max())}
     else:
         checksum = None
 

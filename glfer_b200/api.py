@@ -140,6 +140,12 @@ def lib() -> C.CDLL:
         l.glb_window_table.restype = None
         l.glb_dpss.argtypes = [C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         l.glb_hop.argtypes = [C.c_int, C.c_float]
+        l.glfer_b200_map_levels.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.POINTER(DisplayConfig), C.c_void_p,
+                                            C.c_void_p, C.c_int]
+        l.glfer_b200_set_fused_levels.argtypes = [C.c_int]
+        l.glfer_b200_set_fused_levels.restype = None
+        l.glfer_palette.argtypes = [C.c_int, C.c_void_p]
+        l.glb_short_db_f.argtypes = [C.c_float]
         l.glb_force_generic_kernel.argtypes = [C.c_int]
         l.glb_force_generic_kernel.restype = None
         l.glb_set_kernel_preference.argtypes = [C.c_int]
@@ -384,6 +390,31 @@ def host_dpss(n: int, nw: float, kmax: int):
     if rc != 0:
         raise GlferError("glb_dpss failed")
     return t, lam
+
+
+def map_levels(rows: np.ndarray, log_scale=True, max_level_db=-20.0, min_level_db=-80.0, thr_level=0.0,
+               display_range: np.ndarray | None = None, device: int = 0) -> np.ndarray:
+    """glfer_b200_map_levels: main_window_draw's level mapping on given rows (fixed levels, or a
+    (display_max, display_min) pair per row)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    nrows, nbins = rows.shape
+    out = np.empty((nrows, nbins), dtype=np.uint8)
+    dc = DisplayConfig(int(log_scale), 0, max_level_db, min_level_db, thr_level, None)
+    rng = None if display_range is None else np.ascontiguousarray(display_range, dtype=np.float32)
+    _check(lib().glfer_b200_map_levels(rows.ctypes.data, nrows, nbins, C.byref(dc), _ptr(rng), out.ctypes.data, device))
+    return out
+
+
+def set_fused_levels(on: bool) -> None:
+    """testing aid: False = display levels always mapped in a second pass over float rows"""
+    lib().glfer_b200_set_fused_levels(int(on))
+
+
+def palette(p: int) -> np.ndarray:
+    """glfer_palette: the 256 RGB triplets of set_palette (g_main.c:649-762)"""
+    tab = np.empty((256, 3), dtype=np.uint8)
+    _check(lib().glfer_palette(p, tab.ctypes.data))
+    return tab
 
 
 def force_generic_kernel(on: bool) -> None:

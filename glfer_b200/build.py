@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, "_build")
 
 # (source, tag, extra flags): gram_part.cu is compiled once per subset of FFT sizes, in parallel
 CU_UNITS = [("csrc/gram_kernels.cu", "", [])] + [("csrc/gram_part.cu", f".p{k}", [f"-DGLB_PART={k}"]) for k in range(4)]
-C_SOURCES = ["host/window.c", "host/dpss.c", "host/gram.c", "host/dropin.c", "host/wav.c"]
+C_SOURCES = ["host/window.c", "host/dpss.c", "host/gram.c", "host/dropin.c", "host/wav.c", "host/levels.c"]
 HEADERS = ["csrc/fft_core.cuh", "csrc/fft_wpf.cuh", "csrc/gram_common.cuh", "csrc/tables.hpp", "host/glb_host.h", "../include/glb_shim.h", "../include/fft.h",
            "../include/mtm.h", "../include/avg.h", "../include/lmp.h", "../include/glfer_b200.h"]
 

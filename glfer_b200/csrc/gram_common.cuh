@@ -14,6 +14,7 @@
 
 #include "fft_core.cuh"
 #include "fft_wpf.cuh"
+#include "levels.cuh"
 #include "tables.hpp"
 #include "../../include/glb_shim.h"
 
@@ -63,6 +64,11 @@ struct KParams {
   int rows_db;
   float2 *spectrum;
   const float2 *tw, *vtab, *roots;
+  // fused display mapping (g_main.c:1186-1229): 8-bit palette indices, pixel i = bin M - i, beside or
+  // instead of the float rows
+  unsigned char *levels;
+  long long lev_stride;
+  LevelMap lm;
 };
 
 #ifndef GLB_REG_TARGET
@@ -451,11 +457,13 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
       MidPasses<M, 1, RT>::run(v, t, buf, tw_mid, tr, g);
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
       float *row = (!MULTI && active && p.rows) ? p.rows + fl * p.row_stride : nullptr;
+      unsigned char *lrow = (!MULTI && active && p.levels) ? p.levels + fl * p.lev_stride : nullptr;
       float2 *sp = (!MULTI && active && p.spectrum) ? p.spectrum + fl * (long long) (M + 1) : nullptr;
       const bool db = p.rows_db != 0;
       const float ss = p.spec_scale;
       auto sink_single = [&](int slot, float2 a, bool cj) {
         const int bin = slot_bin<M>(t, slot);
+        if (lrow) lrow[M - bin] = map_level(norm2(a), p.lm);
         if (row) {
           float y = norm2(a);
           if (db) y = 10.f * log10f(y);
@@ -477,6 +485,12 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
         else emit_bins_rt<M>(v, t, tl, sink_single);
       }
       // no barrier here: (A) of the next transform orders these reads before its stores
+    }
+    if (MULTI && active && p.levels) {
+      unsigned char *lrow = p.levels + fl * p.lev_stride;
+#pragma unroll
+      for (int slot = 0; slot < 17; slot++)
+        if (slot < 16 || t == 0) lrow[M - slot_bin<M>(t, slot)] = map_level(acc[slot], p.lm);
     }
     if (MULTI && active && p.rows) {
       float *row = p.rows + fl * p.row_stride;
@@ -632,6 +646,21 @@ __device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[1
   if (t == 0) st_row(row + M / 2, yv[16]);
 }
 
+// The same row as 8-bit display levels: pixel i shows bin M - i (g_main.c:1193-1201), so the bins a warp
+// stores together are still 32 consecutive bytes.
+template <int M>
+__device__ __forceinline__ void store_levels(unsigned char *lrow, int t, const float (&yv)[17], const LevelMap &lm) {
+  constexpr int T = M / kPoints;
+  const int kh = khi<M>(t) - 8 * T;
+  unsigned char *pa = lrow + (M - t), *pb = lrow + t, *pah = lrow + (M - kh), *pbh = lrow + kh;
+#pragma unroll
+  for (int rp = 0; rp < 8; rp++) {
+    *((rp < 4 ? pa : pah) - rp * 2 * T) = map_level(yv[2 * rp], lm);
+    *((rp < 4 ? pb : pbh) + rp * 2 * T) = map_level(yv[2 * rp + 1], lm);
+  }
+  if (t == 0) lrow[M - M / 2] = map_level(yv[16], lm);
+}
+
 // mid passes of the ring kernel
 template <int M, int P, bool RT> struct RingMidPasses {
   static __device__ __forceinline__ void run(float2 (&v)[kPoints], int t, float2 *buf, const float2 *tw, const TwRegs &tr, int g) {
@@ -740,9 +769,10 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   // loop state carried incrementally (no 64-bit multiplies per frame): frames of this group that
   // exist, the row to write and the block the next bulk copy reads
   const int nact = group_active ? (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group) : 0;
-  float *row_ptr = p.rows + fb * p.row_stride;
+  float *row_ptr = p.rows + fb * p.row_stride;                   // (never dereferenced when p.rows is null)
+  unsigned char *lev_ptr = p.levels + fb * p.lev_stride;
   const float *next_src = p.samples + ((f_first + 1) * (long long) hop - p.origin);
-  for (int it = 0; it < p.frames_per_group; ++it, row_ptr += p.row_stride, next_src += hop) {
+  for (int it = 0; it < p.frames_per_group; ++it, row_ptr += p.row_stride, lev_ptr += p.lev_stride, next_src += hop) {
     const bool active = it < nact;
     const bool next_there = it + 1 < nact;
     const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
@@ -831,23 +861,33 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
       if (!MULTI) {
         // the row leaves the registers here: one store per bin, streaming (written once, never
-        // re-read by this kernel); the dB conversion is a single uniform branch per frame
-        if (db) {
+        // re-read by this kernel); the display levels and the dB conversion are uniform branches
+        if (p.levels != nullptr && active) store_levels<M>(lev_ptr, t, yv, p.lm);
+        if (p.rows != nullptr) {
+          if (db) {
 #pragma unroll
-          for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
+            for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
+          }
+          if (active) store_row<M>(row, t, yv);
         }
-        if (active) store_row<M>(row, t, yv);
       }
     }
     if (MULTI && active) {
       float *row = row_ptr;
       const bool db = p.rows_db != 0;
+      if (p.levels != nullptr) {
 #pragma unroll
-      for (int slot = 0; slot < 17; slot++) {
-        if (slot < 16 || t == 0) {
-          float y = acc[slot];
-          if (db) y = 10.f * log10f(y);
-          row[slot_bin<M>(t, slot)] = y;
+        for (int slot = 0; slot < 17; slot++)
+          if (slot < 16 || t == 0) lev_ptr[M - slot_bin<M>(t, slot)] = map_level(acc[slot], p.lm);
+      }
+      if (p.rows != nullptr) {
+#pragma unroll
+        for (int slot = 0; slot < 17; slot++) {
+          if (slot < 16 || t == 0) {
+            float y = acc[slot];
+            if (db) y = 10.f * log10f(y);
+            row[slot_bin<M>(t, slot)] = y;
+          }
         }
       }
     }
@@ -1213,7 +1253,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
       if (kp.hop == (unitw << s2)) qw = s2;
     const bool mean_ok = !kp.fused_mean || (qw >= 0 && (kp.n_ov % kp.hop) == 0);
     const bool pref_ok = (allow & 4) != 0;
-    if (pref_ok && !multi && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && mean_ok &&
+    if (pref_ok && !multi && plain && kp.rows != nullptr && kp.levels == nullptr && kp.spectrum == nullptr && kp.means == nullptr && mean_ok &&
         (kp.hop % 2) == 0 && ((kp.n_ov + kp.origin) % 2) == 0 && ((reinterpret_cast<uintptr_t>(kp.samples) & 7) == 0)) {
       // interior frames: f*hop - n_ov >= max(origin, 0) and the frame ends inside the staged samples
       const long long lo_s = kp.origin > 0 ? kp.origin : 0;
@@ -1264,7 +1304,7 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
     if constexpr (GeoM::RT && M >= 256) {
       // 50 % / 75 % overlap periodograms: two frames per thread (selectable family: measured
       // 0.431 ms vs 0.422 ms for the ring kernel on the metric workload, 3 CTAs/SM vs 6)
-      if (regular && !multi && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr &&
+      if (regular && !multi && plain && kp.rows != nullptr && kp.levels == nullptr && kp.spectrum == nullptr && kp.means == nullptr &&
           (allow & 8) != 0 && (qs == 3 || qs == 2) && kp.nframes >= 2) {
         void (*pk)(const KParams) = qs == 3 ? gram_pair_kernel<M, 3> : gram_pair_kernel<M, 2>;
         const size_t smem = qs == 3 ? PairGeo<M, 3>::SMEM : PairGeo<M, 2>::SMEM;
@@ -1294,7 +1334,8 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
         }
       }
     }
-    if (regular && plain && kp.rows != nullptr && kp.spectrum == nullptr && kp.means == nullptr && (allow & 2) != 0) {
+    if (regular && plain && (kp.rows != nullptr || kp.levels != nullptr) && kp.spectrum == nullptr && kp.means == nullptr &&
+        (allow & 2) != 0) {
       const int nb = kPoints >> qs;
       const RingLayout L = ring_layout<M>(kp.hop, nb);
       size_t smem = (size_t) GeoM::G * L.group_bytes + ((multi ? RingGeo<M, true>::RT : RingGeo<M, false>::RT) ? 0 : Geo<M>::TWS_BYTES);

@@ -152,6 +152,37 @@ extern "C" int glb_tables_destroy(void *tp) {
   return GLB_OK;
 }
 
+// ------------------------------------------------------------------------- display tables
+struct LevelTables {
+  float *thr_f;
+  double *thr_d;
+};
+
+extern "C" int glb_level_tables_create(const float *thr_f, const double *thr_d, int count, void **out) {
+  if (!thr_f || !thr_d || count != kDbN) {
+    glb_set_error("glb_level_tables_create: expected GLB_DB_NTHR thresholds");
+    return GLB_EINVAL;
+  }
+  LevelTables *t = new LevelTables();
+  t->thr_f = nullptr;
+  t->thr_d = nullptr;
+  CU(cudaMalloc(&t->thr_f, sizeof(float) * count));
+  CU(cudaMalloc(&t->thr_d, sizeof(double) * count));
+  CU(cudaMemcpy(t->thr_f, thr_f, sizeof(float) * count, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(t->thr_d, thr_d, sizeof(double) * count, cudaMemcpyHostToDevice));
+  *out = t;
+  return GLB_OK;
+}
+
+extern "C" int glb_level_tables_destroy(void *tp) {
+  LevelTables *t = (LevelTables *) tp;
+  if (!t) return GLB_OK;
+  cudaFree(t->thr_f);
+  cudaFree(t->thr_d);
+  delete t;
+  return GLB_OK;
+}
+
 extern "C" int glb_gram_fused_mean_ok(int n, int hop) {
   if (!glb_fft_supported(n) || hop < 1 || hop > n) return 0;
   const int unit = n / 16;            // 2T
@@ -201,6 +232,28 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   k.tw = tb->tw;
   k.vtab = tb->vtab;
   k.roots = tb->roots;
+  if (a->levels) {
+    if (!a->level_tables) {
+      glb_set_error("glb_launch_gram: levels output needs level_tables");
+      return GLB_EINVAL;
+    }
+    if (a->spectrum) {
+      glb_set_error("glb_launch_gram: levels and spectrum outputs are exclusive");
+      return GLB_EINVAL;
+    }
+    k.levels = a->levels;
+    k.lev_stride = a->levels_stride;
+    k.lm.thr = ((const LevelTables *) a->level_tables)->thr_f;
+    k.lm.lut = a->levels_log ? a->level_lut : nullptr;
+    k.lm.log_scale = a->levels_log;
+    k.lm.dmin = a->level_min;
+    k.lm.dmax = a->level_max;
+    k.lm.thr_level = a->level_thr;
+  }
+  if (!a->rows && !a->levels && !a->spectrum) {
+    glb_set_error("glb_launch_gram: no output requested");
+    return GLB_EINVAL;
+  }
   const bool multi = a->ntapers > 1;
   if (multi && a->spectrum) {
     glb_set_error("glb_launch_gram: spectrum output is only defined for one taper");
@@ -855,33 +908,23 @@ __global__ void agc_kernel(const float *__restrict__ stats, long long nframes, l
 
 // levels_kernel: one warp per row.  Pixel i of a row shows bin n-1-i (g_main.c:1193-1201); in
 // the log scales the level first passes through the reference's `short` level buffer
-// (sig_level = levbuf[..] = 10 log10(x): integer-truncated dB, g_main.c:68,1193-1195).
-__device__ __forceinline__ float short_db(float x) {
-  const double d = 10.0 * log10((double) x);
-  if (!(fabs(d) < 2147483648.0)) return 0.f;        // x86 cvttsd2si overflow -> 0x80000000 -> (short) 0
-  return (float) (short) (int) d;
-}
-
+// (sig_level = levbuf[..] = 10 log10(x): integer-truncated dB, g_main.c:68,1193-1195), located
+// between the host-computed thresholds (levels.cuh) so that it is the host libm's value bit for bit.
 __global__ void __launch_bounds__(256) levels_kernel(const float *__restrict__ rows, long long stride, int nbins,
-                                                     long long nframes, const float *__restrict__ range,
-                                                     const float *__restrict__ fixed_range, int log_scale, float thr,
+                                                     long long nframes, const float *__restrict__ range, LevelMap lm,
                                                      const unsigned char *__restrict__ colortab,
                                                      unsigned char *__restrict__ levels, unsigned char *__restrict__ rgb) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
   for (long long f = warp; f < nframes; f += nwarps) {
-    const float dmax = range ? range[2 * f] : fixed_range[0];
-    const float dmin = range ? range[2 * f + 1] : fixed_range[1];
+    if (range) {                                         // per-frame display range (autoscale)
+      lm.dmax = range[2 * f];
+      lm.dmin = range[2 * f + 1];
+    }
     const float *row = rows + f * stride;
     for (int i = lane; i < nbins; i += 32) {
-      const float x = row[nbins - 1 - i];
-      const float sig_level = log_scale ? short_db(x) : x;
-      const float fl = 255 * ((sig_level - dmin) / (dmax - dmin));
-      unsigned char v;
-      if ((double) fl < 255.0 * (double) thr) v = 0;
-      else if (fl > 255) v = 255;
-      else v = (unsigned char) (((double) fl - 255.0 * (double) thr) / (1.0 - (double) thr));
+      const unsigned char v = map_level(row[nbins - 1 - i], lm);
       if (levels) levels[f * nbins + i] = v;
       if (rgb) {
         unsigned char *px = rgb + (f * nbins + i) * 3;
@@ -903,14 +946,24 @@ extern "C" int glb_launch_agc(const float *stats, long long nframes, long long f
 }
 
 extern "C" int glb_launch_levels(const float *rows, long long stride, int nbins, long long nframes, const float *range,
-                                 const float *fixed_range, int log_scale, float thr, const unsigned char *colortab,
-                                 unsigned char *levels, unsigned char *rgb, void *stream) {
+                                 const float *fixed_range, int log_scale, float thr, const void *level_tables,
+                                 const unsigned char *level_lut, const unsigned char *colortab, unsigned char *levels,
+                                 unsigned char *rgb, void *stream) {
   if (nframes <= 0) return GLB_OK;
-  if ((!range && !fixed_range) || (rgb && !colortab)) { glb_set_error("glb_launch_levels: missing range / palette"); return GLB_EINVAL; }
+  if ((!range && !fixed_range) || (rgb && !colortab) || !level_tables) {
+    glb_set_error("glb_launch_levels: missing range / palette / level tables");
+    return GLB_EINVAL;
+  }
+  LevelMap lm;
+  lm.thr = ((const LevelTables *) level_tables)->thr_f;
+  lm.lut = (!range && log_scale) ? level_lut : nullptr;       // the look-up table is for ONE display range
+  lm.log_scale = log_scale;
+  lm.dmax = fixed_range ? fixed_range[0] : 0.f;
+  lm.dmin = fixed_range ? fixed_range[1] : 0.f;
+  lm.thr_level = thr;
   long long ctas = (nframes * 32 + 255) / 256;
   if (ctas > 148 * 64) ctas = 148 * 64;
-  levels_kernel<<<(int) ctas, 256, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nframes, range, fixed_range, log_scale, thr,
-                                                              colortab, levels, rgb);
+  levels_kernel<<<(int) ctas, 256, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nframes, range, lm, colortab, levels, rgb);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;

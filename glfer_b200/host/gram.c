@@ -61,9 +61,22 @@ struct glfer_gram_plan {
   slot_t slot[NSLOT];
   int *d_cand_all, *d_peak_all;   /* whole-run *peakbin candidates / carried values */
   size_t cand_all_cap;
-  float *d_agc_state, *d_fixed_range;   /* display mapping: carried AGC levels, fixed display range */
+  float *d_agc_state;   /* display mapping: carried AGC levels */
   unsigned char *d_colortab;
+  void *level_tables;   /* dB thresholds on the device (host/levels.c) */
+  unsigned char *d_level_lut;
 };
+
+/* what a display run asks of exec_slot: levels written by the spectrogram kernel itself */
+typedef struct {
+  int log_scale;
+  float dmin, dmax, thr;
+} fused_levels;
+
+static int make_level_tables(void **tables);
+static int g_fused_levels = 1;
+/* testing aid: 0 = always map levels in a second pass over float rows */
+void glfer_b200_set_fused_levels(int on) { g_fused_levels = on; }
 
 static __thread char g_msg[512];
 
@@ -185,7 +198,8 @@ void glfer_gram_plan_destroy(glfer_gram_plan *p)
   glb_free(p->d_tapers);
   glb_free(p->d_cand_all);
   glb_free(p->d_peak_all);
-  glb_free(p->d_agc_state); glb_free(p->d_fixed_range); glb_free(p->d_colortab);
+  glb_free(p->d_agc_state); glb_free(p->d_colortab); glb_free(p->d_level_lut);
+  glb_level_tables_destroy(p->level_tables);
   glb_tables_destroy(p->tables);
   free(p->h_window); free(p->h_tapers); free(p->h_lambda);
   free(p);
@@ -315,7 +329,8 @@ static int stage_slot(glfer_gram_plan *p, slot_t *s, const float *samples, const
 }
 
 /* queue the kernels of frames [first, first + nframes) on a slot */
-static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long nframes, int *cand_out)
+static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long nframes, int *cand_out,
+                     const fused_levels *fl)
 {
   const glfer_gram_config *c = &p->cfg;
   const long long halo = halo_frames(p, first);
@@ -325,7 +340,7 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   if (lo < 0) lo = 0;
   if (lo < s->s_origin || hi > s->s_origin + s->s_count)
     return fail(GLFER_EINVAL, "staged samples do not cover the requested frames (see glfer_gram_required_span)");
-  TRY(ensure((void **) &s->d_psd, &s->psd_cap, (size_t) nf * p->bins, sizeof(float)));
+  if (!fl) TRY(ensure((void **) &s->d_psd, &s->psd_cap, (size_t) nf * p->bins, sizeof(float)));
 
   const float *d_means = NULL;
   long long means_first = 0;
@@ -358,8 +373,18 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   g.taper_scale = p->taper_scale;
   g.first_frame = f0;
   g.nframes = nf;
-  g.rows = s->d_psd;
+  g.rows = fl ? NULL : s->d_psd;
   g.row_stride = p->bins;
+  if (fl) {                           /* levels straight from the kernel's registers: no float rows at all */
+    g.levels = s->d_levels;
+    g.levels_stride = p->bins;
+    g.level_tables = p->level_tables;
+    g.levels_log = fl->log_scale;
+    g.level_lut = p->d_level_lut;
+    g.level_min = fl->dmin;
+    g.level_max = fl->dmax;
+    g.level_thr = fl->thr;
+  }
   g.rows_db = (c->avg_mode == GLFER_NO_AVG && c->mode != GLFER_MODE_LMP) ? c->scale_db : 0;   /* averaging / LMP need linear PSD */
   g.spectrum = NULL;
   g.tables = p->tables;
@@ -468,7 +493,7 @@ int glfer_gram_exec(glfer_gram_plan *p, long long first_frame, long long nframes
   slot_t *s = &p->slot[0];
   s->time_gram = kernel_ms != NULL;
   if (kernel_ms) TRY(glb_event_record(s->ev0, s->stream));
-  int rc = exec_slot(p, s, first_frame, nframes, NULL);
+  int rc = exec_slot(p, s, first_frame, nframes, NULL, NULL);
   s->time_gram = 0;
   if (rc != 0) return rc;
   if (kernel_ms) {
@@ -574,7 +599,7 @@ static int run_impl(glfer_gram_plan *p, const float *samples, const short *pcm, 
     if (clo < 0) clo = 0;
     rc = stage_slot(p, s, samples ? samples + (clo - origin) : NULL, pcm ? pcm + (clo - origin) : NULL, clo, chi - clo);
     if (rc) break;
-    rc = exec_slot(p, s, c0, cn, defer_carry ? p->d_cand_all + done : NULL);
+    rc = exec_slot(p, s, c0, cn, defer_carry ? p->d_cand_all + done : NULL, NULL);
     if (rc) break;
     rc = fetch_slot(p, s, psd_rows ? psd_rows + (size_t) done * p->bins : NULL,
                     avg_rows ? avg_rows + (size_t) done * p->bins : NULL, avg_ret ? avg_ret + done : NULL,
@@ -642,27 +667,33 @@ static int run_display_impl(glfer_gram_plan *p, const float *samples, const shor
     return fail(GLFER_EINVAL, "samples do not cover the requested frames (see glfer_gram_required_span)");
   if (!p->d_agc_state) {
     TRY(glb_malloc((void **) &p->d_agc_state, 2 * sizeof(float)));
-    TRY(glb_malloc((void **) &p->d_fixed_range, 2 * sizeof(float)));
     TRY(glb_malloc((void **) &p->d_colortab, 768));
+    TRY(glb_malloc((void **) &p->d_level_lut, GLB_DB_NTHR));
+    /* the device never evaluates 10 log10 itself */
+    int rt = make_level_tables(&p->level_tables);
+    if (rt != 0) return rt;
   }
   void *st0 = p->slot[0].stream;
   float state[2] = { agc_state ? agc_state[0] : 0.0f, agc_state ? agc_state[1] : 0.0f };
   TRY(glb_memcpy_h2d(p->d_agc_state, state, sizeof state, st0));
+  const float thr = dc->thr_level / 100.0;                  /* g_main.c:1098 */
+  float fixed[2] = { 0.0f, 0.0f };                          /* (display_max, display_min) */
   if (!dc->autoscale) {
-    /* fixed levels, g_main.c:1126-1138 */
-    float mx = pow(10.0, dc->max_level_db / 10.0);
-    float mn = pow(10.0, dc->min_level_db / 10.0);
-    mn = (mx > mn ? mn : mx / 10.0);
-    float r[2];
-    if (dc->log_scale) { r[0] = 10.0 * log10(mx); r[1] = 10.0 * log10(mn); }
-    else { r[0] = mx; r[1] = mn; }
-    TRY(glb_memcpy_h2d(p->d_fixed_range, r, sizeof r, st0));
+    /* fixed levels, g_main.c:1126-1138; in the log scales the level of every integer dB value is
+       tabulated once on the host with the reference's own arithmetic */
+    unsigned char lut[GLB_DB_NTHR];
+    glb_fixed_display_range(dc->max_level_db, dc->min_level_db, dc->log_scale, &fixed[0], &fixed[1]);
+    glb_level_lut(fixed[1], fixed[0], thr, lut);
+    TRY(glb_memcpy_h2d(p->d_level_lut, lut, sizeof lut, st0));
   }
   if (dc->colortab) TRY(glb_memcpy_h2d(p->d_colortab, dc->colortab, 768, st0));
   TRY(glb_stream_sync(st0));
-  const float thr = dc->thr_level / 100.0;                  /* g_main.c:1098 */
   const long long cf = chunk_frames(p);
   const int avg_on = p->cfg.avg_mode != GLFER_NO_AVG;
+  /* fixed display range, rows shown = the estimator's own rows: the spectrogram kernel writes the 8-bit
+     levels itself and no float row ever reaches HBM (1 byte per bin instead of 4 + 4 + 1) */
+  const int fuse = g_fused_levels && !dc->autoscale && !avg_on && p->cfg.mode != GLFER_MODE_LMP && !rgb;
+  const fused_levels fl = { dc->log_scale, fixed[1], fixed[0], thr };
   int rc = 0, ci = 0;
   long long done = 0;
   while (done < nframes && rc == 0) {
@@ -676,14 +707,20 @@ static int run_display_impl(glfer_gram_plan *p, const float *samples, const shor
     if (clo < 0) clo = 0;
     rc = stage_slot(p, s, samples ? samples + (clo - origin) : NULL, pcm ? pcm + (clo - origin) : NULL, clo, chi - clo);
     if (rc) break;
-    rc = exec_slot(p, s, c0, cn, NULL);
-    if (rc) break;
-    /* psdbuf of the GUI: the estimator's output row, which in LMP mode is the statistic */
-    const float *d_psd = (p->cfg.mode == GLFER_MODE_LMP) ? s->d_avg : s->d_psd + (size_t) s->out_halo * p->bins;
-    const float *d_shown = avg_on ? s->d_avg : d_psd;               /* g_main.c:1192-1201 */
     rc = ensure((void **) &s->d_levels, &s->levels_cap, (size_t) cn * p->bins, 1);
     if (rc == 0 && rgb) rc = ensure((void **) &s->d_rgb, &s->rgb_cap, (size_t) cn * p->bins * 3, 1);
     if (rc) break;
+    rc = exec_slot(p, s, c0, cn, NULL, fuse ? &fl : NULL);
+    if (rc) break;
+    if (fuse) {
+      if (levels) rc = shim(glb_memcpy_d2h(levels + (size_t) done * p->bins, s->d_levels, (size_t) cn * p->bins, s->stream));
+      done += cn;
+      ci++;
+      continue;
+    }
+    /* psdbuf of the GUI: the estimator's output row, which in LMP mode is the statistic */
+    const float *d_psd = (p->cfg.mode == GLFER_MODE_LMP) ? s->d_avg : s->d_psd + (size_t) s->out_halo * p->bins;
+    const float *d_shown = avg_on ? s->d_avg : d_psd;               /* g_main.c:1192-1201 */
     const float *d_range = NULL;
     if (dc->autoscale) {
       if ((size_t) cn > s->stats_cap) {
@@ -705,8 +742,9 @@ static int run_display_impl(glfer_gram_plan *p, const float *samples, const shor
       if (range_out) rc = shim(glb_memcpy_d2h(range_out + 2 * done, s->d_range, sizeof(float) * 2 * (size_t) cn, s->stream));
       if (rc) break;
     }
-    rc = shim(glb_launch_levels(d_shown, p->bins, p->bins, cn, d_range, p->d_fixed_range, dc->log_scale, thr,
-                                dc->colortab ? p->d_colortab : NULL, s->d_levels, rgb ? s->d_rgb : NULL, s->stream));
+    rc = shim(glb_launch_levels(d_shown, p->bins, p->bins, cn, d_range, dc->autoscale ? NULL : fixed, dc->log_scale, thr,
+                                p->level_tables, p->d_level_lut, dc->colortab ? p->d_colortab : NULL, s->d_levels,
+                                rgb ? s->d_rgb : NULL, s->stream));
     if (rc) break;
     if (levels) rc = shim(glb_memcpy_d2h(levels + (size_t) done * p->bins, s->d_levels, (size_t) cn * p->bins, s->stream));
     if (rc == 0 && rgb) rc = shim(glb_memcpy_d2h(rgb + (size_t) done * p->bins * 3, s->d_rgb, (size_t) cn * p->bins * 3, s->stream));
@@ -735,6 +773,54 @@ int glfer_gram_run_display_pcm16(glfer_gram_plan *p, const short *pcm, long long
 {
   if (!p || !pcm) return fail(GLFER_EINVAL, "null argument");
   return run_display_impl(p, NULL, pcm, origin, count, first_frame, nframes, dc, agc_state, levels, rgb, display_range);
+}
+
+/* dB thresholds from the host's libm (host/levels.c) on the current device */
+static int make_level_tables(void **tables)
+{
+  float *tf = malloc(sizeof(float) * GLB_DB_NTHR);
+  double *td = malloc(sizeof(double) * GLB_DB_NTHR);
+  if (!tf || !td) { free(tf); free(td); return fail(GLFER_ENOMEM, "out of memory"); }
+  glb_db_thresholds_f(tf);
+  glb_db_thresholds_d(td);
+  const int rc = shim(glb_level_tables_create(tf, td, GLB_DB_NTHR, tables));
+  free(tf); free(td);
+  return rc;
+}
+
+int glfer_b200_map_levels(const float *rows, long long nrows, int nbins, const glfer_display_config *dc,
+                          const float *range, unsigned char *levels, int device)
+{
+  g_msg[0] = 0;
+  if (!rows || !dc || !levels || nrows < 0 || nbins < 1) return fail(GLFER_EINVAL, "bad arguments");
+  if (nrows == 0) return 0;
+  int ndev = 0;
+  if (glb_device_count(&ndev) != GLB_OK || ndev < 1) return fail(GLFER_ENODEV, "no CUDA device (libglfer_b200 has no CPU fallback)");
+  TRY(glb_set_device(device));
+  void *tables = NULL, *d_rows = NULL, *d_lev = NULL, *d_range = NULL, *d_lut = NULL;
+  const size_t cells = (size_t) nrows * nbins;
+  const float thr = dc->thr_level / 100.0;
+  float fixed[2] = { 0.0f, 0.0f };
+  int rc = make_level_tables(&tables);
+  if (rc == 0) rc = shim(glb_malloc(&d_rows, sizeof(float) * cells));
+  if (rc == 0) rc = shim(glb_malloc(&d_lev, cells));
+  if (rc == 0) rc = shim(glb_memcpy_h2d(d_rows, rows, sizeof(float) * cells, NULL));
+  if (rc == 0 && range) {
+    rc = shim(glb_malloc(&d_range, sizeof(float) * 2 * (size_t) nrows));
+    if (rc == 0) rc = shim(glb_memcpy_h2d(d_range, range, sizeof(float) * 2 * (size_t) nrows, NULL));
+  } else if (rc == 0) {
+    unsigned char lut[GLB_DB_NTHR];
+    glb_fixed_display_range(dc->max_level_db, dc->min_level_db, dc->log_scale, &fixed[0], &fixed[1]);
+    glb_level_lut(fixed[1], fixed[0], thr, lut);
+    rc = shim(glb_malloc(&d_lut, sizeof lut));
+    if (rc == 0) rc = shim(glb_memcpy_h2d(d_lut, lut, sizeof lut, NULL));
+  }
+  if (rc == 0) rc = shim(glb_launch_levels(d_rows, nbins, nbins, nrows, d_range, range ? NULL : fixed, dc->log_scale, thr,
+                                           tables, d_lut, NULL, d_lev, NULL, NULL));
+  if (rc == 0) rc = shim(glb_memcpy_d2h(levels, d_lev, cells, NULL));
+  glb_free(d_rows); glb_free(d_lev); glb_free(d_range); glb_free(d_lut);
+  glb_level_tables_destroy(tables);
+  return rc;
 }
 
 /* ---------------------------------------------------------------- time sharding */

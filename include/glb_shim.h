@@ -78,7 +78,21 @@ typedef struct {
   float *spectrum;             /* device out: [nframes][n/2+1] (re,im) pairs, or NULL (periodogram only) */
   const void *tables;          /* from glb_tables_create(n) */
   int groups_hint;             /* 0 = auto: resident frame-groups per launch */
+  /* fused display mapping (main_window_draw, g_main.c:1186-1229): 8-bit palette indices written by the
+     spectrogram kernel itself, beside or instead of the float rows; pixel i of a row shows bin n/2 - i */
+  unsigned char *levels;       /* device out: [nframes][levels_stride], or NULL */
+  long long levels_stride;
+  const void *level_tables;    /* from glb_level_tables_create() */
+  int levels_log;              /* 1: SCALE_LOG / SCALE_LOG_MAX0 (integer-truncated dB), 0: linear */
+  const unsigned char *level_lut;   /* device: level of every integer dB value (fixed display range, log scales) or NULL */
+  float level_min, level_max;  /* display_min / display_max (dB in the log scales); used when level_lut == NULL */
+  float level_thr;             /* opt.thr_level / 100 */
 } glb_gram_args;
+
+/* host-computed tables of the display mapping on the current device: dB thresholds as floats and doubles
+ * (host/levels.c: GLB_DB_NTHR entries each) */
+int glb_level_tables_create(const float *thr_f, const double *thr_d, int count, void **tables);
+int glb_level_tables_destroy(void *tables);
 
 int glb_launch_gram(const glb_gram_args *a, void *stream);
 /* the in-kernel block-mean removal covers hop = (n/16) << s, s = 0..4, with (n - hop) a
@@ -156,10 +170,12 @@ int glb_launch_floor_stats(const float *rows, long long stride, int nbins, long 
 int glb_launch_agc(const float *stats, long long nframes, long long first_frame, float overlap, int log_scale,
                    float *state, float *range, void *stream);
 /* rows -> 8-bit levels (pixel i = bin nbins-1-i) and optional RGB through a 256-entry palette.
- * range per frame, or fixed_range[2] for all frames. */
+ * range: device, per frame (autoscale); or fixed_range[2] = (display_max, display_min): HOST values for all
+ * frames, with the optional device look-up table level_lut (log scales). */
 int glb_launch_levels(const float *rows, long long stride, int nbins, long long nframes, const float *range,
-                      const float *fixed_range, int log_scale, float thr, const unsigned char *colortab,
-                      unsigned char *levels, unsigned char *rgb, void *stream);
+                      const float *fixed_range, int log_scale, float thr, const void *level_tables,
+                      const unsigned char *level_lut, const unsigned char *colortab, unsigned char *levels,
+                      unsigned char *rgb, void *stream);
 
 /* counters */
 unsigned long long glb_kernel_launches(void);

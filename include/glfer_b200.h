@@ -146,6 +146,18 @@ int glfer_gram_run_display_pcm16(glfer_gram_plan *plan, const short *pcm, long l
                                  long long first_frame, long long nframes, const glfer_display_config *dc,
                                  float *agc_state, unsigned char *levels, unsigned char *rgb, float *display_range);
 
+/* The level mapping alone on caller-provided rows (host memory): rows [nrows][nbins] -> levels [nrows][nbins],
+ * pixel i of a row = bin nbins-1-i.  range: [nrows][2] = (display_max, display_min) per row as main_window_draw
+ * holds them (dB in the log scales), or NULL for the fixed levels of dc (dc->autoscale is ignored). */
+int glfer_b200_map_levels(const float *rows, long long nrows, int nbins, const glfer_display_config *dc,
+                          const float *range, unsigned char *levels, int device);
+/* testing aid: 0 = glfer_gram_run_display always maps the levels in a second pass over float rows; 1 (default) =
+ * with a fixed display range and no averaging the spectrogram kernel writes the 8-bit levels itself */
+void glfer_b200_set_fused_levels(int on);
+/* the palettes of set_palette (g_main.c:649-762; glfer.h:47: 0 HSV, 1 THRESH, 2 COOL, 3 HOT, 4 BW, 5 BONE,
+ * 6 COPPER, 7 OTD): 256 RGB triplets into tab[768] */
+int glfer_palette(int palette, unsigned char *tab);
+
 /* ---- time-sharded multi-GPU run inside one process (one host thread per device) ----
  * Frames [0, nframes) are split into ndev contiguous ranges; device g gets samples
  * [F_g*hop - halo, F_{g+1}*hop) (halo = N - hop, plus (depth-1) frames when averaging);

@@ -425,7 +425,8 @@ def compute_floor(psd: np.ndarray):
     n = len(psd)
     srt = np.sort(psd.astype(np.float32))[::-1]
     floor = _seq_sum_f32(srt[int(n * 0.95):])
-    floor = np.float32(np.float32(floor / 0.05) / n)
+    floor = np.float32(float(floor) / 0.05)          # `floor_pwr /= 0.05`: float / double -> double, stored to float
+    floor = np.float32(floor / np.float32(n))        # `floor_pwr /= N2`: float / int -> float
     peak_bin = int(np.argmax(psd)) if psd.max() > 0 else 0
     return float(srt[0]), float(floor), float(max(psd.max(), 0.0)), peak_bin
 

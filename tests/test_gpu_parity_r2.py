@@ -216,3 +216,121 @@ def test_public_api_refuses_uncovered_span(gpu_api):
     with pytest.raises(gpu_api.GlferError):
         p.run(np.ascontiguousarray(x[: 2048 * 20]), origin=0, first_frame=0, nframes=30)
     assert full.shape[0] == 40
+
+
+# ------------------------------------------------------------------ display mapping (pinned to g_main.c)
+def _load_display_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mg2", os.path.join(HERE, "golden", "make_golden_r2.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.DISPLAY_CASES
+
+
+def _product_display(api, x, kw, fs=8000):
+    """the product's glfer_gram_run_display driven with one oracle.ref_gui.draw_rows case (C1 estimator)"""
+    st = kw.get("scale_type", 2)
+    log, max0 = st in (2, 3), st in (1, 3)
+    plan_kw = dict(n=1024, window_type=0, overlap=0.5, sub_mean=True)
+    if kw.get("averaging", 0):
+        binsize = np.float32(fs) / np.float32(kw["data_block_size"])
+        plan_kw.update(avg_mode=kw["averaging"], avg_depth=kw["avgsamples"], avg_minbin=int(np.float32(400.0) / binsize),
+                       avg_maxbin=int(np.float32(1200.0) / binsize), avg_max0=int(max0))
+    p = api.GramPlan(**plan_kw)
+    d = p.run_display(x, log_scale=log, autoscale=kw.get("autoscale", True), max_level_db=kw.get("max_level_db", -20.0),
+                      min_level_db=kw.get("min_level_db", -80.0), thr_level=kw.get("thr_level", 0.0))
+    r = p.run(x)
+    return d, r, plan_kw, log
+
+
+def test_display_levels_exact_on_own_rows_and_close_to_reference_fixture(gpu_api):
+    """Every display variant the compiled reference GUI unit produced a fixture for.  (1) The product's levels
+    EQUAL main_window_draw's arithmetic (restatement pinned bit-exact to g_main.c) applied to the product's own
+    float rows: floor statistics, AGC recurrence, integer-dB level buffer, threshold, clipping, bin reversal.
+    (2) Against the fixture itself (the reference's rows in, so PSD differences of ~1e-6 relative can move a
+    dB value across an integer) nearly every pixel is equal and none is more than one dB step away."""
+    cases = _load_display_cases()
+    for name, kw in cases.items():
+        d, r, plan_kw, log = _product_display(gpu_api, X8, kw)
+        shown = r["avg"] if plan_kw.get("avg_mode") else r["psd"]
+        lev, rng, state = O.display_levels(r["psd"], shown, 0.5, log, kw.get("autoscale", True),
+                                           kw.get("max_level_db", -20.0), kw.get("min_level_db", -80.0), kw.get("thr_level", 0.0))
+        assert np.array_equal(d["levels"], lev), (name, int((d["levels"] != lev).sum()))
+        if kw.get("autoscale", True):
+            assert np.array_equal(d["range"], rng), name
+        ref = G2[f"disp_{name}"]
+        diff = np.abs(d["levels"].astype(np.int32) - ref.astype(np.int32))
+        step = 255.0 / max(1.0, float(np.abs(rng[:, 0] - rng[:, 1]).min())) if log else 2.0
+        assert np.mean(diff == 0) > 0.995, (name, np.mean(diff == 0))
+        assert diff.max() <= np.ceil(step) + 1, (name, diff.max(), step)
+
+
+def test_display_fused_levels_equal_two_pass(gpu_api):
+    """Fixed display range, no averaging: the spectrogram kernel writes the 8-bit levels itself (no float row
+    reaches HBM).  The result must equal the two-pass path (float rows -> levels_kernel) byte for byte, in every
+    kernel family that can carry the fused epilogue."""
+    x = synth.qrss_stream(400000, fs=FS, seed=61, dot_s=0.2)
+    pcm = np.rint(x * 32768.0).astype(np.int16)
+    for kw in (dict(n=4096, window_type=0, overlap=0.5, sub_mean=True),                    # ring, metric shape
+               dict(n=4096, window_type=7, overlap=0.75, sub_mean=True),                   # ring, 75 %
+               dict(n=512, window_type=1, overlap=0.875, sub_mean=False),                  # ring, several groups per CTA
+               dict(n=16384, window_type=0, overlap=0.5, sub_mean=True),                   # ring, big frames
+               dict(n=4096, window_type=0, overlap=0.9, sub_mean=True),                    # general kernel (odd hop)
+               dict(n=2048, mode=1, overlap=0.5, sub_mean=True, mtm_w=4.0, mtm_kmax=5),    # ring multitaper
+               dict(n=32768, mode=1, overlap=0.5, sub_mean=True, mtm_w=8.0, mtm_kmax=3)):  # general multitaper
+        p = gpu_api.GramPlan(**kw)
+        for disp in (dict(log_scale=True, autoscale=False, max_level_db=-35.0, min_level_db=-75.0, thr_level=0.0),
+                     dict(log_scale=True, autoscale=False, max_level_db=-30.0, min_level_db=-90.0, thr_level=12.5),
+                     dict(log_scale=False, autoscale=False, max_level_db=-40.0, min_level_db=-70.0, thr_level=0.0)):
+            gpu_api.set_fused_levels(True)
+            n0 = gpu_api.kernel_launches()
+            fused = p.run_display(x, **disp)["levels"]
+            n_fused = gpu_api.kernel_launches() - n0
+            gpu_api.set_fused_levels(False)
+            n0 = gpu_api.kernel_launches()
+            two = p.run_display(x, **disp)["levels"]
+            n_two = gpu_api.kernel_launches() - n0
+            gpu_api.set_fused_levels(True)
+            assert np.array_equal(fused, two), (kw, disp, int((fused != two).sum()))
+            assert n_fused < n_two                                   # one kernel per chunk instead of two
+            assert fused.min() < fused.max()                         # the range actually exercises the mapping
+        # 16-bit PCM in, 8-bit levels out: the same bytes
+        lv = p.run_display(pcm, log_scale=True, autoscale=False, max_level_db=-35.0, min_level_db=-75.0)["levels"]
+        lf = p.run_display(x, log_scale=True, autoscale=False, max_level_db=-35.0, min_level_db=-75.0)["levels"]
+        assert np.array_equal(lv, lf)
+
+
+def test_integer_db_levels_match_host_libm_on_boundaries(gpu_api):
+    """(short) (10 log10 x) on the device equals the host's libm even ON the integer-dB boundaries: rows whose
+    bins are the floats right at, below and above every threshold 10^(j/10), plus zero, subnormals, the
+    float extremes, NaN and inf (x86 conversion overflow -> level of 0 dB)."""
+    vals = []
+    for j in range(-449, 386):
+        c = np.float32(10.0 ** (j / 10.0))
+        for k in range(-3, 4):
+            v = c
+            for _ in range(abs(k)):
+                v = np.nextafter(v, np.float32(np.inf if k > 0 else 0), dtype=np.float32)
+            vals.append(v)
+    vals += [0.0, -1.0, 1e-45, 3e-45, 1.1754942e-38, 1.1754944e-38, 3.4028235e38, 1.0, np.inf, np.nan]
+    rng = np.random.default_rng(8)
+    vals += list(np.exp(rng.uniform(-100, 80, 20000)).astype(np.float32))
+    nb = 1000
+    row = np.resize(np.array(vals, dtype=np.float32), (-(-len(vals) // nb), nb))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = 10.0 * np.log10(row.astype(np.float64))
+    s_ref = np.where(np.abs(d) < 2147483648.0, np.trunc(d), 0.0).astype(np.float32)
+    for mx, mn, thr in ((-20.0, -80.0, 0.0), (30.0, -300.0, 7.0), (380.0, -440.0, 0.0)):
+        got = gpu_api.map_levels(row, True, mx, mn, thr)
+        dmax, dmin = np.float32(10.0 * np.log10(float(np.float32(10.0 ** (mx / 10.0))))), np.float32(10.0 * np.log10(float(np.float32(10.0 ** (mn / 10.0)))))
+        t = np.float32(np.float32(thr) / 100.0)
+        fl = (np.float32(255) * ((s_ref - dmin) / (dmax - dmin))).astype(np.float32)
+        sc = (fl.astype(np.float64) - 255.0 * float(t)) / (1.0 - float(t))
+        want = np.where(fl.astype(np.float64) < 255.0 * float(t), 0, np.where(fl > 255, 255, sc)).astype(np.int64).astype(np.uint8)
+        assert np.array_equal(got, want[:, ::-1]), (mx, mn, thr, int((got != want[:, ::-1]).sum()))
+    # explicit per-row ranges (the autoscale form: no look-up table, arithmetic per pixel)
+    pr = np.tile(np.array([[-15.5, -95.25]], dtype=np.float32), (row.shape[0], 1))
+    got = gpu_api.map_levels(row, True, display_range=pr)
+    fl = (np.float32(255) * ((s_ref - pr[0, 1]) / (pr[0, 0] - pr[0, 1]))).astype(np.float32)
+    want = np.where(fl < 0, 0, np.where(fl > 255, 255, fl)).astype(np.int64).astype(np.uint8)
+    assert np.array_equal(got, want[:, ::-1])

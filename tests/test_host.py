@@ -123,3 +123,33 @@ def test_invalid_configs_are_rejected(api):
     for kw in (dict(n=1000), dict(n=65536), dict(n=1024, overlap=1.0), dict(n=1024, mode=1, mtm_kmax=32)):
         with pytest.raises(api.GlferError):
             api.GramPlan(**kw)
+
+
+def test_palettes_match_reference_fixture(api):
+    """glfer_palette vs set_palette of the compiled reference GUI unit (g_main.c:649-762)"""
+    g2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "glfer_ref_f64_r2.npz"))
+    for pn in range(8):
+        assert np.array_equal(api.palette(pn), g2["palettes"][pn]), pn
+
+
+def test_db_threshold_tables_reproduce_host_libm(api):
+    """host/levels.c: the number of thresholds <= x IS (short) (10 log10 x), for floats and doubles"""
+    import ctypes as C
+    lib = api.lib()
+    n = 390 + 450 + 1
+    tf = np.empty(n, dtype=np.float32)
+    td = np.empty(n, dtype=np.float64)
+    lib.glb_db_thresholds_f(tf.ctypes.data_as(C.c_void_p))
+    lib.glb_db_thresholds_d(td.ctypes.data_as(C.c_void_p))
+    assert np.all(np.diff(tf[np.isfinite(tf)]) >= 0) and np.all(np.diff(td) >= 0)
+    rng = np.random.default_rng(2)
+    x = np.exp(rng.uniform(-103, 88, 20000)).astype(np.float32)
+    x = np.concatenate([x, tf[np.isfinite(tf)], np.nextafter(tf[np.isfinite(tf)], np.float32(0))])
+    x = x[x > 0]
+    d = 10.0 * np.log10(x.astype(np.float64))
+    want = np.trunc(d).astype(np.int64)
+    got = np.searchsorted(tf, x, side="right") - 1 - 450
+    assert np.array_equal(got, want)
+    xd = np.exp(rng.uniform(-103, 88, 20000))
+    got = np.searchsorted(td, xd, side="right") - 1 - 450
+    assert np.array_equal(got, np.trunc(10.0 * np.log10(xd)).astype(np.int64))
