@@ -29,7 +29,8 @@ class GramConfig(C.Structure):
                 ("a", C.c_float), ("limiter", C.c_int), ("sub_mean", C.c_int), ("mtm_w", C.c_float),
                 ("mtm_kmax", C.c_int), ("avg_mode", C.c_int), ("avg_depth", C.c_int), ("avg_minbin", C.c_int),
                 ("avg_maxbin", C.c_int), ("avg_max0", C.c_int), ("avg_peakbin_init", C.c_int),
-                ("scale_db", C.c_int), ("device", C.c_int), ("lmp_av", C.c_int), ("zero_history", C.c_int)]
+                ("scale_db", C.c_int), ("device", C.c_int), ("lmp_av", C.c_int), ("avg_band_only", C.c_int),
+                ("zero_history", C.c_int)]
 
 
 class FftParams(C.Structure):          # include/fft.h (reference fft.h:51-63)
@@ -82,6 +83,7 @@ def lib() -> C.CDLL:
         l.glfer_gram_plan_destroy.argtypes = [C.c_void_p]
         l.glfer_gram_hop.argtypes = [C.c_void_p]
         l.glfer_gram_bins.argtypes = [C.c_void_p]
+        l.glfer_gram_avg_cols.argtypes = [C.c_void_p]
         l.glfer_gram_num_frames.argtypes = [C.c_void_p, C.c_longlong]
         l.glfer_gram_num_frames.restype = C.c_longlong
         l.glfer_gram_required_span.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_longlong),
@@ -215,9 +217,10 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 
 def make_config(n=1024, window_type=KAISER, overlap=0.0, mode=MODE_FFT, sub_mean=True, a=0.0, limiter=0,
                 mtm_w=4.0, mtm_kmax=7, avg_mode=NO_AVG, avg_depth=4, avg_minbin=0, avg_maxbin=0, avg_max0=0,
-                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4, zero_history=False) -> GramConfig:
+                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4, avg_band_only=False, zero_history=False) -> GramConfig:
     return GramConfig(mode, n, window_type, overlap, a, limiter, int(sub_mean), mtm_w, mtm_kmax, avg_mode, avg_depth,
-                      avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device, lmp_av, int(zero_history))
+                      avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device, lmp_av,
+                      int(avg_band_only), int(zero_history))
 
 
 class GramPlan:
@@ -231,6 +234,7 @@ class GramPlan:
         self.hop = lib().glfer_gram_hop(self._h)
         self.bins = lib().glfer_gram_bins(self._h)
         self.avg = self.cfg.avg_mode != NO_AVG
+        self.avg_cols = lib().glfer_gram_avg_cols(self._h)
 
     def close(self):
         if self._h:
@@ -268,7 +272,7 @@ class GramPlan:
         psd = out.get("psd") if "psd" in out else (np.empty((nframes, self.bins), np.float32) if want_psd else None)
         avg = ret = pk = var = None
         if self.avg:
-            avg = out.get("avg") if "avg" in out else np.empty((nframes, self.bins), np.float32)
+            avg = out.get("avg") if "avg" in out else np.empty((nframes, self.avg_cols), np.float32)
             ret = np.empty(nframes, np.float64)
             pk = np.empty(nframes, np.int32)
             var = np.empty(nframes, np.float64)
@@ -361,7 +365,7 @@ def run_sharded(samples: np.ndarray, ndev: int, devices=None, want_psd: bool = T
     psd = np.empty((nframes, bins), np.float32) if want_psd else None
     avg = ret = pk = var = None
     if cfg.avg_mode != NO_AVG:
-        avg = np.empty((nframes, bins), np.float32)
+        avg = np.empty((nframes, cfg.avg_maxbin - cfg.avg_minbin if cfg.avg_band_only else bins), np.float32)
         ret = np.empty(nframes, np.float64)
         pk = np.empty(nframes, np.int32)
         var = np.empty(nframes, np.float64)

@@ -647,7 +647,9 @@ __device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[1
 }
 
 // The same row as 8-bit display levels: pixel i shows bin M - i (g_main.c:1193-1201), so the bins a warp
-// stores together are still 32 consecutive bytes.
+// stores together are still 32 consecutive bytes.  Only compiled into the LEV = true instantiations of the
+// ring kernel: as a run-time branch of the one kernel it cost the float-row path registers (spills at
+// N = 1024, +4 % at N = 16384).
 template <int M>
 __device__ __forceinline__ void store_levels(unsigned char *lrow, int t, const float (&yv)[17], const LevelMap &lm) {
   constexpr int T = M / kPoints;
@@ -691,7 +693,7 @@ template <int M, bool MULTI> struct RingGeo {
 #endif
   static constexpr int MINB = BIG ? 1 : ((MULTI && GLB_MULTI_MINB > 0 && Geo<M>::THREADS == 128) ? GLB_MULTI_MINB : Geo<M>::MINB);
 };
-template <int M, bool MULTI, int QSC>
+template <int M, bool MULTI, int QSC, bool LEV>
 __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gram_ring_kernel(const KParams p) {
   using GeoM = Geo<M>;
   constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
@@ -862,8 +864,10 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       if (!MULTI) {
         // the row leaves the registers here: one store per bin, streaming (written once, never
         // re-read by this kernel); the display levels and the dB conversion are uniform branches
-        if (p.levels != nullptr && active) store_levels<M>(lev_ptr, t, yv, p.lm);
-        if (p.rows != nullptr) {
+        if constexpr (LEV) {
+          if (active) store_levels<M>(lev_ptr, t, yv, p.lm);
+        }
+        if (!LEV || p.rows != nullptr) {
           if (db) {
 #pragma unroll
             for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
@@ -875,12 +879,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     if (MULTI && active) {
       float *row = row_ptr;
       const bool db = p.rows_db != 0;
-      if (p.levels != nullptr) {
-#pragma unroll
-        for (int slot = 0; slot < 17; slot++)
-          if (slot < 16 || t == 0) lev_ptr[M - slot_bin<M>(t, slot)] = map_level(acc[slot], p.lm);
-      }
-      if (p.rows != nullptr) {
+      if constexpr (LEV) store_levels<M>(lev_ptr, t, acc, p.lm);
+      if (!LEV || p.rows != nullptr) {
 #pragma unroll
         for (int slot = 0; slot < 17; slot++) {
           if (slot < 16 || t == 0) {
@@ -1343,11 +1343,15 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
       if (smem <= 227 * 1024) {
         // 50 % and 75 % overlap have kernels with the ring geometry folded in
         void (*rk)(const KParams) = nullptr;
-        if (qs == 3) rk = multi ? gram_ring_kernel<M, true, 3> : gram_ring_kernel<M, false, 3>;
-        else if (qs == 2) rk = multi ? gram_ring_kernel<M, true, 2> : gram_ring_kernel<M, false, 2>;
-        else rk = multi ? gram_ring_kernel<M, true, -1> : gram_ring_kernel<M, false, -1>;
-        static thread_local int occ_ring[2][5][64];
-        int &occ = occ_ring[multi ? 1 : 0][qs][dev & 63];
+        const bool lev = kp.levels != nullptr;       // 8-bit display levels: a second set of instantiations
+        if (qs == 3) rk = multi ? (lev ? gram_ring_kernel<M, true, 3, true> : gram_ring_kernel<M, true, 3, false>)
+                                : (lev ? gram_ring_kernel<M, false, 3, true> : gram_ring_kernel<M, false, 3, false>);
+        else if (qs == 2) rk = multi ? (lev ? gram_ring_kernel<M, true, 2, true> : gram_ring_kernel<M, true, 2, false>)
+                                     : (lev ? gram_ring_kernel<M, false, 2, true> : gram_ring_kernel<M, false, 2, false>);
+        else rk = multi ? (lev ? gram_ring_kernel<M, true, -1, true> : gram_ring_kernel<M, true, -1, false>)
+                        : (lev ? gram_ring_kernel<M, false, -1, true> : gram_ring_kernel<M, false, -1, false>);
+        static thread_local int occ_ring[2][2][5][64];
+        int &occ = occ_ring[lev ? 1 : 0][multi ? 1 : 0][qs][dev & 63];
         if (occ == 0) {
           // opt in to the device maximum once: the ring size (hence the launch's smem) varies with the overlap
           CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(256) avg_kernel(const glb_avg_args a, int chun
     OutT *orow = out_base + fl * a.out_stride;
     double var = 0.0;
     int cnt = 0;
-    for (int b = tid; b < a.nbins; b += 256) {
+    const int ob0 = a.band_only ? a.minbin : 0, ob1 = a.band_only ? (a.maxbin < a.nbins ? a.maxbin : a.nbins) : a.nbins;
+    for (int b = ob0 + tid; b < ob1; b += 256) {
       double y = 1e-15;
       if (b >= a.minbin && b < a.maxbin) {
         const double c = cum[b - a.minbin];
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(256) avg_kernel(const glb_avg_args a, int chun
         }
       }
       if (sizeof(OutT) == 4 && a.rows_db) y = 10.0 * log10(y);
-      orow[b] = (OutT) y;
+      orow[b - ob0] = (OutT) y;
     }
     if (a.mode == 1) {
 #pragma unroll
@@ -559,8 +560,11 @@ __global__ void __launch_bounds__(256) avg_direct_kernel(const glb_avg_args a) {
         for (int b = lo + lane; b < hi; b += 32) orow[b] = fill;
       }
     };
-    fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
-    if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
+    if (!a.band_only) {
+      fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
+      if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
+    }
+    const int ob0 = a.band_only ? a.minbin : 0;
     for (int b = a.minbin + lane; b < a.maxbin && b < a.nbins; b += 32) {
       double y;
       const double c = window_sum(b);
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(256) avg_direct_kernel(const glb_avg_args a) {
         y = 1e-15;
       }
       if (out_db) y = 10.0 * log10(y);
-      orow[b] = (OutT) y;
+      orow[b - ob0] = (OutT) y;
     }
     if (a.mode == 1) {
 #pragma unroll

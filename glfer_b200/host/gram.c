@@ -52,6 +52,7 @@ typedef struct {
 struct glfer_gram_plan {
   glfer_gram_config cfg;
   int hop, bins, ntapers;
+  int avg_cols;         /* columns of an averaged row: bins, or the band when cfg.avg_band_only */
   float taper_scale;
   float *h_window;      /* unit-energy window as compute_window leaves it */
   double *h_tapers;     /* MTM: [ntapers][n] */
@@ -147,6 +148,7 @@ void glfer_gram_config_default(glfer_gram_config *c)
 int glb_plan_sub_mean(const glfer_gram_plan *p) { return p->cfg.sub_mean; }
 int glfer_gram_hop(const glfer_gram_plan *p) { return p->hop; }
 int glfer_gram_bins(const glfer_gram_plan *p) { return p->bins; }
+int glfer_gram_avg_cols(const glfer_gram_plan *p) { return p->avg_cols; }
 long long glfer_gram_num_frames(const glfer_gram_plan *p, long long nsamples) { return nsamples / p->hop; }
 
 static long long halo_frames(const glfer_gram_plan *p, long long first_frame)
@@ -238,6 +240,8 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
   p->cfg = *cfg;
   p->hop = hop;
   p->bins = cfg->n / 2 + 1;
+  p->avg_cols = (cfg->avg_mode != GLFER_NO_AVG && cfg->avg_band_only) ? cfg->avg_maxbin - cfg->avg_minbin : p->bins;
+  if (p->avg_cols < 1) p->avg_cols = 1;
   const int n = cfg->n;
   p->taper_scale = (float) (1.0 / (2.0 * sqrt((double) n)));
   p->h_window = malloc(sizeof(float) * n);
@@ -393,7 +397,7 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   if (s->time_gram) TRY(glb_event_record(s->ev3, s->stream));
 
   if (c->avg_mode != GLFER_NO_AVG) {
-    TRY(ensure((void **) &s->d_avg, &s->avg_cap, (size_t) nframes * p->bins, sizeof(float)));
+    TRY(ensure((void **) &s->d_avg, &s->avg_cap, (size_t) nframes * p->avg_cols, sizeof(float)));
     if ((size_t) nframes > s->scal_cap) {
       glb_free(s->d_ret); glb_free(s->d_var); glb_free(s->d_cand); glb_free(s->d_peak);
       s->d_ret = s->d_var = NULL; s->d_cand = s->d_peak = NULL; s->scal_cap = 0;
@@ -418,7 +422,8 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
     a.nframes = nframes;
     a.out_double = 0;
     a.avg_rows = s->d_avg;
-    a.out_stride = p->bins;
+    a.out_stride = p->avg_cols;
+    a.band_only = c->avg_band_only;
     a.rows_db = c->scale_db;
     a.ret = s->d_ret;
     a.peak_cand = cand_out ? cand_out : s->d_cand;
@@ -462,7 +467,7 @@ static int fetch_slot(glfer_gram_plan *p, slot_t *s, float *psd_rows, float *avg
     TRY(glb_memcpy_d2h(psd_rows, src, sizeof(float) * nf * p->bins, s->stream));
   }
   if (p->cfg.avg_mode != GLFER_NO_AVG) {
-    if (avg_rows) TRY(glb_memcpy_d2h(avg_rows, s->d_avg, sizeof(float) * nf * p->bins, s->stream));
+    if (avg_rows) TRY(glb_memcpy_d2h(avg_rows, s->d_avg, sizeof(float) * nf * p->avg_cols, s->stream));
     if (avg_ret) TRY(glb_memcpy_d2h(avg_ret, s->d_ret, sizeof(double) * nf, s->stream));
     if (avg_peakbin) TRY(glb_memcpy_d2h(avg_peakbin, s->d_peak, sizeof(int) * nf, s->stream));
     if (avg_variance) TRY(glb_memcpy_d2h(avg_variance, s->d_var, sizeof(double) * nf, s->stream));
@@ -602,7 +607,7 @@ static int run_impl(glfer_gram_plan *p, const float *samples, const short *pcm, 
     rc = exec_slot(p, s, c0, cn, defer_carry ? p->d_cand_all + done : NULL, NULL);
     if (rc) break;
     rc = fetch_slot(p, s, psd_rows ? psd_rows + (size_t) done * p->bins : NULL,
-                    avg_rows ? avg_rows + (size_t) done * p->bins : NULL, avg_ret ? avg_ret + done : NULL,
+                    avg_rows ? avg_rows + (size_t) done * p->avg_cols : NULL, avg_ret ? avg_ret + done : NULL,
                     (avg_peakbin && !defer_carry) ? avg_peakbin + done : NULL,
                     avg_variance ? avg_variance + done : NULL);
     done += cn;
@@ -656,6 +661,8 @@ static int run_display_impl(glfer_gram_plan *p, const float *samples, const shor
   if (nframes < 0 || first_frame < 0) return fail(GLFER_EINVAL, "negative frame range");
   if (p->cfg.scale_db) return fail(GLFER_EINVAL, "display mapping needs linear rows (scale_db = 0)");
   if (rgb && !dc->colortab) return fail(GLFER_EINVAL, "RGB output needs a 256-entry palette");
+  if (p->cfg.avg_mode != GLFER_NO_AVG && p->cfg.avg_band_only)
+    return fail(GLFER_EINVAL, "the display shows whole averaged rows: plan must not be avg_band_only");
   if (dc->autoscale && first_frame > 0 && !agc_state)
     return fail(GLFER_EINVAL, "autoscale from frame > 0 needs the carried AGC state");
   if (nframes == 0) return 0;
@@ -850,9 +857,9 @@ static void *shard_main(void *arg)
   glfer_gram_plan *p = NULL;
   j->rc = glfer_gram_plan_create(&j->cfg, &p);
   if (j->rc == 0) {
-    const size_t off = (size_t) j->first * j->bins;
+    const size_t off = (size_t) j->first * j->bins, aoff = (size_t) j->first * p->avg_cols;
     j->rc = glfer_gram_run(p, j->samples, 0, j->nsamples, j->first, j->count, j->psd_rows ? j->psd_rows + off : NULL,
-                           j->avg_rows ? j->avg_rows + off : NULL, j->avg_ret ? j->avg_ret + j->first : NULL,
+                           j->avg_rows ? j->avg_rows + aoff : NULL, j->avg_ret ? j->avg_ret + j->first : NULL,
                            j->avg_peakbin ? j->avg_peakbin + j->first : NULL,
                            j->avg_variance ? j->avg_variance + j->first : NULL);
   }

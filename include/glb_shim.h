@@ -138,6 +138,7 @@ typedef struct {
   int peakbin_init;            /* caller's *peakbin before the first frame */
   int *unresolved;             /* device counter: frames whose variance needed an unknown carried peakbin */
   int sequential;              /* 1: one CTA walks all frames in order (exact carry; slow) */
+  int band_only;               /* 1: output rows hold bins [minbin, maxbin) only (column j = bin minbin + j); no 1e-15 fill */
 } glb_avg_args;
 
 int glb_launch_avg(const glb_avg_args *a, void *stream);

@@ -61,6 +61,10 @@ typedef struct {
   int lmp_av;          /* opt.lmp_av: rows in the LMP ring (>= 2); the "psd" rows of an LMP plan are the
                           statistic of lmp_do; window forced rectangular (source.c:395), RA9MB / limiter
                           do not reach the spectrum (lmp.c:112-114); no frame averaging in this mode */
+  int avg_band_only;   /* 1: averaged rows hold the band only, [nframes][avg_maxbin - avg_minbin] (column j = bin
+                          avg_minbin + j).  The reference fills the rest of avg[] with the constant 1e-15
+                          (avg.c:152-153); writing and shipping that constant is most of the cost of the averaging
+                          pass when the band is a few dozen bins out of thousands */
   int zero_history;    /* 1: glfer.first_buffer stays TRUE, i.e. prepare_audio zeroes the N-hop history on EVERY
                           frame (fft.c:99-108).  That is what the reference GUI does with opt.autoscale == 0:
                           first_buffer is cleared only inside `if (opt.autoscale)` (g_main.c:1111-1120).
@@ -83,6 +87,7 @@ void glfer_gram_plan_destroy(glfer_gram_plan *plan);
 
 int glfer_gram_hop(const glfer_gram_plan *plan);
 int glfer_gram_bins(const glfer_gram_plan *plan);                       /* n/2 + 1 */
+int glfer_gram_avg_cols(const glfer_gram_plan *plan);                   /* columns of an averaged row: bins, or the band (avg_band_only) */
 long long glfer_gram_num_frames(const glfer_gram_plan *plan, long long nsamples);  /* nsamples / hop */
 /* stream span [lo, hi) the frames [first_frame, first_frame + nframes) read (lo may be
  * negative: indices < 0 are the zero history) */
