@@ -1,0 +1,189 @@
+// gram_big.cu -- the spectrogram kernel for the big frames (N = 16384, 32768) on the 32-points-per-thread
+// FFT core (fft_big.cuh): overlapped-frame gather -> block-mean removal -> taper -> real FFT in three
+// passes (two shared-memory exchanges) -> |X|^2 -> [10 log10] -> one PSD row per frame.
+//
+// Why a second kernel family: at these sizes the 16-point core needs four passes, 512 threads and 74 KB of
+// exchange buffer per frame, so with its 64 KB TMA ring only ONE frame fits an SM and the shared-memory
+// pipe (three exchanges) bounds it (N = 16384: 34 % of the HBM roofline, round 1).  Here a frame is 256
+// threads x 32 points (N = 16384), 70 KB of shared memory and no ring: the hop blocks are read straight
+// from global memory -- the new block was pulled into L2 by prefetch.global.L2 one frame earlier, the
+// older blocks were read by this very CTA one frame ago and sit in L2 -- so two CTAs (two frames in
+// flight) fit an SM, with a third fewer shared-memory wavefronts per frame.  Every sample still crosses
+// HBM once.
+//
+// Geometry: hop = N / NBLK, NBLK = 1, 2, 4 (0 %, 50 %, 75 % overlap), periodogram, no RA9MB / limiter;
+// everything else stays on the 16-point kernels (gram_common.cuh).
+#include "gram_common.cuh"
+#include "fft_big.cuh"
+
+template <int M> struct BigGeo {
+  static constexpr int T = Big<M>::T, N = 2 * M, NW = T / 32;
+  static constexpr size_t BUF_BYTES = (size_t) Big<M>::BUF * sizeof(float2);
+  static constexpr size_t TW_BYTES = (size_t) Big<M>::TW1 * sizeof(float2);
+  static constexpr size_t RED_BYTES = (size_t) 4 * NW * sizeof(float);
+  static constexpr size_t SMEM = BUF_BYTES + TW_BYTES + RED_BYTES;
+  static constexpr int MINB = (T <= 256) ? 2 : 1;
+};
+
+template <int M, int NBLK>
+__global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(const KParams p) {
+  using G = BigGeo<M>;
+  constexpr int T = G::T, N = G::N, NW = G::NW, QB = kBP / NBLK;     // QB registers (float2) per hop block
+  constexpr int HOP = N / NBLK;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+  float2 *tw1 = reinterpret_cast<float2 *>(smem_raw + G::BUF_BYTES);
+  float *red = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES);
+  const int t = threadIdx.x;
+
+  // middle-pass twiddles exp(-2 pi i k r / (32 R1)) = roots[16 k r], one copy per CTA
+  for (int i = t; i < Big<M>::TW1; i += T) tw1[i] = p.roots[(i & 31) * ((i >> 5) + 1) * 16];
+  __syncthreads();
+
+  const long long fb = (long long) blockIdx.x * p.frames_per_group;
+  const int nact = (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group);
+  const bool sub = p.fused_mean != 0;
+  const bool db = p.rows_db != 0;
+  const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers) + t;
+  float *row_ptr = p.rows + fb * p.row_stride;
+  long long s0 = (p.first_frame + fb) * (long long) HOP - (N - HOP);   // stream index of the frame's first sample
+
+  for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride) {
+    float2 v[kBP];
+    const long long rel = s0 - p.origin;
+    if (s0 >= 0 && rel >= 0 && rel + N <= p.count) {
+      const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel) + t;
+#pragma unroll
+      for (int q = 0; q < kBP; q++) v[q] = ldg2(src + T * q);
+    } else {
+      // edge frame: zero history before the stream start (fft.c:103-108), nothing past the staged span
+#pragma unroll
+      for (int q = 0; q < kBP; q++) {
+        float y[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const long long s = s0 + 2 * (t + T * q) + e;
+          const long long r = s - p.origin;
+          y[e] = (s >= 0 && r >= 0 && r < p.count) ? __ldg(p.samples + r) : 0.f;
+        }
+        v[q] = make_float2(y[0], y[1]);
+      }
+    }
+    if (it + 1 < nact) {
+      // the next frame's new hop block towards L2 while this frame is transformed (one 128-byte line per
+      // thread and round); the older blocks of that frame are this frame's newer ones
+      const long long nb = rel + N;
+      for (int i = t * 32; i < HOP; i += T * 32)
+        if (nb + i >= 0 && nb + i < p.count) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.samples + nb + i));
+    }
+    if (sub) {
+      // block means (prepare_audio, fft.c:86-96): block b = registers [b QB, (b + 1) QB).  The summation tree
+      // of a block does not depend on its position in the frame, so its mean is the same bits in every
+      // frame (and time shard) it appears in; zero history sums to a zero mean.
+      float bs[NBLK];
+#pragma unroll
+      for (int b = 0; b < NBLK; b++) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = b * QB; q < (b + 1) * QB; q++) s += v[q].x + v[q].y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((t & 31) == 0) red[b * NW + (t >> 5)] = s;
+      }
+      __syncthreads();                 // also orders the previous frame's last-pass loads before this frame's stores
+#pragma unroll
+      for (int b = 0; b < NBLK; b++) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += red[b * NW + w];
+        bs[b] = s * p.inv_hop_mean;
+      }
+#pragma unroll
+      for (int q = 0; q < kBP; q++) v[q] = sub2(v[q], bc(bs[q / QB]));
+    }
+#pragma unroll
+    for (int q = 0; q < kBP; q++) v[q] = mul2(v[q], ld_taper(w2 + T * q));
+    big_pass0(v);
+    if (!sub) __syncthreads();         // (A) the previous frame's last pass has been read by all
+    big_scatter0<M>(v, t, buf);
+    __syncthreads();
+    big_load1<M>(v, t, buf);
+    big_pass1<M>(v, t, tw1);
+    __syncthreads();                   // every thread has read before anyone overwrites
+    big_scatter1<M>(v, t, buf);
+    __syncthreads();
+    BigLast L;
+    big_load_last<M>(L, t, p.roots, p.vtab);
+    big_load2<M>(v, t, buf);
+    big_pass2<M>(v, t, L);
+    float yv[33];
+    yv[32] = 1.f;                      // only thread 0 has a 33rd bin
+    auto sink = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
+    if (t < 32) big_emit<M, true>(v, t, L, sink);      // warp-uniform: only warp 0 pays for thread 0's re-ordering
+    else big_emit<M, false>(v, t, L, sink);
+    if (db) {
+#pragma unroll
+      for (int s = 0; s < 33; s++) yv[s] = 10.f * log10f(yv[s]);
+    }
+    // the row leaves the registers: slot 2 rp is bin k, slot 2 rp + 1 is bin M - k, k = t + rp 2T (thread 0:
+    // rp 2T, then T + (rp - 8) 2T); consecutive threads store consecutive bins
+    const int kh = big_khi<M>(t) - 16 * T;
+    float *ra = row_ptr + t, *rb = row_ptr + (M - t), *rah = row_ptr + kh, *rbh = row_ptr + (M - kh);
+#pragma unroll
+    for (int rp = 0; rp < 16; rp++) {
+      st_row((rp < 8 ? ra : rah) + rp * 2 * T, yv[2 * rp]);
+      st_row((rp < 8 ? rb : rbh) - rp * 2 * T, yv[2 * rp + 1]);
+    }
+    if (t == 0) st_row(row_ptr + M / 2, yv[32]);
+  }
+}
+
+template <int M, int NBLK>
+static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
+  using G = BigGeo<M>;
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  auto kern = gram_big_kernel<M, NBLK>;
+  static thread_local int occ_cache[64];
+  int &occ = occ_cache[dev & 63];
+  if (occ == 0) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) G::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::T, G::SMEM));
+    if (occ < 1) occ = 1;
+  }
+  // resident grid: every CTA walks a contiguous run of frames (its older hop blocks stay in L2)
+  long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ;
+  if (groups > kp.nframes) groups = kp.nframes;
+  if (groups < 1) groups = 1;
+  KParams k = kp;
+  k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
+  const long long ctas = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
+  kern<<<(unsigned) ctas, G::T, G::SMEM, st>>>(k);
+  CU(cudaGetLastError());
+  g_launches++;
+  g_last_family = 5;
+  return GLB_OK;
+}
+
+template <int M>
+static int launch_big_m(const KParams &kp, int groups_hint, cudaStream_t st) {
+  const int n = 2 * M;
+  if (kp.hop == n) return launch_big<M, 1>(kp, groups_hint, st);
+  if (kp.hop == n / 2) return launch_big<M, 2>(kp, groups_hint, st);
+  if (kp.hop == n / 4) return launch_big<M, 4>(kp, groups_hint, st);
+  return -1;
+}
+
+// -1: this launch is not one the big-frame kernel serves (the caller goes on to the 16-point families)
+int glb_gram_big(int m, const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
+  if (multi || kp.rows == nullptr || kp.levels != nullptr || kp.spectrum != nullptr || kp.means != nullptr) return -1;
+  if (kp.ra9mb_a > 0.f || kp.limiter != 0 || kp.zero_hist) return -1;
+  // pairs of samples are read as one 64-bit word: even offsets, 8-byte aligned base
+  if ((kp.hop & 1) || (kp.origin & 1) || (reinterpret_cast<uintptr_t>(kp.samples) & 7)) return -1;
+  switch (m) {
+    case 8192: return launch_big_m<8192>(kp, groups_hint, st);
+    case 16384: return launch_big_m<16384>(kp, groups_hint, st);
+    default: return -1;
+  }
+}

@@ -273,7 +273,11 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   else if (g_kernel_pref == 3) allow = 7;
   else if (g_kernel_pref == 4) allow = 11;
   const int m = a->n / 2;
-  int rc = glb_gram_part_0(m, k, multi, a->groups_hint, st, allow);
+  int rc = -1;
+  // big frames: the 32-points-per-thread kernel (family 5) unless another family is asked for
+  if ((g_kernel_pref == 0 || g_kernel_pref == 5) && !g_force_generic) rc = glb_gram_big(m, k, multi, a->groups_hint, st);
+  if (rc != -1) return rc;
+  rc = glb_gram_part_0(m, k, multi, a->groups_hint, st, allow);
   if (rc == -1) rc = glb_gram_part_1(m, k, multi, a->groups_hint, st, allow);
   if (rc == -1) rc = glb_gram_part_2(m, k, multi, a->groups_hint, st, allow);
   if (rc == -1) rc = glb_gram_part_3(m, k, multi, a->groups_hint, st, allow);
@@ -802,75 +806,143 @@ extern "C" int glb_launch_halfcomplex_psd(const float *hc, int n, float *psd, fl
 }
 
 // ------------------------------------------------------------------------- floor statistics
-// compute_floor (fft.c:240-294) per PSD row: one CTA sorts the row descending in shared
-// memory (bitonic network over the next power of two, padded with -inf), then takes the
-// head (sig), sums the tail from index (int)(n * 0.95) (floor) and scans for the first
-// maximum (peak value and bin; peak stays (0, 0) when no bin is > 0, fft.c:284-291).
-__global__ void __launch_bounds__(512) floor_stats_kernel(const float *__restrict__ rows, long long stride, int nbins,
-                                                          int npow2, float *__restrict__ stats) {
-  extern __shared__ float srt[];
-  __shared__ float red_v[16];
-  __shared__ int red_i[16];
-  const float *row = rows + (long long) blockIdx.x * stride;
-  const int tid = threadIdx.x;
-  float best = 0.f;
-  int best_i = 0x7fffffff;
-  for (int i = tid; i < npow2; i += 512) {
-    const float v = (i < nbins) ? row[i] : -INFINITY;
-    srt[i] = v;
-    if (i < nbins && v > best) { best = v; best_i = i; }   // thread's bins ascend: first max
-  }
-  __syncthreads();
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < npow2; i += 512) {
-        const int l = i ^ j;
-        if (l > i) {
-          const float a = srt[i], b = srt[l];
-          const bool desc = ((i & k) == 0);
-          if (desc ? (a < b) : (a > b)) { srt[i] = b; srt[l] = a; }
+// compute_floor (fft.c:240-294) per PSD row.  The reference sorts the whole row (qsort, descending) only to
+// take its head (sig = largest bin) and to add up its tail: floor = (sum of the entries from index
+// (int)(n * 0.95) on, i.e. the K = n - (int)(0.95 n) smallest bins, added in DESCENDING order into a float)
+// / 0.05 / n.  One warp per row does exactly that without sorting the row: a four-pass radix select on
+// the order-preserving integer image of the floats finds the K-th smallest value, the K smallest bins
+// are compacted into shared memory (ties are equal values: which of them are taken does not matter),
+// sorted there (bitonic, K <= 1024 entries) and summed by one lane in the reference's order, so the
+// float sum rounds identically.  The first maximum (peak value and bin; (0, 0) when no bin is > 0,
+// fft.c:284-291) comes from a warp reduction.  (The first version bitonic-sorted all 4096 padded
+// entries of every row with a 512-thread CTA: 78 block barriers per row.)
+constexpr int kFsWarps = 8;            // rows per CTA
+constexpr int kFsMaxK = 1024;          // n <= 20480 bins... n = 16385 gives K = 820
+
+__device__ __forceinline__ unsigned fs_key(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);       // ascending keys <=> ascending floats
+}
+
+__global__ void __launch_bounds__(32 * kFsWarps) floor_stats_kernel(const float *__restrict__ rows, long long stride, int nbins,
+                                                                  long long nrows, float *__restrict__ stats) {
+  __shared__ int s_hist[kFsWarps][256];
+  __shared__ float s_cand[kFsWarps][kFsMaxK];
+  __shared__ int s_cnt[kFsWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int *hist = s_hist[w];
+  float *cand = s_cand[w];
+  const int K = nbins - (int) (nbins * 0.95);             // entries of the sorted row from index (int)(n * 0.95) on
+  for (long long r = (long long) blockIdx.x * kFsWarps + w; r < nrows; r += (long long) gridDim.x * kFsWarps) {
+    const float *row = rows + r * stride;
+    // ---- head of the sorted row and the first maximum
+    float best = 0.f, top = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int i = lane; i < nbins; i += 32) {
+      const float v = row[i];
+      if (v > best) { best = v; best_i = i; }               // a lane's bins ascend: its first maximum
+      top = fmaxf(top, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+      top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+    }
+    // ---- radix select: key of the K-th smallest bin, most significant byte first
+    unsigned prefix = 0;
+    int want = K;                                           // rank (1-based, ascending) still to be located
+    for (int pass = 3; pass >= 0 && K > 0; --pass) {
+      for (int b = lane; b < 256; b += 32) hist[b] = 0;
+      __syncwarp();
+      const int sh = 8 * pass;
+      const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (sh + 8));
+      for (int i = lane; i < nbins; i += 32) {
+        const unsigned k = fs_key(row[i]);
+        if ((k & himask) == (prefix & himask)) atomicAdd(&hist[(k >> sh) & 255u], 1);
+      }
+      __syncwarp();
+      // lane l owns digits 8 l .. 8 l + 7
+      int loc[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { loc[j] = hist[8 * lane + j]; tot += loc[j]; }
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      int below = incl - tot;                               // bins in digits before this lane's
+      int digit = -1, below_d = 0;
+      if (below < want && want <= incl) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (digit < 0 && want <= below + loc[j]) { digit = 8 * lane + j; below_d = below; }
+          if (digit < 0) below += loc[j];
         }
       }
-      __syncthreads();
+      const unsigned who = __ballot_sync(0xffffffffu, digit >= 0);
+      const int src = __ffs(who) - 1;
+      digit = __shfl_sync(0xffffffffu, digit, src);
+      below_d = __shfl_sync(0xffffffffu, below_d, src);
+      prefix |= (unsigned) digit << sh;
+      want -= below_d;
+      __syncwarp();
     }
-  }
-  // tail sum (lowest 5 %): `for (i = N2 * 0.95; i < N2; i++) floor_pwr += tmp_buf[i]` is a float
-  // accumulation in index order (fft.c:271-272); one thread repeats it so the sum rounds the same
-  const int start = (int) (nbins * 0.95);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-  }
-  if ((tid & 31) == 0) { red_v[tid >> 5] = best; red_i[tid >> 5] = best_i; }
-  __syncthreads();
-  if (tid == 0) {
-    float fsum = 0.f, pv = 0.f;
-    int pi = 0x7fffffff;
-    for (int i = start; i < nbins; i++) fsum += srt[i];
-    for (int w = 0; w < 16; w++) {
-      if (red_v[w] > pv || (red_v[w] == pv && red_i[w] < pi)) { pv = red_v[w]; pi = red_i[w]; }
+    // ---- the K smallest bins: every key below the threshold, and `want` of the bins equal to it
+    if (lane == 0) s_cnt[w] = 0;
+    __syncwarp();
+    int np2 = 1;
+    while (np2 < K) np2 <<= 1;
+    const int n_lt = K - want;
+    for (int i = lane; i < nbins && K > 0; i += 32) {
+      const float v = row[i];
+      if (fs_key(v) < prefix) cand[atomicAdd(&s_cnt[w], 1)] = v;
     }
-    float fl = (float) ((double) fsum / 0.05);          // `floor_pwr /= 0.05`: double division, stored to float
-    fl = fl / (float) nbins;                             // `floor_pwr /= N2`
-    float *o = stats + (long long) blockIdx.x * 4;
-    o[0] = srt[0];
-    o[1] = fl;
-    o[2] = (pv > 0.f) ? pv : 0.f;
-    o[3] = (pv > 0.f) ? (float) pi : 0.f;
+    __syncwarp();
+    float thr_val = 0.f;
+    {
+      const unsigned b = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
+      thr_val = __uint_as_float(b);
+    }
+    for (int i = n_lt + lane; i < np2; i += 32) cand[i] = (i < K) ? thr_val : -INFINITY;   // ties, then padding
+    __syncwarp();
+    for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < np2; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const float a = cand[i], b = cand[l];
+            const bool desc = ((i & k2) == 0);
+            if (desc ? (a < b) : (a > b)) { cand[i] = b; cand[l] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      float fsum = 0.f;
+      for (int i = 0; i < K; i++) fsum += cand[i];          // `floor_pwr += tmp_buf[i]`, descending order (fft.c:271-272)
+      float fl = (float) ((double) fsum / 0.05);            // `floor_pwr /= 0.05`: double division, stored to float
+      fl = fl / (float) nbins;                              // `floor_pwr /= N2`
+      float *o = stats + r * 4;
+      o[0] = top;
+      o[1] = fl;
+      o[2] = (best > 0.f) ? best : 0.f;
+      o[3] = (best > 0.f) ? (float) best_i : 0.f;
+    }
+    __syncwarp();
   }
 }
 
 extern "C" int glb_launch_floor_stats(const float *rows, long long stride, int nbins, long long nrows, float *stats,
                                       void *stream) {
   if (nrows <= 0) return GLB_OK;
-  if (nbins < 1 || nbins > 32768) { glb_set_error("floor_stats: row too wide"); return GLB_EINVAL; }
-  int np2 = 1;
-  while (np2 < nbins) np2 <<= 1;
-  const size_t smem = (size_t) np2 * sizeof(float);
-  CU(cudaFuncSetAttribute(floor_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  floor_stats_kernel<<<(unsigned) nrows, 512, smem, (cudaStream_t) stream>>>(rows, stride, nbins, np2, stats);
+  if (nbins < 1 || nbins - (int) (nbins * 0.95) > kFsMaxK) { glb_set_error("floor_stats: row too wide"); return GLB_EINVAL; }
+  long long ctas = (nrows + kFsWarps - 1) / kFsWarps;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  floor_stats_kernel<<<(unsigned) ctas, 32 * kFsWarps, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nrows, stats);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;
@@ -880,34 +952,40 @@ extern "C" int glb_launch_floor_stats(const float *rows, long long stride, int n
 // main_window_draw, g_main.c:1109-1229, minus the GTK drawing: AGC of the display range from
 // the per-row floor statistics, then level -> 8-bit palette index (-> RGB).
 //
-// agc_kernel: the display range is a recurrence over frames in mixed double/float arithmetic
-// with a rounding to float at every step (static float display_max_lvl, g_main.c:1080,
-// 1118-1123), so it is walked in order by one thread: O(frames) scalar work, exact semantics.
+// agc_kernel: the display range is a recurrence over frames in mixed double/float arithmetic with a
+// rounding to float at every step (static float display_max_lvl, g_main.c:1080,1118-1123):
+//     lvl = (float) ((1.0 - 0.99) * sig + 0.99 * lvl)
+// Rounding makes it non-associative, so the chain itself is walked in order -- but only the chain: the
+// maximum and the minimum level are two independent chains on two warps (per step two conversions, one
+// multiply and one add on the critical path; the product with the new statistic does not depend on the
+// chain and runs ahead), and the dB conversion of the range (two double log10 per frame, most of the cost
+// of the first version, where one thread did everything) is done for all frames in parallel afterwards.
+// The double products and the sum are kept as separate roundings (__dmul_rn / __dadd_rn: no FMA
+// contraction), as the x86-64 reference build computes them.
 // state[0..1] = (display_max_lvl, display_min_lvl) carried between calls; stats = floor_stats rows.
-__global__ void agc_kernel(const float *__restrict__ stats, long long nframes, long long first_frame, float overlap,
-                           int log_scale, float *__restrict__ state, float *__restrict__ range /* [nframes][2] */) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float mx = state[0], mn = state[1];
-  for (long long i = 0; i < nframes; i++) {
-    float sig = stats[4 * i + 0], flo = stats[4 * i + 1];
-    if (first_frame + i == 0) {                      // glfer.first_buffer == TRUE (g_main.c:1112-1120)
-      if (overlap > 0.0f) { sig /= overlap; flo /= overlap; }
-      mx = sig;
-      mn = flo;
-    } else {                                         // g_main.c:1122-1123
-      mx = (float) ((1.0 - 0.99) * (double) sig + 0.99 * (double) mx);
-      mn = (float) ((1.0 - 0.99) * (double) flo + 0.99 * (double) mn);
+__global__ void __launch_bounds__(256) agc_kernel(const float *__restrict__ stats, long long nframes, long long first_frame,
+                                                  float overlap, int log_scale, float *__restrict__ state,
+                                                  float *__restrict__ range /* [nframes][2] */) {
+  const int tid = threadIdx.x;
+  const int chain = tid >> 5;                          // warp 0: maximum level, warp 1: minimum level
+  if (chain < 2 && (tid & 31) == 0) {
+    float lvl = state[chain];
+    for (long long i = 0; i < nframes; i++) {
+      float s = stats[4 * i + chain];
+      if (first_frame + i == 0) {                      // glfer.first_buffer == TRUE (g_main.c:1112-1120)
+        if (overlap > 0.0f) s /= overlap;
+        lvl = s;
+      } else {                                         // g_main.c:1122-1123
+        lvl = (float) __dadd_rn(__dmul_rn(1.0 - 0.99, (double) s), __dmul_rn(0.99, (double) lvl));
+      }
+      range[2 * i + chain] = lvl;
     }
-    if (log_scale) {                                 // g_main.c:1132-1135
-      range[2 * i + 0] = (float) (10.0 * log10((double) mx));
-      range[2 * i + 1] = (float) (10.0 * log10((double) mn));
-    } else {
-      range[2 * i + 0] = mx;
-      range[2 * i + 1] = mn;
-    }
+    state[chain] = lvl;
   }
-  state[0] = mx;
-  state[1] = mn;
+  __syncthreads();
+  if (log_scale) {                                     // g_main.c:1132-1135
+    for (long long i = tid; i < 2 * nframes; i += blockDim.x) range[i] = (float) (10.0 * log10((double) range[i]));
+  }
 }
 
 // levels_kernel: one warp per row.  Pixel i of a row shows bin n-1-i (g_main.c:1193-1201); in
@@ -943,7 +1021,7 @@ __global__ void __launch_bounds__(256) levels_kernel(const float *__restrict__ r
 extern "C" int glb_launch_agc(const float *stats, long long nframes, long long first_frame, float overlap, int log_scale,
                               float *state, float *range, void *stream) {
   if (nframes <= 0) return GLB_OK;
-  agc_kernel<<<1, 32, 0, (cudaStream_t) stream>>>(stats, nframes, first_frame, overlap, log_scale, state, range);
+  agc_kernel<<<1, 256, 0, (cudaStream_t) stream>>>(stats, nframes, first_frame, overlap, log_scale, state, range);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;

@@ -102,7 +102,8 @@ int glb_gram_fused_mean_ok(int n, int hop);
 /* testing aid: 1 = always use the general kernel (the TMA ring kernel is chosen automatically
  * for the regular geometries) */
 void glb_force_generic_kernel(int on);
-/* 0 = automatic choice, 1 = general kernel, 2 = TMA ring kernel, 3 = warp-per-frame kernel
+/* 0 = automatic choice, 1 = general kernel, 2 = TMA ring kernel, 3 = warp-per-frame kernel, 4 = two frames per
+ * thread, 5 = 32-points-per-thread kernel (N = 16384 / 32768; what the automatic choice takes there)
  * (a preference: launches a family cannot serve fall through to the next one) */
 void glb_set_kernel_preference(int pref);
 

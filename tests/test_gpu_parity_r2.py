@@ -363,3 +363,43 @@ def test_band_only_averaged_rows_equal_the_band_of_full_rows(gpu_api, mode):
     one = gpu_api.run_sharded(x, 1, **kw)
     many = gpu_api.run_sharded(x, 4, devices=[g % nd for g in range(4)], **kw)
     assert one["avg"].shape[1] == 70 and np.array_equal(one["avg"], many["avg"])
+
+
+# ------------------------------------------------------------------ the 32-points-per-thread kernel family
+def test_big_frame_kernel_vs_oracle_and_16_point_families(gpu_api):
+    """N = 16384 / 32768 periodograms at 0 / 50 / 75 % overlap run on gram_big_kernel (family 5) by default:
+    against the oracle, against the 16-point ring and general kernels, on ragged frame counts, with and
+    without block means, dB output, sub-ranges staged at an offset, and zero history at the stream start."""
+    x = synth.qrss_stream(16384 * 41 + 777, fs=FS, seed=81, dot_s=0.2)
+    for n in (16384, 32768):
+        for ov, wt, sm in ((0.5, 0, True), (0.75, 7, True), (0.0, 1, True), (0.5, 6, False)):
+            kw = dict(n=n, window_type=wt, overlap=ov, sub_mean=sm)
+            gpu_api.set_kernel_preference(0)
+            p = gpu_api.GramPlan(**kw)
+            got = p.run(x)["psd"]
+            assert gpu_api.last_kernel_family().startswith("gram_big_kernel"), gpu_api.last_kernel_family()
+            ref = O.periodogram(x, n, wt, ov, sm)
+            assert got.shape == ref.shape
+            assert_psd_close(got, ref, f"big kernel N={n} ov={ov}")
+            for pref in (1, 2):
+                gpu_api.set_kernel_preference(pref)
+                other = gpu_api.GramPlan(**kw).run(x)["psd"]
+                assert not gpu_api.last_kernel_family().startswith("gram_big_kernel")
+                st = assert_psd_close(got, other, f"big vs family {pref}")
+            gpu_api.set_kernel_preference(0)
+            # a sub-range staged at its own origin equals the rows of the full run (zero history only at frame 0)
+            nf = got.shape[0]
+            for first, cnt in ((0, 3), (5, nf - 7), (nf - 2, 2)):
+                lo, hi = p.required_span(first, cnt)
+                lo = max(lo, 0)
+                part = p.run(np.ascontiguousarray(x[lo:hi]), origin=lo, first_frame=first, nframes=cnt)["psd"]
+                assert np.array_equal(part, got[first:first + cnt]), (kw, first, cnt)
+    p = gpu_api.GramPlan(n=16384, window_type=0, overlap=0.5, sub_mean=True, scale_db=True)
+    lin = gpu_api.GramPlan(n=16384, window_type=0, overlap=0.5, sub_mean=True).run(x)["psd"]
+    assert np.allclose(p.run(x)["psd"], 10.0 * np.log10(lin), atol=2e-4)
+    # time shards on the big kernel are bit-identical to one shard
+    nd = gpu_api.device_count()
+    kw = dict(n=16384, window_type=0, overlap=0.5, sub_mean=True)
+    one = gpu_api.run_sharded(x, 1, **kw)
+    many = gpu_api.run_sharded(x, 8, devices=[g % nd for g in range(8)], **kw)
+    assert np.array_equal(one["psd"], many["psd"])

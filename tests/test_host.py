@@ -99,6 +99,17 @@ def test_fft_core_emulation(tmp_path):
     assert all(int(r[3]) == 0 and float(r[2]) < 1e-6 for r in rows)
 
 
+def test_big_frame_core_emulation(tmp_path):
+    """fft_big.cuh (three passes, 32 points per thread: the N = 16384 / 32768 kernel) on the CPU, thread by thread"""
+    exe = str(tmp_path / "emu_big")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "emu_big.cpp")], check=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    rows = [l.split() for l in res.stdout.strip().splitlines()]
+    assert [int(r[0]) for r in rows] == [2048, 4096, 8192, 16384]
+    assert all(int(r[3]) == 0 and float(r[1]) < 1e-4 and float(r[2]) < 1e-6 for r in rows)
+
+
 def test_warp_per_frame_core_emulation(tmp_path):
     """fft_wpf.cuh (two-pass, 64 points per lane) on the CPU, lane by lane"""
     exe = str(tmp_path / "emu_wpf")
