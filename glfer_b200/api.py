@@ -120,6 +120,8 @@ def lib() -> C.CDLL:
         l.fft_do.argtypes = [C.c_void_p, C.POINTER(FftParams)]
         l.fft_psd.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FftParams)]
         l.fft_close.argtypes = [C.POINTER(FftParams)]
+        l.fft_do_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(FftParams)]
+        l.mtm_do_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(MtmParams)]
         l.prepare_audio.argtypes = [C.c_void_p, C.POINTER(FftParams)]
         l.compute_window.argtypes = [C.POINTER(FftParams)]
         l.compute_floor.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),

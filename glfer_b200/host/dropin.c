@@ -86,6 +86,12 @@ typedef struct engine {
   double *d_avg, *d_ret, *d_var;
   int *d_cand;
   float *d_lmp;              /* LMP engines: the statistic row (ring = d_ring [depth][width]) */
+  /* k-block streaming entries (fft_do_batch / mtm_do_batch): grow-only stream + rows buffers */
+  float *d_bstream, *d_brows, *h_bstream, *h_brows;
+  size_t bstream_cap, brows_cap;
+  /* fft_psd with phase / compute_floor: buffers kept for the life of the engine (no cudaMalloc per call) */
+  float *d_scratch;
+  size_t scratch_cap;
 } engine;
 
 static engine *g_engines;
@@ -118,6 +124,8 @@ static void drop_engine(const void *key)
     glb_free(e->d_hc); glb_free(e->d_phase); glb_free(e->d_ring); glb_free(e->d_avg);
     glb_free(e->d_ret); glb_free(e->d_var); glb_free(e->d_cand); glb_free(e->d_lmp);
     glb_host_free(e->h_psd); glb_host_free(e->h_spec);
+    glb_free(e->d_bstream); glb_free(e->d_brows); glb_host_free(e->h_bstream); glb_host_free(e->h_brows);
+    glb_free(e->d_scratch);
     glb_tables_destroy(e->tables);
     glb_stream_destroy(e->stream);
     free(e);
@@ -134,6 +142,30 @@ static void need_device(const char *where)
     glb_set_error("no CUDA device (libglfer_b200 has no CPU fallback)");
     glb_fatal(where);
   }
+}
+
+/* grow-only device scratch of an engine (floats) */
+static float *engine_scratch(engine *e, size_t floats)
+{
+  if (floats > e->scratch_cap) {
+    if (e->d_scratch) MUST(glb_free(e->d_scratch), "free");
+    e->d_scratch = NULL;
+    MUST(glb_malloc((void **) &e->d_scratch, sizeof(float) * floats), "malloc");
+    e->scratch_cap = floats;
+  }
+  return e->d_scratch;
+}
+
+/* the engine behind calls that have no params of their own (compute_floor, fft_psd on foreign params) */
+static engine *scratch_engine(void)
+{
+  static const char key;
+  engine *e = find_engine(&key);
+  if (!e) {
+    e = new_engine(&key);
+    MUST(glb_stream_create(&e->stream), "stream");
+  }
+  return e;
 }
 
 /* device side of an estimator: tables, scaled tapers, one-frame buffers */
@@ -278,18 +310,116 @@ void fft_psd(float *psd_buf, float *phase_buf, fft_params_t *params)
   /* spectrum that was not produced by fft_do on these params (callers that fill outbuf
      themselves), or phase wanted: run fft_psd's formula on the device from outbuf */
   need_device("fft_psd");
-  void *d_hc = NULL, *d_psd = NULL, *d_ph = NULL;
-  MUST(glb_malloc(&d_hc, sizeof(float) * n), "malloc");
-  MUST(glb_malloc(&d_psd, sizeof(float) * bins), "malloc");
-  MUST(glb_malloc(&d_ph, sizeof(float) * bins), "malloc");
-  MUST(glb_memcpy_h2d(d_hc, params->outbuf, sizeof(float) * n, NULL), "h2d");
-  MUST(glb_launch_halfcomplex_psd(d_hc, n, psd_buf ? d_psd : NULL, phase_buf ? d_ph : NULL, NULL), "launch");
+  /* device scratch lives with the engine of these params (a shared one for foreign params): no
+     cudaMalloc / cudaFree per call */
+  engine *se = e ? e : scratch_engine();
+  float *d_hc = engine_scratch(se, (size_t) n + 2 * (size_t) bins);
+  float *d_psd = d_hc + n, *d_ph = d_psd + bins;
+  MUST(glb_memcpy_h2d(d_hc, params->outbuf, sizeof(float) * n, se->stream), "h2d");
+  MUST(glb_launch_halfcomplex_psd(d_hc, n, psd_buf ? d_psd : NULL, phase_buf ? d_ph : NULL, se->stream), "launch");
   if (psd_buf) {
     if (e && e->fresh) memcpy(psd_buf, e->h_psd, sizeof(float) * bins);
-    else MUST(glb_memcpy_d2h(psd_buf, d_psd, sizeof(float) * bins, NULL), "d2h");
+    else MUST(glb_memcpy_d2h(psd_buf, d_psd, sizeof(float) * bins, se->stream), "d2h");
   }
-  if (phase_buf) MUST(glb_memcpy_d2h(phase_buf, d_ph, sizeof(float) * bins, NULL), "d2h");
-  glb_free(d_hc); glb_free(d_psd); glb_free(d_ph);
+  if (phase_buf) MUST(glb_memcpy_d2h(phase_buf, d_ph, sizeof(float) * bins, se->stream), "d2h");
+  MUST(glb_stream_sync(se->stream), "sync");
+}
+
+/* k hop blocks per call (include/fft.h): exactly the sequence
+ *     for b in 0..nblocks-1: fft_do(blocks + b * hop, params); fft_psd(rows + b * bins, NULL, params); first_buffer = FALSE
+ * with ONE upload, ONE kernel launch and ONE download for the first nblocks - 1 blocks: the launch + copy
+ * latency of the per-block calls (~40 us, against 7 us of CPU time for an N = 1024 frame) is paid once per
+ * call instead of once per block.  The last block goes through fft_do itself, so that everything a caller
+ * can observe afterwards (inbuf_audio history, inbuf_fft, outbuf, the block means removed in place) is what
+ * the sequence of single calls leaves behind. */
+static void run_batch(engine *e, fft_params_t *fp, float *blocks, int nblocks, float *rows, float a, int limiter)
+{
+  const int N = fp->n, hop = glb_hop(N, fp->overlap), n_ov = N - hop, bins = N / 2 + 1;
+  if (nblocks <= 0) return;
+  /* block means, in place, as prepare_audio does (fft.c:86-96: float accumulator, in order) */
+  if (fp->sub_mean) {
+    for (int b = 0; b < nblocks; b++) {
+      float *blk = blocks + (size_t) b * hop, m = 0.0f;
+      for (int i = 0; i < hop; i++) m += blk[i];
+      m /= hop;
+      for (int i = 0; i < hop; i++) blk[i] -= m;
+    }
+  }
+  const size_t ns = (size_t) n_ov + (size_t) nblocks * hop;
+  if (ns > e->bstream_cap) {
+    glb_free(e->d_bstream); glb_host_free(e->h_bstream);
+    e->d_bstream = e->h_bstream = NULL;
+    MUST(glb_malloc((void **) &e->d_bstream, sizeof(float) * (ns + 4)), "malloc");
+    MUST(glb_host_alloc((void **) &e->h_bstream, sizeof(float) * ns), "host_alloc");
+    e->bstream_cap = ns;
+  }
+  if ((size_t) nblocks * bins > e->brows_cap) {
+    glb_free(e->d_brows); glb_host_free(e->h_brows);
+    e->d_brows = e->h_brows = NULL;
+    MUST(glb_malloc((void **) &e->d_brows, sizeof(float) * (size_t) nblocks * bins), "malloc");
+    MUST(glb_host_alloc((void **) &e->h_brows, sizeof(float) * (size_t) nblocks * bins), "host_alloc");
+    e->brows_cap = (size_t) nblocks * bins;
+  }
+  /* the stream the frames see: the overlap history (zeros when glfer.first_buffer, fft.c:99-108), then the blocks */
+  if (glb_first_buffer()) memset(e->h_bstream, 0, sizeof(float) * n_ov);
+  else memcpy(e->h_bstream, fp->inbuf_audio + (N - n_ov), sizeof(float) * n_ov);
+  memcpy(e->h_bstream + n_ov, blocks, sizeof(float) * (size_t) nblocks * hop);
+  /* frame F0 + b covers stream samples [(F0 + b) hop - n_ov, (F0 + b + 1) hop) = buffer [b hop, b hop + N) */
+  const long long F0 = (n_ov + hop - 1) / hop;
+  glb_gram_args g;
+  memset(&g, 0, sizeof g);
+  MUST(glb_memcpy_h2d(e->d_bstream, e->h_bstream, sizeof(float) * ns, e->stream), "h2d");
+  g.n = N;
+  g.hop = hop;
+  g.samples = e->d_bstream;
+  g.origin = F0 * hop - n_ov;
+  g.count = (long long) ns;
+  g.tapers = e->d_tapers;
+  g.ntapers = e->ntapers;
+  g.ra9mb_a = a;
+  g.limiter = limiter;
+  g.taper_scale = e->taper_scale;
+  g.first_frame = F0;
+  g.nframes = nblocks;
+  g.rows = e->d_brows;
+  g.row_stride = bins;
+  g.tables = e->tables;
+  MUST(glb_launch_gram(&g, e->stream), "launch");
+  MUST(glb_memcpy_d2h(e->h_brows, e->d_brows, sizeof(float) * (size_t) nblocks * bins, e->stream), "d2h");
+  MUST(glb_stream_sync(e->stream), "sync");
+  memcpy(rows, e->h_brows, sizeof(float) * (size_t) nblocks * bins);
+  /* history as nblocks calls leave it: the last N samples of the stream */
+  if (ns >= (size_t) N) memcpy(fp->inbuf_audio, e->h_bstream + (ns - N), sizeof(float) * N);
+}
+
+void fft_do_batch(float *audio_blocks, int nblocks, float *psd_rows, fft_params_t *params)
+{
+  engine *e = find_engine(params);
+  if (!e) { glb_set_error("fft_do_batch on parameters that did not go through fft_init"); glb_fatal("fft_do_batch"); }
+  if (nblocks <= 0) return;
+  const int hop = glb_hop(params->n, params->overlap), bins = params->n / 2 + 1;
+  if (nblocks > 1) {
+    run_batch(e, params, audio_blocks, nblocks - 1, psd_rows, params->a, params->limiter);
+    glfer_b200_set_first_buffer(0);
+    if (&glfer != NULL) glfer.first_buffer = 0;
+  }
+  /* the last block through the single-block path: inbuf_fft / outbuf / the cached PSD are those of fft_do */
+  fft_do(audio_blocks + (size_t) (nblocks - 1) * hop, params);
+  fft_psd(psd_rows + (size_t) (nblocks - 1) * bins, NULL, params);
+}
+
+void mtm_do_batch(float *audio_blocks, int nblocks, float *psd_rows, mtm_params_t *params)
+{
+  engine *e = find_engine(params);
+  if (!e) { glb_set_error("mtm_do_batch on parameters that did not go through mtm_init"); glb_fatal("mtm_do_batch"); }
+  if (nblocks <= 0) return;
+  const int hop = glb_hop(params->fft.n, params->fft.overlap), bins = params->fft.n / 2 + 1;
+  if (nblocks > 1) {
+    run_batch(e, &params->fft, audio_blocks, nblocks - 1, psd_rows, 0.0f, 0);
+    glfer_b200_set_first_buffer(0);
+    if (&glfer != NULL) glfer.first_buffer = 0;
+  }
+  mtm_do(audio_blocks + (size_t) (nblocks - 1) * hop, psd_rows + (size_t) (nblocks - 1) * bins, NULL, params);
 }
 
 void fft_close(fft_params_t *params)
@@ -305,14 +435,14 @@ void compute_floor(float *psd_buf, int n, float *sig_pwr_p, float *floor_pwr_p, 
                    unsigned int *peak_bin_p)
 {
   need_device("compute_floor");
-  void *d_row = NULL, *d_st = NULL;
+  /* called once per frame by main_window_draw (g_main.c:1109): scratch kept for the life of the process */
+  engine *se = scratch_engine();
   float st[4];
-  MUST(glb_malloc(&d_row, sizeof(float) * n), "malloc");
-  MUST(glb_malloc(&d_st, sizeof st), "malloc");
-  MUST(glb_memcpy_h2d(d_row, psd_buf, sizeof(float) * n, NULL), "h2d");
-  MUST(glb_launch_floor_stats(d_row, n, n, 1, d_st, NULL), "launch");
-  MUST(glb_memcpy_d2h(st, d_st, sizeof st, NULL), "d2h");
-  glb_free(d_row); glb_free(d_st);
+  float *d_row = engine_scratch(se, (size_t) n + 4), *d_st = d_row + n;
+  MUST(glb_memcpy_h2d(d_row, psd_buf, sizeof(float) * n, se->stream), "h2d");
+  MUST(glb_launch_floor_stats(d_row, n, n, 1, d_st, se->stream), "launch");
+  MUST(glb_memcpy_d2h(st, d_st, sizeof st, se->stream), "d2h");
+  MUST(glb_stream_sync(se->stream), "sync");
   *sig_pwr_p = st[0];
   *floor_pwr_p = st[1];
   *peak_pwr_p = st[2];

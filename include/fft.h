@@ -53,6 +53,13 @@ void fft_do(float *audio_buf, fft_params_t *params);
 void fft_psd(float *psd_buf, float *phase_buf, fft_params_t *params);
 void fft_close(fft_params_t *params);
 
+/* Extension (not in the reference): nblocks consecutive hop blocks per call -- exactly the sequence
+ *   for b: fft_do(audio_blocks + b * hop, params); fft_psd(psd_rows + b * (n/2+1), NULL, params); glfer.first_buffer = FALSE;
+ * (hop = (int)(n * (1.0 - overlap)), fft.c:70) with the launch and copy latency of the GPU paid once per call
+ * instead of once per block.  State left in params (history, outbuf, block means removed in place from
+ * audio_blocks) is that of the last single call; glfer.first_buffer is cleared after the first block. */
+void fft_do_batch(float *audio_blocks, int nblocks, float *psd_rows, fft_params_t *params);
+
 /* replaces fft.h:83 (display/AGC statistics of one PSD row) */
 void compute_floor(float *psd_buf, int n, float *sig_pwr_p, float *floor_pwr_p, float *peak_pwr_p,
                    unsigned int *peak_bin_p);

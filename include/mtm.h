@@ -31,6 +31,9 @@ void mtm_init(mtm_params_t *params);
 void mtm_do(float *audio_buf, float *psd_buf, float *phase_buf, mtm_params_t *params);
 void mtm_close(mtm_params_t *params);
 
+/* extension: nblocks hop blocks per call, = nblocks mtm_do calls (see fft_do_batch in fft.h) */
+void mtm_do_batch(float *audio_blocks, int nblocks, float *psd_rows, mtm_params_t *params);
+
 /* replaces g-l_dpss.h:23; v is an NR-style matrix v[1..n][0..kmax] */
 int gl_dpss(int nmax, int kmax, int n, double w, double **v, double *sig, int *totit);
 

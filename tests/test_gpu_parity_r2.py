@@ -403,3 +403,70 @@ def test_big_frame_kernel_vs_oracle_and_16_point_families(gpu_api):
     one = gpu_api.run_sharded(x, 1, **kw)
     many = gpu_api.run_sharded(x, 8, devices=[g % nd for g in range(8)], **kw)
     assert np.array_equal(one["psd"], many["psd"])
+
+
+# ------------------------------------------------------------------ per-call interface: k blocks per call
+def test_fft_do_batch_equals_the_sequence_of_single_calls(gpu_api):
+    import ctypes as C
+    lib = gpu_api.lib()
+    x = synth.qrss_stream(60000, fs=8000, seed=91, dot_s=0.2)
+    for n, wt, ov, sm, a, lim in ((1024, 0, 0.5, 1, 0.0, 0), (512, 7, 0.75, 1, 0.0, 0), (1024, 2, 0.9, 0, 0.0, 0),
+                                  (2048, 0, 0.5, 1, 0.02, 1)):
+        hop = gpu_api.host_hop(n, ov)
+        nb = len(x) // hop
+        bins = n // 2 + 1
+
+        def fresh():
+            p = gpu_api.FftParams()
+            p.n, p.window_type, p.overlap, p.a, p.limiter = n, wt, ov, a, lim
+            lib.glfer_b200_set_autoscale(sm)
+            lib.glfer_b200_set_first_buffer(1)
+            lib.fft_init(C.byref(p))
+            return p
+        # one block per call
+        p1 = fresh()
+        single = np.empty((nb, bins), np.float32)
+        blocks1 = x[: nb * hop].copy().reshape(nb, hop)
+        for b in range(nb):
+            lib.fft_do(blocks1[b].ctypes.data, C.byref(p1))
+            lib.fft_psd(single[b].ctypes.data, None, C.byref(p1))
+            lib.glfer_b200_set_first_buffer(0)
+        # the same blocks in three batched calls (13, then the bulk, then 1)
+        p2 = fresh()
+        batched = np.empty((nb, bins), np.float32)
+        blocks2 = x[: nb * hop].copy().reshape(nb, hop)
+        done = 0
+        for k in (13, nb - 14, 1):
+            lib.fft_do_batch(blocks2[done].ctypes.data, k, batched[done].ctypes.data, C.byref(p2))
+            done += k
+        assert done == nb
+        assert_psd_close(batched, single, f"fft_do_batch n={n} ov={ov}")
+        assert np.array_equal(blocks1, blocks2)                       # block means removed in place, identically
+        h1 = np.ctypeslib.as_array(p1.inbuf_audio, shape=(n,)).copy()
+        h2 = np.ctypeslib.as_array(p2.inbuf_audio, shape=(n,)).copy()
+        assert np.array_equal(h1, h2)                                 # the overlap history the next call starts from
+        o1 = np.ctypeslib.as_array(p1.outbuf, shape=(n,)).copy()
+        o2 = np.ctypeslib.as_array(p2.outbuf, shape=(n,)).copy()
+        assert np.array_equal(o1, o2)                                 # half-complex spectrum of the last frame
+        assert_psd_close(single, O.periodogram(x, n, wt, ov, bool(sm), a, lim), "per call vs oracle")
+        lib.fft_close(C.byref(p1))
+        lib.fft_close(C.byref(p2))
+
+
+def test_compute_floor_bit_exact_and_autoscale_display_on_wide_rows(gpu_api):
+    """compute_floor through the radix-select kernel: sig / floor / peak EQUAL the restatement (pinned bit for bit
+    to the compiled reference) on rows of every width, with ties, zeros and a row of equal values."""
+    import ctypes as C
+    lib = gpu_api.lib()
+    rng = np.random.default_rng(12)
+    for nb in (17, 257, 513, 2049, 8193, 16385):
+        rows = [(rng.standard_normal(nb) ** 2 * 1e-6).astype(np.float32), np.full(nb, 3e-7, np.float32),
+                np.zeros(nb, np.float32), (rng.integers(0, 4, nb) * 1e-5).astype(np.float32)]
+        rows[0][nb // 3] = 2e-3
+        for row in rows:
+            s, f, p, b = C.c_float(), C.c_float(), C.c_float(), C.c_uint()
+            r = row.copy()
+            lib.compute_floor(r.ctypes.data, len(r), C.byref(s), C.byref(f), C.byref(p), C.byref(b))
+            s2, f2, p2, b2 = O.compute_floor(row)
+            assert (np.float32(s.value), np.float32(f.value), np.float32(p.value), b.value) == \
+                (np.float32(s2), np.float32(f2), np.float32(p2), b2), (nb, s.value, s2, f.value, f2)
