@@ -30,7 +30,7 @@ class GramConfig(C.Structure):
                 ("mtm_kmax", C.c_int), ("avg_mode", C.c_int), ("avg_depth", C.c_int), ("avg_minbin", C.c_int),
                 ("avg_maxbin", C.c_int), ("avg_max0", C.c_int), ("avg_peakbin_init", C.c_int),
                 ("scale_db", C.c_int), ("device", C.c_int), ("lmp_av", C.c_int), ("avg_band_only", C.c_int),
-                ("zero_history", C.c_int)]
+                ("mtm_ftest", C.c_int), ("zero_history", C.c_int)]
 
 
 class FftParams(C.Structure):          # include/fft.h (reference fft.h:51-63)
@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.glfer_gram_run.argtypes = run_args
         l.glfer_gram_run_pcm16.argtypes = run_args
+        l.glfer_gram_run_mtm_ftest.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong,
+                                               C.c_void_p, C.c_void_p]
         l.glfer_gram_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]
         l.glfer_gram_stage_pcm16.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]
         l.glfer_gram_exec.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_float)]
@@ -219,10 +221,11 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 
 def make_config(n=1024, window_type=KAISER, overlap=0.0, mode=MODE_FFT, sub_mean=True, a=0.0, limiter=0,
                 mtm_w=4.0, mtm_kmax=7, avg_mode=NO_AVG, avg_depth=4, avg_minbin=0, avg_maxbin=0, avg_max0=0,
-                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4, avg_band_only=False, zero_history=False) -> GramConfig:
+                avg_peakbin_init=0, scale_db=False, device=0, lmp_av=4, avg_band_only=False, mtm_ftest=False,
+                zero_history=False) -> GramConfig:
     return GramConfig(mode, n, window_type, overlap, a, limiter, int(sub_mean), mtm_w, mtm_kmax, avg_mode, avg_depth,
                       avg_minbin, avg_maxbin, avg_max0, avg_peakbin_init, int(scale_db), device, lmp_av,
-                      int(avg_band_only), int(zero_history))
+                      int(avg_band_only), int(mtm_ftest), int(zero_history))
 
 
 class GramPlan:
@@ -294,6 +297,17 @@ class GramPlan:
         _check(fn(self._h, samples.ctypes.data, origin, len(samples), first_frame, nframes, _ptr(psd), _ptr(avg),
                   _ptr(ret), _ptr(pk), _ptr(var)))
         return dict(psd=psd, avg=avg, ret=ret, peakbin=pk, variance=var)
+
+    def run_mtm_ftest(self, samples: np.ndarray, origin: int = 0, first_frame: int = 0, nframes: int | None = None):
+        """glfer_gram_run_mtm_ftest: multitaper rows and the harmonic F-test rows (plan with mtm_ftest=True)."""
+        assert samples.dtype == np.float32 and samples.flags["C_CONTIGUOUS"]
+        if nframes is None:
+            nframes = (origin + len(samples)) // self.hop - first_frame
+        psd = np.empty((nframes, self.bins), np.float32)
+        ft = np.empty((nframes, self.bins), np.float32)
+        _check(lib().glfer_gram_run_mtm_ftest(self._h, samples.ctypes.data, origin, len(samples), first_frame, nframes,
+                                              psd.ctypes.data, ft.ctypes.data))
+        return dict(psd=psd, ftest=ft)
 
     def stage(self, samples: np.ndarray, origin: int = 0):
         assert samples.flags["C_CONTIGUOUS"]

@@ -5,11 +5,11 @@
 // Why a second kernel family: at these sizes the 16-point core needs four passes, 512 threads and 74 KB of
 // exchange buffer per frame, so with its 64 KB TMA ring only ONE frame fits an SM and the shared-memory
 // pipe (three exchanges) bounds it (N = 16384: 34 % of the HBM roofline, round 1).  Here a frame is 256
-// threads x 32 points (N = 16384), 70 KB of shared memory and no ring: the hop blocks are read straight
-// from global memory -- the new block was pulled into L2 by prefetch.global.L2 one frame earlier, the
-// older blocks were read by this very CTA one frame ago and sit in L2 -- so two CTAs (two frames in
-// flight) fit an SM, with a third fewer shared-memory wavefronts per frame.  Every sample still crosses
-// HBM once.
+// threads x 32 points (N = 16384), 72 KB of shared memory and no ring: a frame's samples land by ONE TMA
+// bulk copy in the exchange buffer itself while it is idle (between the last-pass loads of the previous
+// frame and the first-pass stores of this one); its older hop blocks were fetched by this very CTA one
+// frame earlier and come from L2, so every sample still crosses HBM once.  Two CTAs (two frames in
+// flight) fit an SM, with a third fewer shared-memory wavefronts per frame.
 //
 // Geometry: hop = N / NBLK, NBLK = 1, 2, 4 (0 %, 50 %, 75 % overlap), periodogram, no RA9MB / limiter;
 // everything else stays on the 16-point kernels (gram_common.cuh).
@@ -21,7 +21,7 @@ template <int M> struct BigGeo {
   static constexpr size_t BUF_BYTES = (size_t) Big<M>::BUF * sizeof(float2);
   static constexpr size_t TW_BYTES = (size_t) Big<M>::TW1 * sizeof(float2);
   static constexpr size_t RED_BYTES = (size_t) 4 * NW * sizeof(float);
-  static constexpr size_t SMEM = BUF_BYTES + TW_BYTES + RED_BYTES;
+  static constexpr size_t SMEM = BUF_BYTES + TW_BYTES + RED_BYTES + 16;        // + the mbarrier
   static constexpr int MINB = (T <= 256) ? 2 : 1;
 };
 
@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
   float2 *tw1 = reinterpret_cast<float2 *>(smem_raw + G::BUF_BYTES);
   float *red = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES);
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES);
   const int t = threadIdx.x;
 
   // middle-pass twiddles exp(-2 pi i k r / (32 R1)) = roots[16 k r], one copy per CTA
@@ -48,13 +49,35 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   float *row_ptr = p.rows + fb * p.row_stride;
   long long s0 = (p.first_frame + fb) * (long long) HOP - (N - HOP);   // stream index of the frame's first sample
 
+  // The exchange buffer is idle from the last-pass loads of one frame to the first-pass stores of the next:
+  // that is where the NEXT frame's samples land, by one TMA bulk copy (cp.async.bulk + mbarrier) issued as
+  // soon as the buffer is free and completed behind the last pass, the split and the row stores.  No
+  // staging memory of its own, no global-load instructions for samples, no L1 pollution (the taper stays).
+  // A frame qualifies when it lies entirely inside the staged span, 16-byte aligned; the few others
+  // (zero history at the stream start, unaligned origins) are read with checked scalar loads.
+  auto bulk_ok = [&](long long fs0) {
+    const long long r = fs0 - p.origin;
+    return fs0 >= 0 && r >= 0 && r + N <= p.count && (r & 3) == 0;
+  };
+  unsigned phase = 0;
+  if (t == 0) {
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (nact > 0 && bulk_ok(s0)) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(mbar, N * 4u);
+      tma_load_1d(buf, p.samples + (s0 - p.origin), N * 4u, mbar);
+    }
+  }
+  __syncthreads();
+
   for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride) {
     float2 v[kBP];
-    const long long rel = s0 - p.origin;
-    if (s0 >= 0 && rel >= 0 && rel + N <= p.count) {
-      const float2 *src = reinterpret_cast<const float2 *>(p.samples + rel) + t;
+    if (bulk_ok(s0)) {
+      mbar_wait(mbar, phase);
+      phase ^= 1;
 #pragma unroll
-      for (int q = 0; q < kBP; q++) v[q] = ldg2(src + T * q);
+      for (int q = 0; q < kBP; q++) v[q] = buf[t + T * q];
     } else {
       // edge frame: zero history before the stream start (fft.c:103-108), nothing past the staged span
 #pragma unroll
@@ -69,18 +92,11 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
         v[q] = make_float2(y[0], y[1]);
       }
     }
-    if (it + 1 < nact) {
-      // the next frame's new hop block towards L2 while this frame is transformed (one 128-byte line per
-      // thread and round); the older blocks of that frame are this frame's newer ones
-      const long long nb = rel + N;
-      for (int i = t * 32; i < HOP; i += T * 32)
-        if (nb + i >= 0 && nb + i < p.count) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.samples + nb + i));
-    }
+    float bs[NBLK];
     if (sub) {
       // block means (prepare_audio, fft.c:86-96): block b = registers [b QB, (b + 1) QB).  The summation tree
       // of a block does not depend on its position in the frame, so its mean is the same bits in every
       // frame (and time shard) it appears in; zero history sums to a zero mean.
-      float bs[NBLK];
 #pragma unroll
       for (int b = 0; b < NBLK; b++) {
         float s = 0.f;
@@ -90,7 +106,9 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if ((t & 31) == 0) red[b * NW + (t >> 5)] = s;
       }
-      __syncthreads();                 // also orders the previous frame's last-pass loads before this frame's stores
+    }
+    __syncthreads();                   // (A) block sums visible; everyone has taken its samples out of the buffer
+    if (sub) {
 #pragma unroll
       for (int b = 0; b < NBLK; b++) {
         float s = 0.f;
@@ -104,7 +122,6 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
 #pragma unroll
     for (int q = 0; q < kBP; q++) v[q] = mul2(v[q], ld_taper(w2 + T * q));
     big_pass0(v);
-    if (!sub) __syncthreads();         // (A) the previous frame's last pass has been read by all
     big_scatter0<M>(v, t, buf);
     __syncthreads();
     big_load1<M>(v, t, buf);
@@ -115,6 +132,12 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     BigLast L;
     big_load_last<M>(L, t, p.roots, p.vtab);
     big_load2<M>(v, t, buf);
+    __syncthreads();                   // (E) the last-pass loads are done: the buffer is free for the next frame
+    if (t == 0 && it + 1 < nact && bulk_ok(s0 + HOP)) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(mbar, N * 4u);
+      tma_load_1d(buf, p.samples + (s0 + HOP - p.origin), N * 4u, mbar);
+    }
     big_pass2<M>(v, t, L);
     float yv[33];
     yv[32] = 1.f;                      // only thread 0 has a 33rd bin

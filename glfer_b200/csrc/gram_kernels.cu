@@ -780,6 +780,53 @@ extern "C" int glb_launch_lmp(const float *psd, long long psd_first_frame, long 
   return GLB_OK;
 }
 
+// ------------------------------------------------------------------------- harmonic F-test
+// mtm.c:204-233 per (frame, bin): den accumulates |y_j - mu U0_j|^2 over the tapers in the reference's float
+// buffer (`ftest[i] += ...`: double terms, one rounding to float per taper), then
+// ftest = kmax |mu|^2 sum_U0_sqr / den in double, stored to float.  DC: real parts only (:205-206,223-224);
+// even n: the Nyquist denominator is never accumulated (the loops stop at (n+1)/2) and its numerator is
+// mu[n/2]^2 + mu[n - n/2]^2 = twice the (real) Nyquist value squared (:229-233).
+__global__ void __launch_bounds__(256) ftest_kernel(const float2 *__restrict__ spec, long long nframes, int nbins, int n,
+                                                    int ntapers, const double *__restrict__ u0, double sum_u0_sqr,
+                                                    float *__restrict__ out, long long stride) {
+  const long long plane = nframes * (long long) nbins;
+  const long long total = plane;
+  const int half = (n + 1) / 2;
+  for (long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long) gridDim.x * blockDim.x) {
+    const long long f = idx / nbins;
+    const int i = (int) (idx - f * nbins);
+    const float2 m = spec[idx];
+    const double mr = (double) m.x, mi = (i == 0) ? 0.0 : (double) m.y;
+    float den = 0.f;
+    double num;
+    if (i < half) {
+      for (int j = 0; j < ntapers; j++) {
+        const float2 y = spec[(long long) (1 + j) * plane + idx];
+        const double tr = (double) y.x - mr * u0[j];
+        const double ti = (i == 0) ? 0.0 : (double) y.y - mi * u0[j];
+        den = (float) ((double) den + (__dmul_rn(tr, tr) + __dmul_rn(ti, ti)));
+      }
+      num = (double) (ntapers - 1) * (__dmul_rn(mr, mr) + __dmul_rn(mi, mi)) * sum_u0_sqr;
+    } else {
+      num = (double) (ntapers - 1) * (__dmul_rn(mr, mr) + __dmul_rn(mr, mr)) * sum_u0_sqr;
+    }
+    out[f * stride + i] = (float) (num / (double) den);
+  }
+}
+
+extern "C" int glb_launch_ftest(const float *spec, long long nframes, int nbins, int n, int ntapers, const double *u0,
+                                double sum_u0_sqr, float *ftest, long long stride, void *stream) {
+  if (nframes <= 0) return GLB_OK;
+  if (!spec || !u0 || !ftest || ntapers < 1) { glb_set_error("glb_launch_ftest: invalid arguments"); return GLB_EINVAL; }
+  long long ctas = (nframes * nbins + 255) / 256;
+  if (ctas > 148 * 32) ctas = 148 * 32;
+  ftest_kernel<<<(unsigned) ctas, 256, 0, (cudaStream_t) stream>>>((const float2 *) spec, nframes, nbins, n, ntapers, u0,
+                                                                  sum_u0_sqr, ftest, stride);
+  CU(cudaGetLastError());
+  g_launches++;
+  return GLB_OK;
+}
+
 // ------------------------------------------------------------------------- half-complex PSD
 // fft_psd (fft.c:203-226) for a spectrum that did not come from gram_kernel (callers that
 // fill outbuf themselves).  phase = atan2(Re, Im), the reference's argument order.

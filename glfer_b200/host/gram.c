@@ -64,6 +64,12 @@ struct glfer_gram_plan {
   size_t cand_all_cap;
   float *d_agc_state;   /* display mapping: carried AGC levels */
   unsigned char *d_colortab;
+  /* harmonic F-test (mtm_ftest): hn and the unit-energy tapers scaled for the spectrum output, U0 */
+  float *d_ftapers;     /* [ntapers + 1][n] */
+  double *d_u0;
+  double sum_u0_sqr;
+  float *d_fspec, *d_ftest;
+  size_t fspec_cap, ftest_cap;
   void *level_tables;   /* dB thresholds on the device (host/levels.c) */
   unsigned char *d_level_lut;
 };
@@ -198,6 +204,7 @@ void glfer_gram_plan_destroy(glfer_gram_plan *p)
     glb_stream_destroy(s->stream);
   }
   glb_free(p->d_tapers);
+  glb_free(p->d_ftapers); glb_free(p->d_u0); glb_free(p->d_fspec); glb_free(p->d_ftest);
   glb_free(p->d_cand_all);
   glb_free(p->d_peak_all);
   glb_free(p->d_agc_state); glb_free(p->d_colortab); glb_free(p->d_level_lut);
@@ -266,6 +273,33 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
     if (glb_dpss(n, (double) cfg->mtm_w, cfg->mtm_kmax, p->h_tapers, p->h_lambda) != 0) {
       glfer_gram_plan_destroy(p);
       return fail(GLFER_EINVAL, "DPSS computation failed");
+    }
+    if (cfg->mtm_ftest) {
+      /* mtm_init, mtm.c:78-84,123-136: U0 in double, sum_U0_sqr and hn through float accumulators */
+      const int K = p->ntapers;
+      double *u0 = malloc(sizeof(double) * K);
+      float *ft = malloc(sizeof(float) * (size_t) (K + 1) * n);
+      float s2 = 0.0f;
+      for (int k = 0; k < K; k++) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += p->h_tapers[(size_t) k * n + i];
+        u0[k] = s;
+        s2 += u0[k] * u0[k];
+      }
+      for (int i = 0; i < n; i++) {
+        float h = 0.0f;
+        for (int k = 0; k < K; k++) h += u0[k] * p->h_tapers[(size_t) k * n + i];
+        h /= s2;
+        ft[i] = (float) ((double) h * (double) p->taper_scale);
+        for (int k = 0; k < K; k++) ft[(size_t) (k + 1) * n + i] = (float) (p->h_tapers[(size_t) k * n + i] * (double) p->taper_scale);
+      }
+      p->sum_u0_sqr = (double) s2;
+      rc = shim(glb_malloc((void **) &p->d_ftapers, sizeof(float) * (size_t) (K + 1) * n));
+      if (rc == 0) rc = shim(glb_memcpy_h2d(p->d_ftapers, ft, sizeof(float) * (size_t) (K + 1) * n, NULL));
+      if (rc == 0) rc = shim(glb_malloc((void **) &p->d_u0, sizeof(double) * K));
+      if (rc == 0) rc = shim(glb_memcpy_h2d(p->d_u0, u0, sizeof(double) * K, NULL));
+      free(u0); free(ft);
+      if (rc != 0) { glfer_gram_plan_destroy(p); return rc; }
     }
     scaled = malloc(sizeof(float) * (size_t) p->ntapers * n);
     for (int k = 0; k < p->ntapers; k++) {
@@ -530,6 +564,93 @@ int glfer_gram_fetch(glfer_gram_plan *p, float *psd_rows, float *avg_rows, doubl
   int rc = fetch_slot(p, &p->slot[0], psd_rows, avg_rows, avg_ret, avg_peakbin, avg_variance);
   if (rc != 0) return rc;
   return shim(glb_stream_sync(p->slot[0].stream));
+}
+
+/* ---------------------------------------------------------------- harmonic F-test
+ * One chunk: the complex spectrum of every frame under hn and under each taper (ntapers + 1 launches of the
+ * general kernel with its spectrum output), then mtm.c:204-233 per bin.  Not a throughput path: the
+ * reference itself computes the statistic only to discard it. */
+static int ftest_slot(glfer_gram_plan *p, slot_t *s, long long first, long long nframes)
+{
+  const glfer_gram_config *c = &p->cfg;
+  const size_t plane = (size_t) nframes * p->bins;
+  TRY(ensure((void **) &p->d_fspec, &p->fspec_cap, plane * 2 * (size_t) (p->ntapers + 1), sizeof(float)));
+  TRY(ensure((void **) &p->d_ftest, &p->ftest_cap, plane, sizeof(float)));
+  long long lo, hi;
+  glfer_gram_required_span(p, first, nframes, &lo, &hi);
+  if (lo < 0) lo = 0;
+  const float *d_means = NULL;
+  long long means_first = 0;
+  const int fused_mean = c->sub_mean && glb_gram_fused_mean_ok(c->n, p->hop);
+  if (c->sub_mean && !fused_mean) {
+    const long long b_lo = lo / p->hop, b_hi = first + nframes;
+    TRY(ensure((void **) &s->d_means, &s->means_cap, (size_t) (b_hi - b_lo), sizeof(float)));
+    TRY(glb_launch_block_means(s->d_samples, s->s_origin, s->s_count, p->hop, b_lo, b_hi - b_lo, s->d_means, s->stream));
+    d_means = s->d_means;
+    means_first = b_lo;
+  }
+  for (int j = 0; j <= p->ntapers; j++) {
+    glb_gram_args g;
+    memset(&g, 0, sizeof g);
+    g.n = c->n;
+    g.hop = p->hop;
+    g.samples = s->d_samples;
+    g.origin = s->s_origin;
+    g.count = s->s_count;
+    g.tapers = p->d_ftapers + (size_t) j * c->n;
+    g.ntapers = 1;
+    g.block_means = d_means;
+    g.means_first_block = means_first;
+    g.fused_mean = fused_mean;
+    g.zero_history = c->zero_history;
+    g.taper_scale = p->taper_scale;
+    g.first_frame = first;
+    g.nframes = nframes;
+    g.spectrum = p->d_fspec + (size_t) j * plane * 2;
+    g.tables = p->tables;
+    TRY(glb_launch_gram(&g, s->stream));
+  }
+  return shim(glb_launch_ftest(p->d_fspec, nframes, p->bins, c->n, p->ntapers, p->d_u0, p->sum_u0_sqr, p->d_ftest, p->bins, s->stream));
+}
+
+int glfer_gram_run_mtm_ftest(glfer_gram_plan *p, const float *samples, long long origin, long long count,
+                             long long first_frame, long long nframes, float *psd_rows, float *ftest_rows)
+{
+  g_msg[0] = 0;
+  if (!p || !samples) return fail(GLFER_EINVAL, "null argument");
+  if (p->cfg.mode != GLFER_MODE_MTM || !p->d_ftapers) return fail(GLFER_EINVAL, "plan was not created as a multitaper plan with mtm_ftest = 1");
+  if (nframes < 0 || first_frame < 0) return fail(GLFER_EINVAL, "negative frame range");
+  if (nframes == 0) return 0;
+  TRY(glb_set_device(p->cfg.device));
+  long long lo, hi;
+  glfer_gram_required_span(p, first_frame, nframes, &lo, &hi);
+  if (lo < 0) lo = 0;
+  if (lo < origin || hi > origin + count)
+    return fail(GLFER_EINVAL, "samples do not cover the requested frames (see glfer_gram_required_span)");
+  /* chunks bounded by the spectra they need: (ntapers + 1) complex rows per frame */
+  long long cf = (256LL << 20) / ((long long) (p->ntapers + 1) * p->bins * 8);
+  if (cf < 16) cf = 16;
+  slot_t *s = &p->slot[0];
+  long long done = 0;
+  while (done < nframes) {
+    const long long c0 = first_frame + done;
+    const long long cn = (nframes - done < cf) ? nframes - done : cf;
+    long long clo, chi;
+    glfer_gram_required_span(p, c0, cn, &clo, &chi);
+    if (clo < 0) clo = 0;
+    TRY(stage_slot(p, s, samples + (clo - origin), NULL, clo, chi - clo));
+    if (psd_rows) {
+      TRY(exec_slot(p, s, c0, cn, NULL, NULL));
+      TRY(fetch_slot(p, s, psd_rows + (size_t) done * p->bins, NULL, NULL, NULL, NULL));
+    }
+    if (ftest_rows) {
+      TRY(ftest_slot(p, s, c0, cn));
+      TRY(glb_memcpy_d2h(ftest_rows + (size_t) done * p->bins, p->d_ftest, sizeof(float) * (size_t) cn * p->bins, s->stream));
+    }
+    TRY(glb_stream_sync(s->stream));
+    done += cn;
+  }
+  return 0;
 }
 
 /* ---------------------------------------------------------------- host-buffer API */

@@ -179,6 +179,11 @@ int glb_launch_levels(const float *rows, long long stride, int nbins, long long 
                       const unsigned char *level_lut, const unsigned char *colortab, unsigned char *levels,
                       unsigned char *rgb, void *stream);
 
+/* Harmonic F-test (mtm.c:204-233) from the complex spectra of one chunk of frames: spec = [ntapers + 1][nframes][nbins]
+ * (re, im) pairs, plane 0 = mu (the hn-weighted frame), plane 1 + j = y_j.  u0: device, [ntapers] doubles. */
+int glb_launch_ftest(const float *spec, long long nframes, int nbins, int n, int ntapers, const double *u0,
+                     double sum_u0_sqr, float *ftest, long long stride, void *stream);
+
 /* counters */
 unsigned long long glb_kernel_launches(void);
 /* family of the last spectrogram kernel launched: 1 general, 2 TMA ring, 3 warp-per-frame, 4 two frames per thread */

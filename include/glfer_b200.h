@@ -65,6 +65,8 @@ typedef struct {
                           avg_minbin + j).  The reference fills the rest of avg[] with the constant 1e-15
                           (avg.c:152-153); writing and shipping that constant is most of the cost of the averaging
                           pass when the band is a few dozen bins out of thousands */
+  int mtm_ftest;       /* 1 (MTM plans): also prepare Thomson's harmonic F-test, which mtm_do computes into a file-static
+                          nothing reads (mtm.c:59,165-174,204-210,222-233); rows through glfer_gram_run_mtm_ftest() */
   int zero_history;    /* 1: glfer.first_buffer stays TRUE, i.e. prepare_audio zeroes the N-hop history on EVERY
                           frame (fft.c:99-108).  That is what the reference GUI does with opt.autoscale == 0:
                           first_buffer is cleared only inside `if (opt.autoscale)` (g_main.c:1111-1120).
@@ -111,6 +113,14 @@ int glfer_gram_run(glfer_gram_plan *plan, const float *samples, long long origin
 int glfer_gram_run_pcm16(glfer_gram_plan *plan, const short *pcm, long long origin, long long count,
                          long long first_frame, long long nframes, float *psd_rows, float *avg_rows,
                          double *avg_ret, int *avg_peakbin, double *avg_variance);
+
+/* Multitaper rows plus the harmonic F-test of every frame (plan created with mtm_ftest = 1):
+ *   ftest[f][i] = kmax |mu(i)|^2 sum_U0_sqr / sum_j |y_j(i) - mu(i) U0_j|^2        (mtm.c:204-233)
+ * with mu = FFT(frame * hn), hn = sum_j U0_j v_j / sum_U0_sqr, U0_j = sum_i v_j[i] (mtm.c:78-84,125-136).  As in the
+ * reference the DC bin uses real parts only and, for even n, ftest[f][n/2] = num / 0 (inf, or nan for a zero
+ * numerator).  Either output may be NULL. */
+int glfer_gram_run_mtm_ftest(glfer_gram_plan *plan, const float *samples, long long origin, long long count,
+                             long long first_frame, long long nframes, float *psd_rows, float *ftest_rows);
 
 /* ---- device-resident path: stage once, execute many times, fetch when wanted ---- */
 int glfer_gram_stage(glfer_gram_plan *plan, const float *samples, long long origin, long long count);

@@ -470,3 +470,42 @@ def test_compute_floor_bit_exact_and_autoscale_display_on_wide_rows(gpu_api):
             s2, f2, p2, b2 = O.compute_floor(row)
             assert (np.float32(s.value), np.float32(f.value), np.float32(p.value), b.value) == \
                 (np.float32(s2), np.float32(f2), np.float32(p2), b2), (nb, s.value, s2, f.value, f2)
+
+
+# ------------------------------------------------------------------ harmonic F-test
+def _ftest_stats(got, ref):
+    fin = np.isfinite(ref)
+    rel = np.abs(got[fin].astype(np.float64) - ref[fin]) / np.maximum(ref[fin], 1e-30)
+    return fin, rel
+
+
+def test_mtm_harmonic_ftest_vs_reference_fixture(gpu_api):
+    """Thomson's harmonic F-test, computed by mtm_do into a file-static nothing reads (mtm.c:204-233), made live:
+    against the values the compiled reference left in that static (oracle/ref_mtm_unit.c), double path.
+    The statistic is a ratio whose denominator is what is LEFT of |y_k|^2 after removing the line component,
+    so float32 spectra reproduce it to ~1e-5 where F is moderate and to ~1e-3 on the strongest lines."""
+    for n, key in ((1024, "c3_ftest_1024"), (4096, "c3_ftest_4096")):
+        p = gpu_api.GramPlan(n=n, mode=1, overlap=0.5, sub_mean=True, mtm_w=4.0, mtm_kmax=7, mtm_ftest=True)
+        r = p.run_mtm_ftest(X8)
+        ref = G2[key]
+        assert r["ftest"].shape == ref.shape
+        fin, rel = _ftest_stats(r["ftest"], ref)
+        assert np.array_equal(np.isfinite(r["ftest"]), fin)            # inf at Nyquist (never accumulated denominator)
+        assert not fin[:, -1].any() and fin[:, :-1].all()
+        print(n, "ftest rel err: median %.2e  p99 %.2e  max %.2e  (F max %.1f)" % (np.median(rel), np.quantile(rel, 0.99), rel.max(), ref[fin].max()))
+        assert np.median(rel) < 2e-5 and np.quantile(rel, 0.99) < 1e-3 and rel.max() < 5e-2
+        # the multitaper rows of the same call are the plan's usual rows
+        assert np.array_equal(r["psd"], p.run(X8)["psd"])
+    # odd hop (block-mean table path) and a sub-range, against the oracle restatement
+    x = X8[:30000]
+    p = gpu_api.GramPlan(n=1024, mode=1, overlap=0.9, sub_mean=True, mtm_w=3.0, mtm_kmax=4, mtm_ftest=True)
+    tap, lam = p.tapers()
+    ref = O.multitaper_ftest(x, 1024, 0.9, 3.0, 4, True, tapers=tap, lam=lam)
+    got = p.run_mtm_ftest(x)["ftest"]
+    fin, rel = _ftest_stats(got, ref)
+    assert np.median(rel) < 2e-5 and np.quantile(rel, 0.99) < 1e-3
+    lo, hi = p.required_span(40, 25)
+    part = p.run_mtm_ftest(np.ascontiguousarray(x[max(lo, 0):hi]), origin=max(lo, 0), first_frame=40, nframes=25)["ftest"]
+    assert np.array_equal(part, got[40:65], equal_nan=True)
+    with pytest.raises(gpu_api.GlferError):
+        gpu_api.GramPlan(n=1024, mode=1, overlap=0.5, mtm_kmax=4).run_mtm_ftest(x)      # plan without mtm_ftest
