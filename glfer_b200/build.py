@@ -12,6 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libglfer_b200.so")
+LIB_FFTW = os.path.join(HERE, "libglfer_b200_fftw.so")      # fft_params_t in the reference's FFTW (double) layout
 OBJ = os.path.join(HERE, "_build")
 
 # (source, tag, extra flags): gram_part.cu is compiled once per subset of FFT sizes, in parallel
@@ -101,6 +102,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print("link", LIB)
         # nvcc links the static CUDA runtime: the .so depends on libcuda only at run time
         _run([nvcc, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-pthread", "-lm", "-lpthread"])
+    # the same library for callers built WITH FFTW (HAVE_LIBRFFTW): fft_params_t starts with the plan and its
+    # buffers are doubles (reference fft.h:36-48); only the per-call layer depends on the layout
+    fobjs = []
+    for o in objs:
+        if os.path.basename(o) == "dropin.c.o":
+            s = os.path.join(HERE, "host/dropin.c")
+            fo = os.path.join(OBJ, "dropin.c.fftw.o")
+            if force or _stale(fo, [s] + hdrs):
+                if verbose:
+                    print("gcc host/dropin.c -DGLFER_FFTW_LAYOUT")
+                _run(["gcc"] + C_FLAGS + ["-DGLFER_FFTW_LAYOUT", "-c", s, "-o", fo])
+            fobjs.append(fo)
+        else:
+            fobjs.append(o)
+    if force or _stale(LIB_FFTW, fobjs):
+        if verbose:
+            print("link", LIB_FFTW)
+        _run([nvcc, "-shared", "-o", LIB_FFTW] + fobjs + ["-Xcompiler", "-pthread", "-lm", "-lpthread"])
     return LIB
 
 

@@ -11,8 +11,8 @@
 // frame earlier and come from L2, so every sample still crosses HBM once.  Two CTAs (two frames in
 // flight) fit an SM, with a third fewer shared-memory wavefronts per frame.
 //
-// Geometry: hop = N / NBLK, NBLK = 1, 2, 4 (0 %, 50 %, 75 % overlap), periodogram, no RA9MB / limiter;
-// everything else stays on the 16-point kernels (gram_common.cuh).
+// Geometry: hop = N / NBLK, NBLK = 1, 2, 4 (0 %, 50 %, 75 % overlap), periodogram or multitaper, no RA9MB /
+// limiter; everything else stays on the 16-point kernels (gram_common.cuh).
 #include "gram_common.cuh"
 #include "fft_big.cuh"
 
@@ -21,11 +21,16 @@ template <int M> struct BigGeo {
   static constexpr size_t BUF_BYTES = (size_t) Big<M>::BUF * sizeof(float2);
   static constexpr size_t TW_BYTES = (size_t) Big<M>::TW1 * sizeof(float2);
   static constexpr size_t RED_BYTES = (size_t) 4 * NW * sizeof(float);
-  static constexpr size_t SMEM = BUF_BYTES + TW_BYTES + RED_BYTES + 16;        // + the mbarrier
+  static constexpr size_t ACC_BYTES = (size_t) 33 * T * sizeof(float);         // multitaper: the row being summed
+  static constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0); }
   static constexpr int MINB = (T <= 256) ? 2 : 1;
 };
 
-template <int M, int NBLK>
+// MULTI: Thomson multitaper (mtm_do, mtm.c:189-220): the frame goes through the transform once per taper -- its
+// samples land again by TMA from L2 each time, the block means are formed once -- and the eigenspectra
+// (1 / lambda_k folded into the tapers) are summed in a shared-memory row [33][T], so that the register
+// budget of the periodogram kernel (two frames per SM at N = 16384) holds for the multitaper one too.
+template <int M, int NBLK, bool MULTI>
 __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(const KParams p) {
   using G = BigGeo<M>;
   constexpr int T = G::T, N = G::N, NW = G::NW, QB = kBP / NBLK;     // QB registers (float2) per hop block
@@ -35,6 +40,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   float2 *tw1 = reinterpret_cast<float2 *>(smem_raw + G::BUF_BYTES);
   float *red = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES);
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES);
+  float *acc = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16) + threadIdx.x;   // [slot][T]
   const int t = threadIdx.x;
 
   // middle-pass twiddles exp(-2 pi i k r / (32 R1)) = roots[16 k r], one copy per CTA
@@ -45,7 +51,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   const int nact = (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group);
   const bool sub = p.fused_mean != 0;
   const bool db = p.rows_db != 0;
-  const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers) + t;
+  const int ntap = MULTI ? p.ntapers : 1;
   float *row_ptr = p.rows + fb * p.row_stride;
   long long s0 = (p.first_frame + fb) * (long long) HOP - (N - HOP);   // stream index of the frame's first sample
 
@@ -72,6 +78,9 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   __syncthreads();
 
   for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride) {
+   float bs[NBLK];
+   for (int j = 0; j < ntap; ++j) {
+    const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers + (size_t) j * N) + t;
     float2 v[kBP];
     if (bulk_ok(s0)) {
       mbar_wait(mbar, phase);
@@ -92,8 +101,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
         v[q] = make_float2(y[0], y[1]);
       }
     }
-    float bs[NBLK];
-    if (sub) {
+    if (sub && j == 0) {
       // block means (prepare_audio, fft.c:86-96): block b = registers [b QB, (b + 1) QB).  The summation tree
       // of a block does not depend on its position in the frame, so its mean is the same bits in every
       // frame (and time shard) it appears in; zero history sums to a zero mean.
@@ -109,12 +117,14 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     }
     __syncthreads();                   // (A) block sums visible; everyone has taken its samples out of the buffer
     if (sub) {
+      if (j == 0) {
 #pragma unroll
-      for (int b = 0; b < NBLK; b++) {
-        float s = 0.f;
+        for (int b = 0; b < NBLK; b++) {
+          float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < NW; w++) s += red[b * NW + w];
-        bs[b] = s * p.inv_hop_mean;
+          for (int w = 0; w < NW; w++) s += red[b * NW + w];
+          bs[b] = s * p.inv_hop_mean;
+        }
       }
 #pragma unroll
       for (int q = 0; q < kBP; q++) v[q] = sub2(v[q], bc(bs[q / QB]));
@@ -133,10 +143,15 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     big_load_last<M>(L, t, p.roots, p.vtab);
     big_load2<M>(v, t, buf);
     __syncthreads();                   // (E) the last-pass loads are done: the buffer is free for the next frame
-    if (t == 0 && it + 1 < nact && bulk_ok(s0 + HOP)) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(mbar, N * 4u);
-      tma_load_1d(buf, p.samples + (s0 + HOP - p.origin), N * 4u, mbar);
+    {
+      // what lands next: this frame again for its next taper (from L2), else the next frame
+      const bool again = j + 1 < ntap;
+      const long long sn = again ? s0 : s0 + HOP;
+      if (t == 0 && (again || it + 1 < nact) && bulk_ok(sn)) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(mbar, N * 4u);
+        tma_load_1d(buf, p.samples + (sn - p.origin), N * 4u, mbar);
+      }
     }
     big_pass2<M>(v, t, L);
     float yv[33];
@@ -144,6 +159,18 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     auto sink = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
     if (t < 32) big_emit<M, true>(v, t, L, sink);      // warp-uniform: only warp 0 pays for thread 0's re-ordering
     else big_emit<M, false>(v, t, L, sink);
+    if constexpr (MULTI) {
+      // sum over the tapers in this thread's column of the shared-memory row (own entries only: no hazard)
+      if (j > 0) {
+#pragma unroll
+        for (int sl = 0; sl < 33; sl++) yv[sl] += acc[sl * T];
+      }
+      if (j + 1 < ntap) {
+#pragma unroll
+        for (int sl = 0; sl < 33; sl++) acc[sl * T] = yv[sl];
+        continue;
+      }
+    }
     if (db) {
 #pragma unroll
       for (int s = 0; s < 33; s++) yv[s] = 10.f * log10f(yv[s]);
@@ -158,21 +185,23 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
       st_row((rp < 8 ? rb : rbh) - rp * 2 * T, yv[2 * rp + 1]);
     }
     if (t == 0) st_row(row_ptr + M / 2, yv[32]);
+   }
   }
 }
 
-template <int M, int NBLK>
+template <int M, int NBLK, bool MULTI>
 static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
   using G = BigGeo<M>;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  auto kern = gram_big_kernel<M, NBLK>;
+  auto kern = gram_big_kernel<M, NBLK, MULTI>;
+  constexpr size_t smem = G::smem(MULTI);
   static thread_local int occ_cache[64];
   int &occ = occ_cache[dev & 63];
   if (occ == 0) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) G::SMEM));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::T, G::SMEM));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::T, smem));
     if (occ < 1) occ = 1;
   }
   // resident grid: every CTA walks a contiguous run of frames (its older hop blocks stay in L2)
@@ -182,7 +211,7 @@ static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
   KParams k = kp;
   k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
   const long long ctas = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-  kern<<<(unsigned) ctas, G::T, G::SMEM, st>>>(k);
+  kern<<<(unsigned) ctas, G::T, smem, st>>>(k);
   CU(cudaGetLastError());
   g_launches++;
   g_last_family = 5;
@@ -190,23 +219,29 @@ static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
 }
 
 template <int M>
-static int launch_big_m(const KParams &kp, int groups_hint, cudaStream_t st) {
+static int launch_big_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
   const int n = 2 * M;
-  if (kp.hop == n) return launch_big<M, 1>(kp, groups_hint, st);
-  if (kp.hop == n / 2) return launch_big<M, 2>(kp, groups_hint, st);
-  if (kp.hop == n / 4) return launch_big<M, 4>(kp, groups_hint, st);
+  if (multi) {
+    if (kp.hop == n) return launch_big<M, 1, true>(kp, groups_hint, st);
+    if (kp.hop == n / 2) return launch_big<M, 2, true>(kp, groups_hint, st);
+    if (kp.hop == n / 4) return launch_big<M, 4, true>(kp, groups_hint, st);
+    return -1;
+  }
+  if (kp.hop == n) return launch_big<M, 1, false>(kp, groups_hint, st);
+  if (kp.hop == n / 2) return launch_big<M, 2, false>(kp, groups_hint, st);
+  if (kp.hop == n / 4) return launch_big<M, 4, false>(kp, groups_hint, st);
   return -1;
 }
 
 // -1: this launch is not one the big-frame kernel serves (the caller goes on to the 16-point families)
 int glb_gram_big(int m, const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
-  if (multi || kp.rows == nullptr || kp.levels != nullptr || kp.spectrum != nullptr || kp.means != nullptr) return -1;
+  if (kp.rows == nullptr || kp.levels != nullptr || kp.spectrum != nullptr || kp.means != nullptr) return -1;
   if (kp.ra9mb_a > 0.f || kp.limiter != 0 || kp.zero_hist) return -1;
   // pairs of samples are read as one 64-bit word: even offsets, 8-byte aligned base
   if ((kp.hop & 1) || (kp.origin & 1) || (reinterpret_cast<uintptr_t>(kp.samples) & 7)) return -1;
   switch (m) {
-    case 8192: return launch_big_m<8192>(kp, groups_hint, st);
-    case 16384: return launch_big_m<16384>(kp, groups_hint, st);
+    case 8192: return launch_big_m<8192>(kp, multi, groups_hint, st);
+    case 16384: return launch_big_m<16384>(kp, multi, groups_hint, st);
     default: return -1;
   }
 }

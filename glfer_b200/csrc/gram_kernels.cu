@@ -1010,29 +1010,53 @@ extern "C" int glb_launch_floor_stats(const float *rows, long long stride, int n
 // The double products and the sum are kept as separate roundings (__dmul_rn / __dadd_rn: no FMA
 // contraction), as the x86-64 reference build computes them.
 // state[0..1] = (display_max_lvl, display_min_lvl) carried between calls; stats = floor_stats rows.
+constexpr int kAgcTile = 1536;          // frames staged per tile (36 KB of static shared memory)
+
 __global__ void __launch_bounds__(256) agc_kernel(const float *__restrict__ stats, long long nframes, long long first_frame,
                                                   float overlap, int log_scale, float *__restrict__ state,
                                                   float *__restrict__ range /* [nframes][2] */) {
+  // per tile: the products (1.0 - 0.99) * stat for both chains, formed by all threads; then the two chains walk
+  // the tile out of shared memory (the loads do not depend on the chain and run ahead of it); the level of
+  // every frame goes back through shared memory and is written (and converted to dB) by all threads
+  __shared__ double s_a[2][kAgcTile];
+  __shared__ float s_lvl[2][kAgcTile];
+  __shared__ float s_state[2];
   const int tid = threadIdx.x;
-  const int chain = tid >> 5;                          // warp 0: maximum level, warp 1: minimum level
-  if (chain < 2 && (tid & 31) == 0) {
-    float lvl = state[chain];
-    for (long long i = 0; i < nframes; i++) {
-      float s = stats[4 * i + chain];
-      if (first_frame + i == 0) {                      // glfer.first_buffer == TRUE (g_main.c:1112-1120)
+  if (tid < 2) s_state[tid] = state[tid];
+  __syncthreads();
+  for (long long base = 0; base < nframes; base += kAgcTile) {
+    const int cnt = (int) ((nframes - base < kAgcTile) ? nframes - base : kAgcTile);
+    for (int i = tid; i < 2 * cnt; i += blockDim.x) {
+      const int f = i >> 1, chain = i & 1;
+      s_a[chain][f] = __dmul_rn(1.0 - 0.99, (double) stats[4 * (base + f) + chain]);
+    }
+    __syncthreads();
+    const int chain = tid >> 5;                        // warp 0: maximum level, warp 1: minimum level
+    if (chain < 2 && (tid & 31) == 0) {
+      float lvl = s_state[chain];
+      int i = 0;
+      if (first_frame + base == 0) {                   // glfer.first_buffer == TRUE (g_main.c:1112-1120)
+        float s = stats[chain];
         if (overlap > 0.0f) s /= overlap;
         lvl = s;
-      } else {                                         // g_main.c:1122-1123
-        lvl = (float) __dadd_rn(__dmul_rn(1.0 - 0.99, (double) s), __dmul_rn(0.99, (double) lvl));
+        s_lvl[chain][0] = lvl;
+        i = 1;
       }
-      range[2 * i + chain] = lvl;
+#pragma unroll 8
+      for (; i < cnt; i++) {                           // g_main.c:1122-1123
+        lvl = (float) __dadd_rn(s_a[chain][i], __dmul_rn(0.99, (double) lvl));
+        s_lvl[chain][i] = lvl;
+      }
+      s_state[chain] = lvl;
     }
-    state[chain] = lvl;
+    __syncthreads();
+    for (int i = tid; i < 2 * cnt; i += blockDim.x) {
+      const float l = s_lvl[i & 1][i >> 1];
+      range[2 * base + i] = log_scale ? (float) (10.0 * log10((double) l)) : l;      // g_main.c:1132-1135
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (log_scale) {                                     // g_main.c:1132-1135
-    for (long long i = tid; i < 2 * nframes; i += blockDim.x) range[i] = (float) (10.0 * log10((double) range[i]));
-  }
+  if (tid < 2) state[tid] = s_state[tid];
 }
 
 // levels_kernel: one warp per row.  Pixel i of a row shows bin n-1-i (g_main.c:1193-1201); in

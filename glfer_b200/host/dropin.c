@@ -78,6 +78,7 @@ typedef struct engine {
   void *tables, *stream;
   float *d_frame, *d_tapers, *d_psd, *d_spec, *d_hc, *d_phase;
   float *h_psd, *h_spec;     /* pinned */
+  float *h_frame;            /* FFTW layout: the frame converted to float for the upload (pinned) */
   int fresh;                 /* h_psd holds the PSD of the last *_do on this key */
   /* averaging engines */
   int width, depth;
@@ -123,7 +124,7 @@ static void drop_engine(const void *key)
     glb_free(e->d_frame); glb_free(e->d_tapers); glb_free(e->d_psd); glb_free(e->d_spec);
     glb_free(e->d_hc); glb_free(e->d_phase); glb_free(e->d_ring); glb_free(e->d_avg);
     glb_free(e->d_ret); glb_free(e->d_var); glb_free(e->d_cand); glb_free(e->d_lmp);
-    glb_host_free(e->h_psd); glb_host_free(e->h_spec);
+    glb_host_free(e->h_psd); glb_host_free(e->h_spec); glb_host_free(e->h_frame);
     glb_free(e->d_bstream); glb_free(e->d_brows); glb_host_free(e->h_bstream); glb_host_free(e->h_brows);
     glb_free(e->d_scratch);
     glb_tables_destroy(e->tables);
@@ -189,6 +190,7 @@ static engine *make_estimator(const void *key, int n, int ntapers, const float *
   MUST(glb_malloc((void **) &e->d_spec, sizeof(float) * 2 * (n / 2 + 1)), "malloc");
   MUST(glb_host_alloc((void **) &e->h_psd, sizeof(float) * (n / 2 + 1)), "host_alloc");
   MUST(glb_host_alloc((void **) &e->h_spec, sizeof(float) * 2 * (n / 2 + 1)), "host_alloc");
+  MUST(glb_host_alloc((void **) &e->h_frame, sizeof(float) * n), "host_alloc");
   MUST(glb_memcpy_h2d(e->d_tapers, scaled_tapers, sizeof(float) * (size_t) ntapers * n, NULL), "h2d");
   return e;
 }
@@ -242,31 +244,72 @@ void prepare_audio(float *audio_buf, fft_params_t *params)
     for (int i = 0; i < n_eff; i++) audio_buf[i] -= sig_mean;
   }
   if (!glb_first_buffer())
-    memmove(params->inbuf_audio, params->inbuf_audio + (N - n_overlap), sizeof(float) * n_overlap);
+    memmove(params->inbuf_audio, params->inbuf_audio + (N - n_overlap), sizeof(glfer_real) * n_overlap);
   else
-    memset(params->inbuf_audio, 0, sizeof(float) * n_overlap);
-  memcpy(params->inbuf_audio + n_overlap, audio_buf, sizeof(float) * n_eff);
+    memset(params->inbuf_audio, 0, sizeof(glfer_real) * n_overlap);
+  for (int i = 0; i < n_eff; i++) params->inbuf_audio[i + n_overlap] = audio_buf[i];
+  /* fft.c:127-156 with the reference's own types: inp_val and ftmp are floats, the buffers glfer_real */
   const int windowed = params->window_type != RECTANGULAR_WINDOW;
   for (int i = 0; i < N; i++) {
-    float x = params->inbuf_audio[i];
-    if (params->a > 0.0) x = x / (params->a + x * x);
-    if (windowed) x = params->window[i] * x;
-    if (params->limiter == 1) {
-      const float l = log(fabs(x));
-      x = (x > 0 ? exp(l * 0.1) : -exp(l * 0.1));
+    if (params->a > 0.0) {
+      const float inp_val = params->inbuf_audio[i];
+      params->inbuf_fft[i] = inp_val / (params->a + inp_val * inp_val);
+      if (windowed) params->inbuf_fft[i] *= params->window[i];
+    } else if (windowed) {
+      params->inbuf_fft[i] = params->window[i] * params->inbuf_audio[i];
+    } else {
+      params->inbuf_fft[i] = params->inbuf_audio[i];
     }
-    params->inbuf_fft[i] = x;
+    if (params->limiter == 1) {
+      const float ftmp = log(fabs(params->inbuf_fft[i]));
+      params->inbuf_fft[i] = (params->inbuf_fft[i] > 0 ? exp(ftmp * 0.1) : -exp(ftmp * 0.1));
+    }
   }
+}
+
+/* the three buffers of an estimator (fft.c:171-180, mtm.c:96-106, lmp.c:66-75) */
+static void alloc_buffers(fft_params_t *fp, const char *where)
+{
+  const int n = fp->n;
+  fp->inbuf_audio = calloc(n, sizeof(glfer_real));
+  fp->inbuf_fft = calloc(n, sizeof(glfer_real));
+#ifdef GLFER_FFTW_LAYOUT
+  fp->plan = NULL;
+  fp->outbuf = calloc(n, sizeof(glfer_real));
+#else
+  fp->outbuf = fp->inbuf_fft;
+#endif
+  if (!fp->inbuf_audio || !fp->inbuf_fft || !fp->outbuf) { glb_set_error("out of memory"); glb_fatal(where); }
+}
+
+static void free_buffers(fft_params_t *fp)
+{
+  free(fp->inbuf_audio); fp->inbuf_audio = NULL;
+#ifdef GLFER_FFTW_LAYOUT
+  free(fp->outbuf);
+#endif
+  free(fp->inbuf_fft); fp->inbuf_fft = NULL;
+  fp->outbuf = NULL;
+}
+
+/* the frame as the device wants it: floats (the samples ARE floats, whatever the buffer type) */
+static const float *frame_as_float(engine *e, const fft_params_t *fp)
+{
+#ifdef GLFER_FFTW_LAYOUT
+  for (int i = 0; i < fp->n; i++) e->h_frame[i] = (float) fp->inbuf_audio[i];
+  return e->h_frame;
+#else
+  (void) e;
+  return fp->inbuf_audio;
+#endif
 }
 
 void fft_init(fft_params_t *params)
 {
   const int n = params->n;
-  params->inbuf_audio = calloc(n, sizeof(float));
-  params->inbuf_fft = calloc(n, sizeof(float));
-  params->outbuf = params->inbuf_fft;            /* fft.c:180 */
+  alloc_buffers(params, "fft_init");
   params->window = malloc(n * sizeof(float));
-  if (!params->inbuf_audio || !params->inbuf_fft || !params->window) { glb_set_error("out of memory"); glb_fatal("fft_init"); }
+  if (!params->window) { glb_set_error("out of memory"); glb_fatal("fft_init"); }
   compute_window(params);
   params->sub_mean = glb_autoscale();            /* fft.c:186 */
   const float scale = (float) (1.0 / (2.0 * sqrt((double) n)));
@@ -280,7 +323,7 @@ void fft_init(fft_params_t *params)
 }
 
 /* half-complex layout of fft_real_radix2_transform / rfftw_one: out[k] = Re, out[n-k] = Im */
-static void spectrum_to_halfcomplex(const float *spec, int n, float *hc)
+static void spectrum_to_halfcomplex(const float *spec, int n, glfer_real *hc)
 {
   hc[0] = spec[0];
   for (int k = 1; k < (n + 1) / 2; k++) {
@@ -295,7 +338,7 @@ void fft_do(float *audio_buf, fft_params_t *params)
   engine *e = find_engine(params);
   if (!e) { glb_set_error("fft_do on parameters that did not go through fft_init"); glb_fatal("fft_do"); }
   prepare_audio(audio_buf, params);
-  run_frame(e, params->inbuf_audio, params->a, params->limiter, 1);
+  run_frame(e, frame_as_float(e, params), params->a, params->limiter, 1);
   spectrum_to_halfcomplex(e->h_spec, params->n, params->outbuf);   /* overwrites inbuf_fft, as in-place FFT does */
 }
 
@@ -315,7 +358,16 @@ void fft_psd(float *psd_buf, float *phase_buf, fft_params_t *params)
   engine *se = e ? e : scratch_engine();
   float *d_hc = engine_scratch(se, (size_t) n + 2 * (size_t) bins);
   float *d_psd = d_hc + n, *d_ph = d_psd + bins;
+#ifdef GLFER_FFTW_LAYOUT
+  float *hc32 = malloc(sizeof(float) * n);
+  if (!hc32) { glb_set_error("out of memory"); glb_fatal("fft_psd"); }
+  for (int i = 0; i < n; i++) hc32[i] = (float) params->outbuf[i];
+  MUST(glb_memcpy_h2d(d_hc, hc32, sizeof(float) * n, se->stream), "h2d");
+  MUST(glb_stream_sync(se->stream), "sync");
+  free(hc32);
+#else
   MUST(glb_memcpy_h2d(d_hc, params->outbuf, sizeof(float) * n, se->stream), "h2d");
+#endif
   MUST(glb_launch_halfcomplex_psd(d_hc, n, psd_buf ? d_psd : NULL, phase_buf ? d_ph : NULL, se->stream), "launch");
   if (psd_buf) {
     if (e && e->fresh) memcpy(psd_buf, e->h_psd, sizeof(float) * bins);
@@ -362,7 +414,7 @@ static void run_batch(engine *e, fft_params_t *fp, float *blocks, int nblocks, f
   }
   /* the stream the frames see: the overlap history (zeros when glfer.first_buffer, fft.c:99-108), then the blocks */
   if (glb_first_buffer()) memset(e->h_bstream, 0, sizeof(float) * n_ov);
-  else memcpy(e->h_bstream, fp->inbuf_audio + (N - n_ov), sizeof(float) * n_ov);
+  else for (int i = 0; i < n_ov; i++) e->h_bstream[i] = (float) fp->inbuf_audio[N - n_ov + i];
   memcpy(e->h_bstream + n_ov, blocks, sizeof(float) * (size_t) nblocks * hop);
   /* frame F0 + b covers stream samples [(F0 + b) hop - n_ov, (F0 + b + 1) hop) = buffer [b hop, b hop + N) */
   const long long F0 = (n_ov + hop - 1) / hop;
@@ -389,7 +441,7 @@ static void run_batch(engine *e, fft_params_t *fp, float *blocks, int nblocks, f
   MUST(glb_stream_sync(e->stream), "sync");
   memcpy(rows, e->h_brows, sizeof(float) * (size_t) nblocks * bins);
   /* history as nblocks calls leave it: the last N samples of the stream */
-  if (ns >= (size_t) N) memcpy(fp->inbuf_audio, e->h_bstream + (ns - N), sizeof(float) * N);
+  if (ns >= (size_t) N) for (int i = 0; i < N; i++) fp->inbuf_audio[i] = e->h_bstream[ns - N + i];
 }
 
 void fft_do_batch(float *audio_blocks, int nblocks, float *psd_rows, fft_params_t *params)
@@ -425,9 +477,7 @@ void mtm_do_batch(float *audio_blocks, int nblocks, float *psd_rows, mtm_params_
 void fft_close(fft_params_t *params)
 {
   drop_engine(params);
-  free(params->inbuf_audio); params->inbuf_audio = NULL;
-  free(params->inbuf_fft); params->inbuf_fft = NULL;
-  params->outbuf = NULL;
+  free_buffers(params);
   free(params->window); params->window = NULL;
 }
 
@@ -474,15 +524,13 @@ void mtm_init(mtm_params_t *params)
 {
   const int n = params->fft.n, kmax = params->kmax;
   if (kmax < 0 || kmax > 31) { fprintf(stderr, "libglfer_b200: mtm kmax %d outside 0..31\n", kmax); exit(-1); }
-  params->fft.inbuf_audio = calloc(n, sizeof(float));
-  params->fft.inbuf_fft = calloc(n, sizeof(float));
-  params->fft.outbuf = params->fft.inbuf_fft;    /* mtm.c:106 */
+  alloc_buffers(&params->fft, "mtm_init");       /* mtm.c:96-106 */
   params->fft.sub_mean = glb_autoscale();        /* mtm.c:111 */
   params->window = nr_dmatrix(1, n, 0, kmax);    /* mtm.c:118 */
   params->sig = malloc(sizeof(double) * (kmax + 1));
   double *tap = malloc(sizeof(double) * (size_t) (kmax + 1) * n);
   double *lam = malloc(sizeof(double) * (kmax + 1));
-  if (!params->fft.inbuf_audio || !params->fft.inbuf_fft || !params->sig || !tap || !lam) {
+  if (!params->sig || !tap || !lam) {
     glb_set_error("out of memory");
     glb_fatal("mtm_init");
   }
@@ -507,16 +555,14 @@ void mtm_do(float *audio_buf, float *psd_buf, float *phase_buf, mtm_params_t *pa
   engine *e = find_engine(params);
   if (!e) { glb_set_error("mtm_do on parameters that did not go through mtm_init"); glb_fatal("mtm_do"); }
   prepare_audio(audio_buf, &params->fft);
-  run_frame(e, params->fft.inbuf_audio, 0.0f, 0, 0);
+  run_frame(e, frame_as_float(e, &params->fft), 0.0f, 0, 0);
   memcpy(psd_buf, e->h_psd, sizeof(float) * (params->fft.n / 2 + 1));
 }
 
 void mtm_close(mtm_params_t *params)
 {
   drop_engine(params);
-  free(params->fft.inbuf_audio); params->fft.inbuf_audio = NULL;
-  free(params->fft.inbuf_fft); params->fft.inbuf_fft = NULL;
-  params->fft.outbuf = NULL;
+  free_buffers(&params->fft);
   if (params->window) nr_free_dmatrix(params->window, 1, 0);
   params->window = NULL;
   free(params->sig); params->sig = NULL;
@@ -527,11 +573,8 @@ void lmp_init(lmp_params_t *params)
 {
   const int n = params->fft.n, nl = params->avg;
   if (nl < 2) { fprintf(stderr, "libglfer_b200: lmp avg %d < 2 (lmp.c:145 divides by avg - 1)\n", nl); exit(-1); }
-  params->fft.inbuf_audio = calloc(n, sizeof(float));
-  params->fft.inbuf_fft = calloc(n, sizeof(float));
-  params->fft.outbuf = params->fft.inbuf_fft;    /* lmp.c:75 */
+  alloc_buffers(&params->fft, "lmp_init");       /* lmp.c:66-75 */
   params->fft.sub_mean = glb_autoscale();        /* lmp.c:80 */
-  if (!params->fft.inbuf_audio || !params->fft.inbuf_fft) { glb_set_error("out of memory"); glb_fatal("lmp_init"); }
   const float scale = (float) (1.0 / (2.0 * sqrt((double) n)));
   float *scaled = malloc(sizeof(float) * n);
   for (int i = 0; i < n; i++) scaled[i] = scale;          /* the frame goes into the FFT as it is (lmp.c:112-114) */
@@ -552,7 +595,7 @@ void lmp_do(float *audio_buf, float *psd_buf, float *phase_buf, lmp_params_t *pa
   if (!e || !e->d_lmp) { glb_set_error("lmp_do on parameters that did not go through lmp_init"); glb_fatal("lmp_do"); }
   const int n = params->fft.n, bins = n / 2 + 1;
   prepare_audio(audio_buf, &params->fft);
-  run_frame(e, params->fft.inbuf_audio, 0.0f, 0, 1);
+  run_frame(e, frame_as_float(e, &params->fft), 0.0f, 0, 1);
   spectrum_to_halfcomplex(e->h_spec, n, params->fft.outbuf);       /* the in-place FFT of lmp.c:119 */
   const int slot = (int) (e->frames % e->depth);                   /* j_l, lmp.c:124 */
   MUST(glb_memcpy_d2d(e->d_ring + (size_t) slot * bins, e->d_psd, sizeof(float) * bins, e->stream), "d2d");
@@ -567,9 +610,7 @@ void lmp_do(float *audio_buf, float *psd_buf, float *phase_buf, lmp_params_t *pa
 void lmp_close(lmp_params_t *params)
 {
   drop_engine(params);
-  free(params->fft.inbuf_audio); params->fft.inbuf_audio = NULL;
-  free(params->fft.inbuf_fft); params->fft.inbuf_fft = NULL;
-  params->fft.outbuf = NULL;
+  free_buffers(&params->fft);
 }
 
 /* ------------------------------------------------------------------ avg.h */

@@ -3,9 +3,13 @@
  * Same type, field and function names, argument meaning and ownership rules as the
  * reference's fft.h so that source.c:141-146,320-325, glfer.c:143, g_main.c:1109 and
  * g_scope.c:186-197 compile and link unchanged against this library instead of
- * fft.c + fft_radix2.c.  Layout is the reference's no-FFTW variant (fft.h:51-63: float
- * buffers, outbuf aliasing inbuf_fft, fft.c:178-180); build glfer without
- * HAVE_LIBRFFTW when linking against this library.
+ * fft.c + fft_radix2.c.  Both layouts of the reference exist:
+ *   default               the no-FFTW variant (fft.h:51-63: float buffers, outbuf aliasing inbuf_fft,
+ *                         fft.c:178-180)                                   -> libglfer_b200.so
+ *   -DGLFER_FFTW_LAYOUT   the HAVE_LIBRFFTW variant (fft.h:36-48: `fftw_plan plan` first, fftw_real =
+ *                         double buffers, outbuf a buffer of its own, fft.c:171-176; g_scope.c:189-197
+ *                         reads them as double *)                          -> libglfer_b200_fftw.so
+ * Compile the caller with the same definition as the reference build it replaces.
  *
  * What changes underneath: fft_do() runs window multiply + real FFT + |X|^2 on the
  * GPU (one frame per call here; the batched path is glfer_b200.h).  There is no CPU
@@ -19,11 +23,24 @@
 extern "C" {
 #endif
 
+#ifdef GLFER_FFTW_LAYOUT
+/* replaces fft.h:36-48 (and the two FFTW 2 types it needs: `typedef double fftw_real`, an opaque plan) */
+typedef double fftw_real;
+typedef void *fftw_plan;
+typedef fftw_real glfer_real;
+typedef struct {
+  fftw_plan plan;       /* never dereferenced by callers; the library keeps its engine handle here */
+  fftw_real *inbuf_audio;
+  fftw_real *inbuf_fft;
+  fftw_real *outbuf;    /* half-complex spectrum in a buffer of its own (fft.c:173) */
+#else
+typedef float glfer_real;
 /* replaces fft.h:51-63 */
 typedef struct {
   float *inbuf_audio;   /* N samples: (N - hop) of history + hop new ones (fft.c:98-113) */
   float *inbuf_fft;     /* windowed frame as handed to the FFT (fft.c:127-156) */
   float *outbuf;        /* half-complex spectrum, aliases inbuf_fft (fft.c:180) */
+#endif
   int n;                /* FFT size */
   float *window;        /* unit-energy window, N floats (fft.c:309-360) */
   int window_type;      /* enum below */

@@ -483,7 +483,7 @@ def test_mtm_harmonic_ftest_vs_reference_fixture(gpu_api):
     """Thomson's harmonic F-test, computed by mtm_do into a file-static nothing reads (mtm.c:204-233), made live:
     against the values the compiled reference left in that static (oracle/ref_mtm_unit.c), double path.
     The statistic is a ratio whose denominator is what is LEFT of |y_k|^2 after removing the line component,
-    so float32 spectra reproduce it to ~1e-5 where F is moderate and to ~1e-3 on the strongest lines."""
+    so float32 spectra reproduce it less closely on the strongest lines (measured: median 2e-7, worst bin 1.5e-4)."""
     for n, key in ((1024, "c3_ftest_1024"), (4096, "c3_ftest_4096")):
         p = gpu_api.GramPlan(n=n, mode=1, overlap=0.5, sub_mean=True, mtm_w=4.0, mtm_kmax=7, mtm_ftest=True)
         r = p.run_mtm_ftest(X8)
@@ -493,7 +493,8 @@ def test_mtm_harmonic_ftest_vs_reference_fixture(gpu_api):
         assert np.array_equal(np.isfinite(r["ftest"]), fin)            # inf at Nyquist (never accumulated denominator)
         assert not fin[:, -1].any() and fin[:, :-1].all()
         print(n, "ftest rel err: median %.2e  p99 %.2e  max %.2e  (F max %.1f)" % (np.median(rel), np.quantile(rel, 0.99), rel.max(), ref[fin].max()))
-        assert np.median(rel) < 2e-5 and np.quantile(rel, 0.99) < 1e-3 and rel.max() < 5e-2
+        # measured on B200: median 2e-7, 99th percentile 2e-6, worst bin 1.5e-4 (F = 493)
+        assert np.median(rel) < 2e-6 and np.quantile(rel, 0.99) < 2e-5 and rel.max() < 1e-3
         # the multitaper rows of the same call are the plan's usual rows
         assert np.array_equal(r["psd"], p.run(X8)["psd"])
     # odd hop (block-mean table path) and a sub-range, against the oracle restatement
@@ -503,9 +504,93 @@ def test_mtm_harmonic_ftest_vs_reference_fixture(gpu_api):
     ref = O.multitaper_ftest(x, 1024, 0.9, 3.0, 4, True, tapers=tap, lam=lam)
     got = p.run_mtm_ftest(x)["ftest"]
     fin, rel = _ftest_stats(got, ref)
-    assert np.median(rel) < 2e-5 and np.quantile(rel, 0.99) < 1e-3
+    assert np.median(rel) < 2e-6 and np.quantile(rel, 0.99) < 1e-4
     lo, hi = p.required_span(40, 25)
     part = p.run_mtm_ftest(np.ascontiguousarray(x[max(lo, 0):hi]), origin=max(lo, 0), first_frame=40, nframes=25)["ftest"]
     assert np.array_equal(part, got[40:65], equal_nan=True)
     with pytest.raises(gpu_api.GlferError):
         gpu_api.GramPlan(n=1024, mode=1, overlap=0.5, mtm_kmax=4).run_mtm_ftest(x)      # plan without mtm_ftest
+
+
+# ------------------------------------------------------------------ the FFTW (double buffers) struct layout
+def test_fftw_layout_library_per_call_interface(gpu_api):
+    """libglfer_b200_fftw.so: fft_params_t as the reference built WITH FFTW lays it out (fft.h:36-48: plan first,
+    fftw_real = double buffers, outbuf its own buffer).  The same calls, the same rows as the float-layout
+    library; the buffers a caller reads (g_scope.c:189-197) are doubles."""
+    import ctypes as C
+    path = os.path.join(os.path.dirname(gpu_api.LIB_PATH), "libglfer_b200_fftw.so")
+    assert os.path.exists(path)
+    lf = C.CDLL(path)
+
+    class FftParamsFFTW(C.Structure):
+        _fields_ = [("plan", C.c_void_p), ("inbuf_audio", C.POINTER(C.c_double)), ("inbuf_fft", C.POINTER(C.c_double)),
+                    ("outbuf", C.POINTER(C.c_double)), ("n", C.c_int), ("window", C.POINTER(C.c_float)),
+                    ("window_type", C.c_int), ("overlap", C.c_float), ("a", C.c_float), ("limiter", C.c_int),
+                    ("sub_mean", C.c_int)]
+
+    class MtmParamsFFTW(C.Structure):
+        _fields_ = [("fft", FftParamsFFTW), ("window", C.POINTER(C.POINTER(C.c_double))), ("sig", C.POINTER(C.c_double)),
+                    ("w", C.c_float), ("kmax", C.c_int)]
+    x = X8[:30000]
+    for n, wt, ov, a, lim in ((1024, 0, 0.5, 0.0, 0), (512, 7, 0.75, 0.02, 1)):
+        hop = gpu_api.host_hop(n, ov)
+        nb, bins = len(x) // hop, n // 2 + 1
+        p = FftParamsFFTW()
+        p.n, p.window_type, p.overlap, p.a, p.limiter = n, wt, ov, a, lim
+        lf.glfer_b200_set_autoscale(1)
+        lf.glfer_b200_set_first_buffer(1)
+        lf.fft_init(C.byref(p))
+        rows = np.empty((nb, bins), np.float32)
+        blocks = x[: nb * hop].copy().reshape(nb, hop)
+        for b in range(nb):
+            lf.fft_do(blocks[b].ctypes.data_as(C.c_void_p), C.byref(p))
+            lf.fft_psd(rows[b].ctypes.data_as(C.c_void_p), None, C.byref(p))
+            lf.glfer_b200_set_first_buffer(0)
+        ref, spec = O.periodogram(x, n, wt, ov, True, a, lim, return_spectrum=True)
+        assert_psd_close(rows, ref, f"FFTW layout n={n}")
+        hist = np.ctypeslib.as_array(p.inbuf_audio, shape=(n,))
+        assert hist.dtype == np.float64
+        want = O.gather_frames(x, n, ov, True)[-1]
+        assert np.array_equal(hist, want.astype(np.float64))          # doubles holding the float samples
+        assert C.addressof(p.outbuf.contents) != C.addressof(p.inbuf_fft.contents)      # not aliased (fft.c:173)
+        out = np.ctypeslib.as_array(p.outbuf, shape=(n,)).copy()
+        scale = np.sqrt(np.mean(np.abs(spec[-1]) ** 2))
+        assert np.abs(out[1:n // 2] - spec[-1].real[1:n // 2]).max() < 3e-6 * scale * np.sqrt(n)
+        assert np.abs(out[n - 1:n // 2:-1] - spec[-1].imag[1:n // 2]).max() < 3e-6 * scale * np.sqrt(n)
+        lf.fft_close(C.byref(p))
+    # multitaper through the same layout
+    m = MtmParamsFFTW()
+    m.fft.n, m.fft.window_type, m.fft.overlap, m.w, m.kmax = 1024, 5, 0.5, 4.0, 7
+    lf.glfer_b200_set_first_buffer(1)
+    lf.mtm_init(C.byref(m))
+    nb = len(x) // 512
+    rows = np.empty((nb, 513), np.float32)
+    blocks = x[: nb * 512].copy().reshape(nb, 512)
+    for b in range(nb):
+        lf.mtm_do(blocks[b].ctypes.data_as(C.c_void_p), rows[b].ctypes.data_as(C.c_void_p), None, C.byref(m))
+        lf.glfer_b200_set_first_buffer(0)
+    assert_psd_close(rows, O.multitaper(x, 1024, 0.5, 4.0, 7, True), "FFTW layout mtm_do")
+    lf.mtm_close(C.byref(m))
+
+
+def test_big_frame_multitaper_kernel(gpu_api):
+    """multitaper at N = 16384 / 32768 on the 32-point kernel (eigenspectra summed in shared memory, the frame
+    re-landed by TMA per taper): against the oracle and the 16-point general kernel, 0 / 50 / 75 % overlap."""
+    x = synth.qrss_stream(32768 * 9 + 333, fs=FS, seed=83, dot_s=0.2)
+    for n, ov, kmax, nw in ((16384, 0.5, 7, 4.0), (32768, 0.5, 15, 8.0), (32768, 0.75, 3, 3.0), (16384, 0.0, 2, 2.5)):
+        kw = dict(n=n, mode=1, overlap=ov, sub_mean=True, mtm_w=nw, mtm_kmax=kmax)
+        gpu_api.set_kernel_preference(0)
+        p = gpu_api.GramPlan(**kw)
+        got = p.run(x)["psd"]
+        assert gpu_api.last_kernel_family().startswith("gram_big_kernel"), gpu_api.last_kernel_family()
+        tap, lam = p.tapers()
+        ref = O.multitaper(x, n, ov, nw, kmax, True, tapers=tap, lam=lam)
+        assert_psd_close(got, ref, f"big multitaper N={n} ov={ov} K'={kmax + 1}")
+        gpu_api.set_kernel_preference(1)
+        other = gpu_api.GramPlan(**kw).run(x)["psd"]
+        gpu_api.set_kernel_preference(0)
+        assert_psd_close(got, other, "big multitaper vs general kernel")
+        nf = got.shape[0]
+        lo, hi = p.required_span(2, nf - 3)
+        part = p.run(np.ascontiguousarray(x[max(lo, 0):hi]), origin=max(lo, 0), first_frame=2, nframes=nf - 3)["psd"]
+        assert np.array_equal(part, got[2:nf - 1])

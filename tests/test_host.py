@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("fft.h", "mtm.h", "avg.h", "glfer_b200.h", "glb_shim.h"):
+    for h in ("fft.h", "mtm.h", "avg.h", "lmp.h", "glfer_b200.h", "glb_shim.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         for m in re.finditer(r"^[ \t]*(?:extern\s+)?(?:const\s+)?(?:unsigned\s+)?[A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+\**"
@@ -32,6 +32,16 @@ def test_library_exports_every_declared_symbol(built_lib):
     decl = _declared_symbols()
     assert len(decl) > 60
     missing = sorted(decl - exported)
+    assert not missing, missing
+
+
+def test_fftw_layout_library_exports_the_same_interface(built_lib):
+    """libglfer_b200_fftw.so (fft_params_t in the reference's HAVE_LIBRFFTW layout) carries every declared symbol too"""
+    path = os.path.join(os.path.dirname(built_lib), "libglfer_b200_fftw.so")
+    assert os.path.exists(path)
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    missing = sorted(_declared_symbols() - exported)
     assert not missing, missing
 
 
