@@ -500,7 +500,11 @@ __global__ void __launch_bounds__(256) avg_direct_kernel(const glb_avg_args a) {
     const long long r = a.psd_ring_rows > 0 ? g2 % a.psd_ring_rows : g2 - a.psd_first_frame;
     return a.psd + r * a.psd_stride;
   };
-  for (long long fl = warp; fl < a.nframes; fl += nwarps) {
+  // a warp takes a contiguous run of frames: consecutive frames share depth - 1 of their rows, which then
+  // come from L1 instead of L2 (the kernel is latency bound: a frame is a few hundred bytes)
+  const long long per = (a.nframes + nwarps - 1) / nwarps;
+  const long long fl_end = ((warp + 1) * per < a.nframes) ? (warp + 1) * per : a.nframes;
+  for (long long fl = warp * per; fl < fl_end; ++fl) {
     const long long f = a.first_frame + fl;
     const long long eff = (f + 1 < a.depth) ? f + 1 : a.depth;
     const long long g0 = f - eff + 1;
@@ -612,8 +616,10 @@ extern "C" int glb_launch_avg(const glb_avg_args *a, void *stream) {
   if (smem > 200 * 1024) { glb_set_error("glb_launch_avg: band too wide"); return GLB_EINVAL; }
   cudaStream_t st = (cudaStream_t) stream;
   if (!a->sequential && a->depth <= 32) {
-    long long ctas = (a->nframes * 32 + 255) / 256;
+    // runs of ~8 frames per warp
+    long long ctas = (a->nframes * 4 + 255) / 256;
     if (ctas > 148 * 64) ctas = 148 * 64;
+    if (ctas < 1) ctas = 1;
     if (a->out_double) avg_direct_kernel<double><<<(int) ctas, 256, 0, st>>>(*a);
     else avg_direct_kernel<float><<<(int) ctas, 256, 0, st>>>(*a);
     CU(cudaGetLastError());
@@ -720,12 +726,22 @@ extern "C" int glb_launch_peak_carry(const int *cand, int *peakbin, long long nf
 // (mean, then variance) in slot order and stay in L1/L2.  Double arithmetic throughout, as the
 // reference (my, sy, v_hat are doubles); IEEE sqrt and division, so inf / NaN appear exactly
 // where the reference produces them (v_hat = 0).
+// RN(x / d) for a constant divisor d with r = RN(1 / d) (Markstein): exact for finite x away from the
+// underflow range, which PSD sums are
+__device__ __forceinline__ double div_const(double x, double d, double r) {
+  const double q = __dmul_rn(x, r);
+  const double e = __fma_rn(-q, d, x);
+  return __fma_rn(e, r, q);
+}
+
 __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd, long long psd_first_frame, long long psd_stride,
                                                   int ring_rows, int nbins, long long first_frame, long long nframes, int nl,
                                                   double c0, double c1, int rows_db, float *__restrict__ out, long long out_stride) {
   const int bin = blockIdx.x * blockDim.x + threadIdx.x;
   if (bin >= nbins) return;
   // slot written by frame f = f mod nl, kept incrementally (one 64-bit division per thread)
+  const double dnl = (double) nl, dnl1 = (double) (nl - 1);
+  const double rnl = 1.0 / dnl, rnl1 = 1.0 / dnl1;          // correctly rounded reciprocals (IEEE division)
   int fm = (int) ((first_frame + blockIdx.y) % nl);
   const int fstep = (int) (gridDim.y % (unsigned) nl);
   for (long long fi = blockIdx.y; fi < nframes; fi += gridDim.y) {
@@ -738,18 +754,36 @@ __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd,
       if (d < 0) d += nl;
       return (long long) d <= f ? cur[-(long long) d * psd_stride] : 0.f;      // g = f - d < 0: never written
     };
+    // The two divisions by the integers nl and nl - 1 are done as Markstein's correctly rounded division by
+    // a constant (q = x r; e = fma(-q, d, x) exact; RN(q + e r) = RN(x / d) when r = RN(1 / d) and q is
+    // faithful): 3 double operations each instead of a general division -- the kernel is bound by the FP64
+    // pipe.  Products and sums keep the reference's separate roundings (no FMA contraction).
     double my = 0.0, sy = 0.0;
-    for (int j = 0; j < nl; j++) my += (double) row(j);
-    my /= nl;
-    for (int j = 0; j < nl; j++) {
-      const double d = (double) row(j) - my;
-      sy += d * d;
+    float rv[8];
+    const bool small = nl <= 8;                       // ring kept in registers: one read of the rows
+    if (small) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < nl) { rv[j] = row(j); my = __dadd_rn(my, (double) rv[j]); }
+    } else {
+      for (int j = 0; j < nl; j++) my = __dadd_rn(my, (double) row(j));
     }
-    sy /= (nl - 1);
-    double v = my * my - sy;
+    my = div_const(my, dnl, rnl);
+    if (small) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < nl) { const double d = __dadd_rn((double) rv[j], -my); sy = __dadd_rn(sy, __dmul_rn(d, d)); }
+    } else {
+      for (int j = 0; j < nl; j++) {
+        const double d = __dadd_rn((double) row(j), -my);
+        sy = __dadd_rn(sy, __dmul_rn(d, d));
+      }
+    }
+    sy = div_const(sy, dnl1, rnl1);
+    double v = __dadd_rn(__dmul_rn(my, my), -sy);
     if (v < 0.0) v = 0.0;
-    v = 0.5 * (my - sqrt(v));
-    float o = (float) (c0 + (nl * my) / (c1 * v));
+    v = __dmul_rn(0.5, __dadd_rn(my, -sqrt(v)));
+    float o = (float) __dadd_rn(c0, __ddiv_rn(__dmul_rn(dnl, my), __dmul_rn(c1, v)));
     if ((double) o <= 1.0e-3) o = 1e-3f;
     if (bin == 0) o = 1e-3f;
     if (rows_db) o = 10.f * log10f(o);
