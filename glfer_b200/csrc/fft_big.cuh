@@ -72,16 +72,15 @@ template <int S> struct BigDft<32, S> { static GLB_HD void run(float2 *v) { dft3
 GLB_HD void big_pass0(float2 *v) { dft32<1>(v); }
 
 template <int M> GLB_HD void big_scatter0(const float2 *v, int t, float2 *buf) {
-  float2 *dst = buf + 33 * t;
 #pragma unroll
-  for (int r = 0; r < kBP; r++) dst[r] = v[r];
+  for (int r = 0; r < kBP; r++) buf[chk<Big<M>::BUF>(33 * t + r)] = v[r];
 }
 
 template <int M> GLB_HD void big_load1(float2 *v, int t, const float2 *buf) {
   constexpr int T = Big<M>::T;
-  const float2 *src = buf + t + (t >> 5);
+  const int base = t + (t >> 5);
 #pragma unroll
-  for (int q = 0; q < kBP; q++) v[q] = src[q * (T + T / 32)];
+  for (int q = 0; q < kBP; q++) v[q] = buf[chk<Big<M>::BUF>(base + q * (T + T / 32))];
 }
 
 // pass 1: S1 butterflies of radix R1; butterfly u works on v[u + r S1]; twiddle exp(-2 pi i k r / (32 R1)),
@@ -103,22 +102,21 @@ template <int M> GLB_HD void big_pass1(float2 *v, int t, const float2 *tw1) {
 // output r' of butterfly j = t + u T is input (t >> 5) + u R1/2 of last-pass butterfly (t & 31) + 32 r'
 template <int M> GLB_HD void big_scatter1(const float2 *v, int t, float2 *buf) {
   constexpr int R1 = Big<M>::R1, S1 = Big<M>::S1;
-  float2 *dst = buf + 17 * (t & 31) + (t >> 5);
+  const int base = 17 * (t & 31) + (t >> 5);
 #pragma unroll
   for (int u = 0; u < S1; u++)
 #pragma unroll
-    for (int r = 0; r < R1; r++) dst[17 * 32 * r + u * (R1 / 2)] = v[u + r * S1];
+    for (int r = 0; r < R1; r++) buf[chk<Big<M>::BUF>(base + 17 * 32 * r + u * (R1 / 2))] = v[u + r * S1];
 }
 
 // last pass, radix 16: butterfly A = t in v[0..15], butterfly B = 2T - t (thread 0: T) in v[16..31]
 template <int M> GLB_HD void big_load2(float2 *v, int t, const float2 *buf) {
   constexpr int T = Big<M>::T;
   const int jB = (t == 0) ? T : 2 * T - t;
-  const float2 *a = buf + 17 * t, *b = buf + 17 * jB;
 #pragma unroll
   for (int r = 0; r < 16; r++) {
-    v[r] = a[r];
-    v[16 + r] = b[r];
+    v[r] = buf[chk<Big<M>::BUF>(17 * t + r)];
+    v[16 + r] = buf[chk<Big<M>::BUF>(17 * jB + r)];
   }
 }
 

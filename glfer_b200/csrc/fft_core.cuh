@@ -25,9 +25,27 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #endif
 
+// Checked build (-DGLB_CHECKED=1, glfer_b200.build.build_variant("checked", ...)): every shared-memory
+// exchange index, every bulk-copy source range and every row store is bounds-checked on the device and
+// traps on a violation.  compute-sanitizer is closed on the GPU pool this was developed on; the checked
+// library run over every kernel family (tools/sanitize_driver.py) is the memory-safety evidence instead.
+#ifndef GLB_CHECKED
+#define GLB_CHECKED 0
+#endif
+#if GLB_CHECKED && defined(__CUDA_ARCH__)
+#define GLB_CHECK(cond) do { if (!(cond)) { printf("GLB_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define GLB_CHECK(cond) do { } while (0)
+#endif
+
 namespace glb {
 
 constexpr int kPoints = 16;          // complex points per thread
+// index of an exchange-buffer access, checked against the buffer size in the checked build
+template <int LIMIT> GLB_HD int chk(int idx) {
+  GLB_CHECK(idx >= 0 && idx < LIMIT);
+  return idx;
+}
 
 // ------------------------------------------------------------------ radix plans
 // The last pass is always radix 8 with two butterflies (j, M/8 - j) per thread, so
@@ -271,7 +289,7 @@ template <int M, int P> GLB_HD int scatter_index(int base, int r) {
 template <int M>
 GLB_HD void pass_load(float2 *v, int t, const float2 *buf) {
 #pragma unroll
-  for (int q = 0; q < kPoints; q++) v[q] = buf[ld_index<M>(t, q)];
+  for (int q = 0; q < kPoints; q++) v[q] = buf[chk<BufSize<M>::value>(ld_index<M>(t, q))];
 }
 
 // Final pass: radix 8, Ns = M/8 = 2T.  Thread t owns butterflies jA = t and
@@ -472,7 +490,7 @@ GLB_HD void pass_store(float2 *v, int t, float2 *buf, const float2 *tw) {
     Dft<R, S>::run(v + u);
     const int base = scatter_base<M, P>(t, u);
 #pragma unroll
-    for (int r = 0; r < R; r++) buf[scatter_index<M, P>(base, r)] = v[u + r * S];
+    for (int r = 0; r < R; r++) buf[chk<BufSize<M>::value>(scatter_index<M, P>(base, r))] = v[u + r * S];
   }
 }
 
@@ -495,7 +513,7 @@ GLB_HD void pass_scatter(const float2 *v, int t, float2 *buf) {
   for (int u = 0; u < S; u++) {
     const int base = scatter_base<M, P>(t, u);
 #pragma unroll
-    for (int r = 0; r < R; r++) buf[scatter_index<M, P>(base, r)] = v[u + r * S];
+    for (int r = 0; r < R; r++) buf[chk<BufSize<M>::value>(scatter_index<M, P>(base, r))] = v[u + r * S];
   }
 }
 
@@ -510,14 +528,14 @@ GLB_HD void pass_scatter2(const float2 *va, const float2 *vb, int t, float4 *buf
     const int base = scatter_base<M, P>(t, u);
 #pragma unroll
     for (int r = 0; r < R; r++)
-      buf[scatter_index<M, P>(base, r)] = make_float4(va[u + r * S].x, va[u + r * S].y, vb[u + r * S].x, vb[u + r * S].y);
+      buf[chk<BufSize<M>::value>(scatter_index<M, P>(base, r))] = make_float4(va[u + r * S].x, va[u + r * S].y, vb[u + r * S].x, vb[u + r * S].y);
   }
 }
 template <int M>
 GLB_HD void pass_load2(float2 *va, float2 *vb, int t, const float4 *buf) {
 #pragma unroll
   for (int q = 0; q < kPoints; q++) {
-    const float4 e = buf[ld_index<M>(t, q)];
+    const float4 e = buf[chk<BufSize<M>::value>(ld_index<M>(t, q))];
     va[q] = make_float2(e.x, e.y);
     vb[q] = make_float2(e.z, e.w);
   }
@@ -603,8 +621,8 @@ GLB_HD void last_pass_load(float2 *v, int t, const float2 *buf) {
   const int jB = (t == 0) ? T : 2 * T - t;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    v[r] = buf[last_index<M>(jA, r)];
-    v[8 + r] = buf[last_index<M>(jB, r)];
+    v[r] = buf[chk<BufSize<M>::value>(last_index<M>(jA, r))];
+    v[8 + r] = buf[chk<BufSize<M>::value>(last_index<M>(jB, r))];
   }
 }
 template <int M>
@@ -614,7 +632,7 @@ GLB_HD void last_pass_load2(float2 *va, float2 *vb, int t, const float4 *buf) {
   const int jB = (t == 0) ? T : 2 * T - t;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    const float4 a = buf[last_index<M>(jA, r)], b = buf[last_index<M>(jB, r)];
+    const float4 a = buf[chk<BufSize<M>::value>(last_index<M>(jA, r))], b = buf[chk<BufSize<M>::value>(last_index<M>(jB, r))];
     va[r] = make_float2(a.x, a.y);
     vb[r] = make_float2(a.z, a.w);
     va[8 + r] = make_float2(b.x, b.y);

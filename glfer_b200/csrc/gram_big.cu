@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     mbar_init(mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (nact > 0 && bulk_ok(s0)) {
+      GLB_CHECK_SRC(p, p.samples + (s0 - p.origin), N);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(mbar, N * 4u);
       tma_load_1d(buf, p.samples + (s0 - p.origin), N * 4u, mbar);
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
       const bool again = j + 1 < ntap;
       const long long sn = again ? s0 : s0 + HOP;
       if (t == 0 && (again || it + 1 < nact) && bulk_ok(sn)) {
+        GLB_CHECK_SRC(p, p.samples + (sn - p.origin), N);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(mbar, N * 4u);
         tma_load_1d(buf, p.samples + (sn - p.origin), N * 4u, mbar);
@@ -179,6 +181,9 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     // rp 2T, then T + (rp - 8) 2T); consecutive threads store consecutive bins
     const int kh = big_khi<M>(t) - 16 * T;
     float *ra = row_ptr + t, *rb = row_ptr + (M - t), *rah = row_ptr + kh, *rbh = row_ptr + (M - kh);
+    GLB_CHECK_ROW(p, row_ptr);
+    GLB_CHECK_ROW(p, row_ptr + M);
+    GLB_CHECK(kh + 30 * T <= M && M - kh - 30 * T >= 0);
 #pragma unroll
     for (int rp = 0; rp < 16; rp++) {
       st_row((rp < 8 ? ra : rah) + rp * 2 * T, yv[2 * rp]);

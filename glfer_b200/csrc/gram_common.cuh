@@ -143,6 +143,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// checked build: a bulk copy must read inside the staged samples [lo, hi)
+#define GLB_CHECK_SRC(p, src, floats) GLB_CHECK((src) >= (p).samples && (src) + (floats) <= (p).samples + (p).count)
+// ... and a row store must land inside the launch's rows
+#define GLB_CHECK_ROW(p, ptr) GLB_CHECK((ptr) >= (p).rows && (ptr) < (p).rows + (p).nframes * (p).row_stride)
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -638,6 +642,7 @@ __device__ __forceinline__ void store_row(float *row, int t, const float (&yv)[1
   constexpr int T = M / kPoints;
   const int kh = khi<M>(t) - 8 * T;
   float *ra = row + t, *rb = row + (M - t), *rah = row + kh, *rbh = row + (M - kh);
+  GLB_CHECK(t >= 0 && t <= M && kh + 14 * T <= M && M - kh - 14 * T >= 0);
 #pragma unroll
   for (int rp = 0; rp < 8; rp++) {
     st_row((rp < 4 ? ra : rah) + rp * 2 * T, yv[2 * rp]);
@@ -746,6 +751,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
         float2 *z = reinterpret_cast<float2 *>(ring + (size_t) lb * hop);
         for (int i = 0; i < (1 << qs); i++) z[t + T * i] = make_float2(0.f, 0.f);
       } else if (t == 0) {
+        GLB_CHECK_SRC(p, p.samples + (blk * hop - p.origin), hop);
         mbar_expect_tx(&mbar[lb], blk_bytes);
         tma_load_1d(ring + (size_t) lb * hop, p.samples + (blk * hop - p.origin), blk_bytes, &mbar[lb]);
       }
@@ -784,6 +790,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       phase_bits ^= 1u << slot_new;
     }
     auto request_next = [&]() {
+      GLB_CHECK_SRC(p, next_src, hop);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&mbar[slot_next], blk_bytes);
       tma_load_1d(ring + (size_t) slot_next * hop, next_src, blk_bytes, &mbar[slot_next]);
@@ -872,7 +879,11 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
 #pragma unroll
             for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
           }
-          if (active) store_row<M>(row, t, yv);
+          if (active) {
+            GLB_CHECK_ROW(p, row);
+            GLB_CHECK_ROW(p, row + M);
+            store_row<M>(row, t, yv);
+          }
         }
       }
     }

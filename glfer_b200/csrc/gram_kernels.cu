@@ -269,13 +269,13 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   // N = 4096, 0.726 ms vs 0.746 ms for warp-per-frame, whose 67 KB of straight-line code per
   // frame stalls on instruction fetch; warp-per-frame stays selectable for experiments)
   int allow = 3;                                  // 1 general, 2 ring, 4 warp-per-frame, 8 pair
-  if (g_force_generic || g_kernel_pref == 1 || a->zero_history) allow = 1;     // zeroed history: general kernel only
+  if (g_force_generic || g_kernel_pref == 1 || a->zero_history || a->general_only) allow = 1;     // zeroed history: general kernel only
   else if (g_kernel_pref == 3) allow = 7;
   else if (g_kernel_pref == 4) allow = 11;
   const int m = a->n / 2;
   int rc = -1;
   // big frames: the 32-points-per-thread kernel (family 5) unless another family is asked for
-  if ((g_kernel_pref == 0 || g_kernel_pref == 5) && !g_force_generic) rc = glb_gram_big(m, k, multi, a->groups_hint, st);
+  if ((g_kernel_pref == 0 || g_kernel_pref == 5) && !g_force_generic && !a->general_only) rc = glb_gram_big(m, k, multi, a->groups_hint, st);
   if (rc != -1) return rc;
   rc = glb_gram_part_0(m, k, multi, a->groups_hint, st, allow);
   if (rc == -1) rc = glb_gram_part_1(m, k, multi, a->groups_hint, st, allow);

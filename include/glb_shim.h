@@ -78,6 +78,8 @@ typedef struct {
   float *spectrum;             /* device out: [nframes][n/2+1] (re,im) pairs, or NULL (periodogram only) */
   const void *tables;          /* from glb_tables_create(n) */
   int groups_hint;             /* 0 = auto: resident frame-groups per launch */
+  int general_only;            /* 1: general kernel whatever the geometry (plain global loads: the per-call layer hands
+                                  it pinned HOST memory, which every device access reaches over PCIe) */
   /* fused display mapping (main_window_draw, g_main.c:1186-1229): 8-bit palette indices written by the
      spectrogram kernel itself, beside or instead of the float rows; pixel i of a row shows bin n/2 - i */
   unsigned char *levels;       /* device out: [nframes][levels_stride], or NULL */

@@ -166,6 +166,9 @@ int glfer_gram_run_display_pcm16(glfer_gram_plan *plan, const short *pcm, long l
  * holds them (dB in the log scales), or NULL for the fixed levels of dc (dc->autoscale is ignored). */
 int glfer_b200_map_levels(const float *rows, long long nrows, int nbins, const glfer_display_config *dc,
                           const float *range, unsigned char *levels, int device);
+/* per-call interface (fft_do / mtm_do / lmp_do): 1 (default) = the frame is read from, and the results are written
+ * to, pinned host memory by the kernel itself (no copy-engine round trips); 0 = staged through device buffers */
+void glfer_b200_set_zero_copy(int on);
 /* testing aid: 0 = glfer_gram_run_display always maps the levels in a second pass over float rows; 1 (default) =
  * with a fixed display range and no averaging the spectrogram kernel writes the 8-bit levels itself */
 void glfer_b200_set_fused_levels(int on);
