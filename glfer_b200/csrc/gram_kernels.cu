@@ -736,12 +736,11 @@ __device__ __forceinline__ double div_const(double x, double d, double r) {
 
 __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd, long long psd_first_frame, long long psd_stride,
                                                   int ring_rows, int nbins, long long first_frame, long long nframes, int nl,
-                                                  double c0, double c1, int rows_db, float *__restrict__ out, long long out_stride) {
+                                                  double c0, double c1, double rnl, double rnl1, int rows_db, float *__restrict__ out, long long out_stride) {
   const int bin = blockIdx.x * blockDim.x + threadIdx.x;
   if (bin >= nbins) return;
   // slot written by frame f = f mod nl, kept incrementally (one 64-bit division per thread)
   const double dnl = (double) nl, dnl1 = (double) (nl - 1);
-  const double rnl = 1.0 / dnl, rnl1 = 1.0 / dnl1;          // correctly rounded reciprocals (IEEE division)
   int fm = (int) ((first_frame + blockIdx.y) % nl);
   const int fstep = (int) (gridDim.y % (unsigned) nl);
   for (long long fi = blockIdx.y; fi < nframes; fi += gridDim.y) {
@@ -807,8 +806,10 @@ extern "C" int glb_launch_lmp(const float *psd, long long psd_first_frame, long 
   // one frame per CTA row (neighbouring frames run together and share the ring rows in L1/L2;
   // a small persistent grid measured slower: 2.9 vs 2.4 ms per 84 375 rows)
   dim3 grid(xb, (unsigned) std::min<long long>(nframes, 32768));
+  // RN(1 / nl), RN(1 / (nl - 1)): IEEE divisions on the host, the same bits as on the device
+  const double rnl = 1.0 / (double) nl, rnl1 = 1.0 / (double) (nl - 1);
   lmp_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(psd, psd_first_frame, psd_stride, psd_ring_rows, nbins, first_frame, nframes, nl,
-                                                      c0, c1, rows_db, out, out_stride);
+                                                      c0, c1, rnl, rnl1, rows_db, out, out_stride);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;
