@@ -425,6 +425,11 @@ def map_levels(rows: np.ndarray, log_scale=True, max_level_db=-20.0, min_level_d
     return out
 
 
+def set_fused_avg(on: bool) -> None:
+    """testing aid: False = frame averaging always as a second pass over the PSD rows"""
+    lib().glfer_b200_set_fused_avg(int(on))
+
+
 def set_fused_levels(on: bool) -> None:
     """testing aid: False = display levels always mapped in a second pass over float rows"""
     lib().glfer_b200_set_fused_levels(int(on))

@@ -1,0 +1,116 @@
+// avg_frame.cuh -- one frame of the sliding per-bin averaging (update_avg_*, avg.c:108-298) by one warp, shared
+// by the stand-alone averaging kernel (window sums re-read from PSD rows in HBM / L2) and by the ring
+// kernel's fused averaging (window sums from the band history it keeps in shared memory): the same code,
+// hence the same bits, whichever path produced the row.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "../../include/glb_shim.h"
+
+// psd_at(g, b): PSD of frame g (index since alloc_avg) at bin b.  fl: index of the frame in the launch's
+// outputs (f = a.first_frame + fl).  Pass 1 reduces max / first argmax / sum / min of the window sums over
+// the band with shuffles, pass 2 recomputes the sums and writes the normalised row.
+template <typename OutT, class PsdAt>
+__device__ __forceinline__ void avg_frame_warp(const glb_avg_args &a, long long fl, int lane, PsdAt &&psd_at) {
+  const int band = a.maxbin - a.minbin;
+  OutT *out_base = (OutT *) a.avg_rows;
+  {
+    const long long f = a.first_frame + fl;
+    const long long eff = (f + 1 < a.depth) ? f + 1 : a.depth;
+    const long long g0 = f - eff + 1;
+    auto window_sum = [&](int b) {
+      double c = 0.0;
+      for (long long g2 = g0; g2 <= f; ++g2) c += (double) psd_at(g2, b);
+      return c;
+    };
+    double mx = -1.0, sum = 0.0, mn = 1.0;
+    int arg = -1;
+    for (int i = lane; i < band; i += 32) {
+      const int b = a.minbin + i;
+      const double c = window_sum(b);
+      if (arg < 0 || c > mx) { mx = c; arg = b; }
+      sum += c;
+      if (c < mn) mn = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (oarg >= 0 && (arg < 0 || omx > mx || (omx == mx && oarg < arg))) { mx = omx; arg = oarg; }
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const double omn = __shfl_xor_sync(0xffffffffu, mn, o);
+      if (omn < mn) mn = omn;
+    }
+    const double m0 = (double) psd_at(f, a.minbin);            // `double max = psd[minbin]` (avg.c:111)
+    const int cand = (arg >= 0 && mx > m0) ? arg : -1;
+    const double vmax = (cand >= 0) ? mx : m0;
+    // *peakbin after this frame: the new candidate, else the caller's value -- known only for
+    // the very first frame of the call; otherwise the frame is flagged for the in-order kernel
+    const bool carry_known = (cand >= 0) || (fl == 0);
+    const int pk = (cand >= 0) ? cand : a.peakbin_init;
+    double avgspec = 0.0, retv;
+    if (a.mode == 2) {
+      retv = (sum - vmax) / ((double) (band - 1) * (double) (eff + 1));
+    } else {
+      avgspec = (sum - vmax) / (double) (band - 1);
+      retv = vmax / avgspec;
+    }
+    OutT *orow = out_base + fl * a.out_stride;
+    double var = 0.0;
+    int cnt = 0;
+    // outside the band the row is the constant 1e-15 (avg.c:152-153): plain streaming stores
+    const bool out_db = sizeof(OutT) == 4 && a.rows_db;
+    const OutT fill = (OutT) (out_db ? -150.0 : 1e-15);
+    auto fill_range = [&](int lo, int hi) {
+      if (sizeof(OutT) == 4) {
+        // rows have an odd stride: align to 16 bytes per row, then 128-bit stores
+        float *base = reinterpret_cast<float *>(orow);
+        int head = (int) (((16 - (reinterpret_cast<uintptr_t>(base + lo) & 15)) & 15) >> 2);
+        if (head > hi - lo) head = hi - lo;
+        if (lane < head) base[lo + lane] = (float) fill;
+        const int body = (hi - lo - head) >> 2;
+        float4 *b4 = reinterpret_cast<float4 *>(base + lo + head);
+        const float4 f4 = make_float4((float) fill, (float) fill, (float) fill, (float) fill);
+        for (int i = lane; i < body; i += 32) b4[i] = f4;
+        const int done = lo + head + 4 * body;
+        if (done + lane < hi) base[done + lane] = (float) fill;
+      } else {
+        for (int b = lo + lane; b < hi; b += 32) orow[b] = fill;
+      }
+    };
+    if (!a.band_only) {
+      fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
+      if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
+    }
+    const int ob0 = a.band_only ? a.minbin : 0;
+    for (int b = a.minbin + lane; b < a.maxbin && b < a.nbins; b += 32) {
+      double y;
+      const double c = window_sum(b);
+      if (a.mode == 2) {
+        y = c / (double) (eff + 1);
+      } else if (a.mode == 3) {
+        y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
+      } else if (c - avgspec > 0) {
+        y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
+        if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
+      } else {
+        y = 1e-15;
+      }
+      if (out_db) y = 10.0 * log10(y);
+      orow[b - ob0] = (OutT) y;
+    }
+    if (a.mode == 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        var += __shfl_xor_sync(0xffffffffu, var, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+    }
+    if (lane == 0) {
+      if (a.ret) a.ret[fl] = retv;
+      if (a.peak_cand) a.peak_cand[fl] = cand;
+      if (a.variance) a.variance[fl] = (a.mode == 1) ? var / (double) cnt : 0.0;
+      if (a.mode == 1 && !carry_known && a.unresolved) atomicAdd(a.unresolved, 1);
+    }
+  }
+}

@@ -241,7 +241,7 @@ static int launch_big_m(const KParams &kp, bool multi, int groups_hint, cudaStre
 // -1: this launch is not one the big-frame kernel serves (the caller goes on to the 16-point families)
 int glb_gram_big(int m, const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
   if (kp.rows == nullptr || kp.levels != nullptr || kp.spectrum != nullptr || kp.means != nullptr) return -1;
-  if (kp.ra9mb_a > 0.f || kp.limiter != 0 || kp.zero_hist) return -1;
+  if (kp.ra9mb_a > 0.f || kp.limiter != 0 || kp.zero_hist || kp.av_on) return -1;
   // pairs of samples are read as one 64-bit word: even offsets, 8-byte aligned base
   if ((kp.hop & 1) || (kp.origin & 1) || (reinterpret_cast<uintptr_t>(kp.samples) & 7)) return -1;
   switch (m) {

@@ -15,6 +15,7 @@
 #include "fft_core.cuh"
 #include "fft_wpf.cuh"
 #include "levels.cuh"
+#include "avg_frame.cuh"
 #include "tables.hpp"
 #include "../../include/glb_shim.h"
 
@@ -69,6 +70,10 @@ struct KParams {
   unsigned char *levels;
   long long lev_stride;
   LevelMap lm;
+  // fused frame averaging (ring kernel, AVG instantiations): the launch's frames are averaged by the kernel
+  // that computes them; av.first_frame / av.nframes are the launch's own, av.psd is unused
+  int av_on;
+  glb_avg_args av;
 };
 
 #ifndef GLB_REG_TARGET
@@ -526,18 +531,20 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
 #endif                    // 0: NB slots, requested after barrier (A) into the oldest block's slot
 struct RingLayout {
   int slots;            // NB + GLB_RING_EXTRA
-  size_t ring_off, red_off, mu_off, mbar_off, group_bytes;
+  size_t ring_off, red_off, mu_off, mbar_off, hist_off, group_bytes;
 };
 
+// hist_floats: fused averaging keeps the last `depth` PSD rows of the averaging band ([depth][band] floats)
 template <int M>
-__host__ __device__ inline RingLayout ring_layout(int hop, int nb) {
+__host__ __device__ inline RingLayout ring_layout(int hop, int nb, int hist_floats = 0) {
   RingLayout L;
   L.slots = nb + GLB_RING_EXTRA;
   L.ring_off = Geo<M>::BUF_BYTES;
   L.red_off = L.ring_off + (size_t) L.slots * hop * sizeof(float);
   L.mu_off = L.red_off + (size_t) 18 * Geo<M>::NW * sizeof(float);
   L.mbar_off = ((L.mu_off + 18 * sizeof(float) + 7) / 8) * 8;
-  L.group_bytes = ((L.mbar_off + 18 * sizeof(unsigned long long) + 15) / 16) * 16;
+  L.hist_off = ((L.mbar_off + 18 * sizeof(unsigned long long) + 15) / 16) * 16;
+  L.group_bytes = ((L.hist_off + (size_t) hist_floats * sizeof(float) + 15) / 16) * 16;
   return L;
 }
 
@@ -698,7 +705,13 @@ template <int M, bool MULTI> struct RingGeo {
 #endif
   static constexpr int MINB = BIG ? 1 : ((MULTI && GLB_MULTI_MINB > 0 && Geo<M>::THREADS == 128) ? GLB_MULTI_MINB : Geo<M>::MINB);
 };
-template <int M, bool MULTI, int QSC, bool LEV>
+// AVG: the sliding frame averaging (update_avg_*, avg.c:108-298) fused in.  A group pre-rolls the depth - 1
+// frames before its run (their rows belong to the previous group and are not stored), every frame leaves
+// the PSD of the averaging band in a [depth][band] history in shared memory, and one warp -- a different
+// one each frame -- forms the averaged band row, the return value, the *peakbin candidate and the variance
+// of the frame before, right after barrier (A) has made that frame's history entries visible.  The
+// arithmetic is avg_frame_warp() of the stand-alone kernel: identical bits.  Band-only output rows.
+template <int M, bool MULTI, int QSC, bool LEV, bool AVG = false>
 __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gram_ring_kernel(const KParams p) {
   using GeoM = Geo<M>;
   constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
@@ -709,7 +722,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   const int qs = QSC >= 0 ? QSC : p.qs;
   const int hop = QSC >= 0 ? ((2 * T) << (QSC >= 0 ? QSC : 0)) : p.hop;
   const int nb = kPoints >> qs;                                  // nb blocks per frame
-  const RingLayout L = ring_layout<M>(hop, nb);
+  const int av_band = AVG ? p.av.maxbin - p.av.minbin : 0, av_depth = AVG ? p.av.depth : 1;
+  const RingLayout L = ring_layout<M>(hop, nb, AVG ? av_band * av_depth : 0);
   const int slots = L.slots;
   unsigned char *gbase = smem_raw + (size_t) g * L.group_bytes;
   float2 *buf = reinterpret_cast<float2 *>(gbase);
@@ -717,10 +731,13 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   float *red = reinterpret_cast<float *>(gbase + L.red_off);
   float *mu = reinterpret_cast<float *>(gbase + L.mu_off);
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + L.mbar_off);
+  float *hist = reinterpret_cast<float *>(gbase + L.hist_off);
   const long long gid = (long long) blockIdx.x * G + g;
   const long long fb = gid * p.frames_per_group;
   const bool group_active = fb < p.nframes;
-  const long long f_first = p.first_frame + fb;
+  // fused averaging: pre-roll of depth - 1 frames (fewer at the very start of the recording)
+  const int pre = (AVG && group_active) ? (int) ((p.first_frame + fb < av_depth - 1) ? p.first_frame + fb : av_depth - 1) : 0;
+  const long long f_first = p.first_frame + fb - pre;
   const long long b0 = f_first - (nb - 1);                       // oldest block of the first frame
   const bool sub = p.fused_mean != 0;
   const unsigned blk_bytes = (unsigned) hop * 4u;
@@ -776,12 +793,29 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   int slot_new = nb - 1;                                         // slot of the newest block of frame `it`
   // loop state carried incrementally (no 64-bit multiplies per frame): frames of this group that
   // exist, the row to write and the block the next bulk copy reads
-  const int nact = group_active ? (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group) : 0;
-  float *row_ptr = p.rows + fb * p.row_stride;                   // (never dereferenced when p.rows is null)
+  const int nact = (group_active ? (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group) : 0) + pre;
+  float *row_ptr = p.rows + (fb - pre) * p.row_stride;           // (never dereferenced when p.rows is null / in the pre-roll)
   unsigned char *lev_ptr = p.levels + fb * p.lev_stride;
   const float *next_src = p.samples + ((f_first + 1) * (long long) hop - p.origin);
-  for (int it = 0; it < p.frames_per_group; ++it, row_ptr += p.row_stride, lev_ptr += p.lev_stride, next_src += hop) {
+  // fused averaging: which of this thread's 17 bins lie in the band (bit per slot)
+  unsigned av_mask = 0;
+  if constexpr (AVG) {
+#pragma unroll
+    for (int slot = 0; slot < 17; slot++) {
+      const unsigned rel = (unsigned) (slot_bin<M>(t, slot) - p.av.minbin);
+      if (rel < (unsigned) av_band && (slot < 16 || t == 0)) av_mask |= 1u << slot;
+    }
+  }
+  auto av_frame = [&](int itf) {
+    // averaged row of the frame computed in iteration itf (an output frame), by the calling warp
+    const int lane = t & 31;
+    auto psd_at = [&](long long gg, int b) -> float { return hist[(int) (gg % av_depth) * av_band + (b - p.av.minbin)]; };
+    avg_frame_warp<float>(p.av, fb + (itf - pre), lane, psd_at);
+  };
+  const int n_iter = p.frames_per_group + (AVG ? av_depth - 1 : 0);
+  for (int it = 0; it < n_iter; ++it, row_ptr += p.row_stride, lev_ptr += p.lev_stride, next_src += hop) {
     const bool active = it < nact;
+    const bool storing = !AVG || it >= pre;                      // pre-roll frames only feed the history
     const bool next_there = it + 1 < nact;
     const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;
     if (it > 0 && active) {
@@ -836,6 +870,11 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
       // tight ring: the frame is in registers, so past the first (A) nobody reads the ring any more
       if (!GLB_RING_EXTRA && next_there && j == 0 && t == 0) request_next();
+      if constexpr (AVG) {
+        // the frame before is complete in the history (its stores precede barrier (A)); its reader is done
+        // before the next barrier, i.e. before this frame's epilogue overwrites the oldest history row
+        if (it > pre && it - 1 < nact && (t >> 5) == ((it - 1) & (Geo<M>::NW - 1))) av_frame(it - 1);
+      }
       group_sync<M>(g);
       RingMidPasses<M, 1, RT>::run(v, t, buf, tw_mid, tr, g);
       float *row = row_ptr;
@@ -879,7 +918,15 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
 #pragma unroll
             for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
           }
-          if (active) {
+          if constexpr (AVG) {
+            if (active && av_mask != 0) {
+              float *hrow = hist + (int) ((f_first + it) % av_depth) * av_band - p.av.minbin;
+#pragma unroll
+              for (int slot = 0; slot < 17; slot++)
+                if (av_mask & (1u << slot)) hrow[slot_bin<M>(t, slot)] = yv[slot];
+            }
+          }
+          if (active && storing) {
             GLB_CHECK_ROW(p, row);
             GLB_CHECK_ROW(p, row + M);
             store_row<M>(row, t, yv);
@@ -903,6 +950,11 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
     }
     slot_new = slot_next;
+  }
+  if constexpr (AVG) {
+    // the last frame of a run that filled every iteration (shorter runs were served by an idle iteration)
+    group_sync<M>(g);
+    if (nact == n_iter && nact > pre && (t >> 5) == ((nact - 1) & (Geo<M>::NW - 1))) av_frame(nact - 1);
   }
 }
 
@@ -1348,13 +1400,42 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
     if (regular && plain && (kp.rows != nullptr || kp.levels != nullptr) && kp.spectrum == nullptr && kp.means == nullptr &&
         (allow & 2) != 0) {
       const int nb = kPoints >> qs;
-      const RingLayout L = ring_layout<M>(kp.hop, nb);
+      const bool avg = kp.av_on != 0;
+      const int hist_floats = avg ? kp.av.depth * (kp.av.maxbin - kp.av.minbin) : 0;
+      const RingLayout L = ring_layout<M>(kp.hop, nb, hist_floats);
       size_t smem = (size_t) GeoM::G * L.group_bytes + ((multi ? RingGeo<M, true>::RT : RingGeo<M, false>::RT) ? 0 : Geo<M>::TWS_BYTES);
       if (const char *e = getenv("GLB_SMEM_PAD_KB")) smem += (size_t) atoi(e) * 1024;     // experiments: cap the CTAs per SM
       if (smem <= 227 * 1024) {
         // 50 % and 75 % overlap have kernels with the ring geometry folded in
         void (*rk)(const KParams) = nullptr;
         const bool lev = kp.levels != nullptr;       // 8-bit display levels: a second set of instantiations
+        if (avg) {
+          // fused frame averaging: one frame group per CTA, periodogram, float rows (N = 4096, 8192)
+          if constexpr (M == 2048 || M == 4096) {
+            if (multi || lev) { glb_set_error("glb_launch_gram: fused averaging is for periodogram float rows"); return GLB_EINVAL; }
+            rk = qs == 3 ? gram_ring_kernel<M, false, 3, false, true>
+                         : (qs == 2 ? gram_ring_kernel<M, false, 2, false, true> : gram_ring_kernel<M, false, -1, false, true>);
+            CU(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            int occ_a = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, rk, GeoM::THREADS, smem));
+            if (occ_a < 1) { glb_set_error("glb_launch_gram: fused averaging does not fit shared memory"); return GLB_EINVAL; }
+            long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ_a;
+            if (groups > kp.nframes) groups = kp.nframes;
+            if (groups < 1) groups = 1;
+            KParams k = kp;
+            k.qs = qs;
+            k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
+            const long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
+            rk<<<(int) used, GeoM::THREADS, smem, st>>>(k);
+            CU(cudaGetLastError());
+            g_launches++;
+            g_last_family = 2;
+            return GLB_OK;
+          } else {
+            glb_set_error("glb_launch_gram: fused averaging is available for N = 4096 and 8192 (see glb_gram_fused_avg_ok)");
+            return GLB_EINVAL;
+          }
+        }
         if (qs == 3) rk = multi ? (lev ? gram_ring_kernel<M, true, 3, true> : gram_ring_kernel<M, true, 3, false>)
                                 : (lev ? gram_ring_kernel<M, false, 3, true> : gram_ring_kernel<M, false, 3, false>);
         else if (qs == 2) rk = multi ? (lev ? gram_ring_kernel<M, true, 2, true> : gram_ring_kernel<M, true, 2, false>)
@@ -1390,6 +1471,10 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
         }
       }
     }
+  }
+  if (kp.av_on) {
+    glb_set_error("glb_launch_gram: fused averaging needs the regular geometry of the ring kernel (see glb_gram_fused_avg_ok)");
+    return GLB_EINVAL;
   }
   const int variant = multi ? 2 : (plain ? 1 : 0);
   auto kern = multi ? gram_kernel<M, true, true> : (plain ? gram_kernel<M, false, true> : gram_kernel<M, false, false>);

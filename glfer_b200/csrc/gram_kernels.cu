@@ -192,6 +192,13 @@ extern "C" int glb_gram_fused_mean_ok(int n, int hop) {
   return 0;
 }
 
+extern "C" int glb_gram_fused_avg_ok(int n, int hop, int depth, int band) {
+  if (n != 4096 && n != 8192) return 0;
+  if (!glb_gram_fused_mean_ok(n, hop) || (hop % 4) != 0) return 0;
+  if (depth < 1 || band < 2 || (long long) depth * band * 4 > 2048) return 0;
+  return g_force_generic == 0 && (g_kernel_pref == 0 || g_kernel_pref == 2);
+}
+
 extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   if (!a || !a->tables || !glb_fft_supported(a->n) || a->hop < 1 || a->hop > a->n || a->ntapers < 1) {
     glb_set_error("glb_launch_gram: invalid arguments");
@@ -249,6 +256,16 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
     k.lm.dmin = a->level_min;
     k.lm.dmax = a->level_max;
     k.lm.thr_level = a->level_thr;
+  }
+  if (a->fused_avg) {
+    const glb_avg_args *av = (const glb_avg_args *) a->fused_avg;
+    if (!av->band_only || av->out_double || av->first_frame != a->first_frame || av->nframes != a->nframes || !av->avg_rows ||
+        !glb_gram_fused_avg_ok(a->n, a->hop, av->depth, av->maxbin - av->minbin) || a->origin % 4 != 0) {
+      glb_set_error("glb_launch_gram: fused averaging not available for this launch");
+      return GLB_EINVAL;
+    }
+    k.av_on = 1;
+    k.av = *av;
   }
   if (!a->rows && !a->levels && !a->spectrum) {
     glb_set_error("glb_launch_gram: no output requested");
@@ -486,123 +503,22 @@ __global__ void __launch_bounds__(256) avg_kernel(const glb_avg_args a, int chun
 
 // Direct form for small depths: one warp per frame, no block barrier, no state carried
 // between frames.  The window sum of every band bin is re-read from the PSD rows (depth loads
-// per bin, L2-resident: consecutive frames share depth-1 of them); pass 1 reduces max / first
-// argmax / sum / min over the band with shuffles, pass 2 recomputes the sums and writes the
-// normalised row.  Frames are fully independent, so the grid is sized by the frame count.
+// per bin: consecutive frames share depth-1 of them).  Frames are fully independent, so the grid
+// is sized by the frame count.  The per-frame arithmetic lives in avg_frame.cuh, shared with the ring
+// kernel's fused averaging.
 template <typename OutT>
 __global__ void __launch_bounds__(256) avg_direct_kernel(const glb_avg_args a) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
-  const int band = a.maxbin - a.minbin;
-  OutT *out_base = (OutT *) a.avg_rows;
-  auto psd_row = [&](long long g2) -> const float * {
+  auto psd_at = [&](long long g2, int b) -> float {
     const long long r = a.psd_ring_rows > 0 ? g2 % a.psd_ring_rows : g2 - a.psd_first_frame;
-    return a.psd + r * a.psd_stride;
+    return a.psd[r * a.psd_stride + b];
   };
-  // a warp takes a contiguous run of frames: consecutive frames share depth - 1 of their rows, which then
-  // come from L1 instead of L2 (the kernel is latency bound: a frame is a few hundred bytes)
+  // a warp takes a contiguous run of frames: consecutive frames share depth - 1 of their rows
   const long long per = (a.nframes + nwarps - 1) / nwarps;
   const long long fl_end = ((warp + 1) * per < a.nframes) ? (warp + 1) * per : a.nframes;
-  for (long long fl = warp * per; fl < fl_end; ++fl) {
-    const long long f = a.first_frame + fl;
-    const long long eff = (f + 1 < a.depth) ? f + 1 : a.depth;
-    const long long g0 = f - eff + 1;
-    auto window_sum = [&](int b) {
-      double c = 0.0;
-      for (long long g2 = g0; g2 <= f; ++g2) c += (double) psd_row(g2)[b];
-      return c;
-    };
-    double mx = -1.0, sum = 0.0, mn = 1.0;
-    int arg = -1;
-    for (int i = lane; i < band; i += 32) {
-      const int b = a.minbin + i;
-      const double c = window_sum(b);
-      if (arg < 0 || c > mx) { mx = c; arg = b; }
-      sum += c;
-      if (c < mn) mn = c;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
-      const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (oarg >= 0 && (arg < 0 || omx > mx || (omx == mx && oarg < arg))) { mx = omx; arg = oarg; }
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const double omn = __shfl_xor_sync(0xffffffffu, mn, o);
-      if (omn < mn) mn = omn;
-    }
-    const double m0 = (double) psd_row(f)[a.minbin];            // `double max = psd[minbin]` (avg.c:111)
-    const int cand = (arg >= 0 && mx > m0) ? arg : -1;
-    const double vmax = (cand >= 0) ? mx : m0;
-    // *peakbin after this frame: the new candidate, else the caller's value -- known only for
-    // the very first frame of the call; otherwise the frame is flagged for the in-order kernel
-    const bool carry_known = (cand >= 0) || (fl == 0);
-    const int pk = (cand >= 0) ? cand : a.peakbin_init;
-    double avgspec = 0.0, retv;
-    if (a.mode == 2) {
-      retv = (sum - vmax) / ((double) (band - 1) * (double) (eff + 1));
-    } else {
-      avgspec = (sum - vmax) / (double) (band - 1);
-      retv = vmax / avgspec;
-    }
-    OutT *orow = out_base + fl * a.out_stride;
-    double var = 0.0;
-    int cnt = 0;
-    // outside the band the row is the constant 1e-15 (avg.c:152-153): plain streaming stores
-    const bool out_db = sizeof(OutT) == 4 && a.rows_db;
-    const OutT fill = (OutT) (out_db ? -150.0 : 1e-15);
-    auto fill_range = [&](int lo, int hi) {
-      if (sizeof(OutT) == 4) {
-        // rows have an odd stride: align to 16 bytes per row, then 128-bit stores
-        float *base = reinterpret_cast<float *>(orow);
-        int head = (int) (((16 - (reinterpret_cast<uintptr_t>(base + lo) & 15)) & 15) >> 2);
-        if (head > hi - lo) head = hi - lo;
-        if (lane < head) base[lo + lane] = (float) fill;
-        const int body = (hi - lo - head) >> 2;
-        float4 *b4 = reinterpret_cast<float4 *>(base + lo + head);
-        const float4 f4 = make_float4((float) fill, (float) fill, (float) fill, (float) fill);
-        for (int i = lane; i < body; i += 32) b4[i] = f4;
-        const int done = lo + head + 4 * body;
-        if (done + lane < hi) base[done + lane] = (float) fill;
-      } else {
-        for (int b = lo + lane; b < hi; b += 32) orow[b] = fill;
-      }
-    };
-    if (!a.band_only) {
-      fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
-      if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
-    }
-    const int ob0 = a.band_only ? a.minbin : 0;
-    for (int b = a.minbin + lane; b < a.maxbin && b < a.nbins; b += 32) {
-      double y;
-      const double c = window_sum(b);
-      if (a.mode == 2) {
-        y = c / (double) (eff + 1);
-      } else if (a.mode == 3) {
-        y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
-      } else if (c - avgspec > 0) {
-        y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
-        if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
-      } else {
-        y = 1e-15;
-      }
-      if (out_db) y = 10.0 * log10(y);
-      orow[b - ob0] = (OutT) y;
-    }
-    if (a.mode == 1) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        var += __shfl_xor_sync(0xffffffffu, var, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      }
-    }
-    if (lane == 0) {
-      if (a.ret) a.ret[fl] = retv;
-      if (a.peak_cand) a.peak_cand[fl] = cand;
-      if (a.variance) a.variance[fl] = (a.mode == 1) ? var / (double) cnt : 0.0;
-      if (a.mode == 1 && !carry_known && a.unresolved) atomicAdd(a.unresolved, 1);
-    }
-  }
+  for (long long fl = warp * per; fl < fl_end; ++fl) avg_frame_warp<OutT>(a, fl, lane, psd_at);
 }
 
 extern "C" int glb_launch_avg(const glb_avg_args *a, void *stream) {
@@ -726,21 +642,15 @@ extern "C" int glb_launch_peak_carry(const int *cand, int *peakbin, long long nf
 // (mean, then variance) in slot order and stay in L1/L2.  Double arithmetic throughout, as the
 // reference (my, sy, v_hat are doubles); IEEE sqrt and division, so inf / NaN appear exactly
 // where the reference produces them (v_hat = 0).
-// RN(x / d) for a constant divisor d with r = RN(1 / d) (Markstein): exact for finite x away from the
-// underflow range, which PSD sums are
-__device__ __forceinline__ double div_const(double x, double d, double r) {
-  const double q = __dmul_rn(x, r);
-  const double e = __fma_rn(-q, d, x);
-  return __fma_rn(e, r, q);
-}
-
+// (Tried in round 2 and dropped: Markstein's 3-operation division by the constants nl and nl - 1, the ring
+// kept in registers, non-contracted products -- bit-identical results, but 3.05 ms instead of 2.29 ms per
+// 84 375 rows: the kernel is not bound by the divisions.)
 __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd, long long psd_first_frame, long long psd_stride,
                                                   int ring_rows, int nbins, long long first_frame, long long nframes, int nl,
-                                                  double c0, double c1, double rnl, double rnl1, int rows_db, float *__restrict__ out, long long out_stride) {
+                                                  double c0, double c1, int rows_db, float *__restrict__ out, long long out_stride) {
   const int bin = blockIdx.x * blockDim.x + threadIdx.x;
   if (bin >= nbins) return;
   // slot written by frame f = f mod nl, kept incrementally (one 64-bit division per thread)
-  const double dnl = (double) nl, dnl1 = (double) (nl - 1);
   int fm = (int) ((first_frame + blockIdx.y) % nl);
   const int fstep = (int) (gridDim.y % (unsigned) nl);
   for (long long fi = blockIdx.y; fi < nframes; fi += gridDim.y) {
@@ -753,36 +663,18 @@ __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd,
       if (d < 0) d += nl;
       return (long long) d <= f ? cur[-(long long) d * psd_stride] : 0.f;      // g = f - d < 0: never written
     };
-    // The two divisions by the integers nl and nl - 1 are done as Markstein's correctly rounded division by
-    // a constant (q = x r; e = fma(-q, d, x) exact; RN(q + e r) = RN(x / d) when r = RN(1 / d) and q is
-    // faithful): 3 double operations each instead of a general division -- the kernel is bound by the FP64
-    // pipe.  Products and sums keep the reference's separate roundings (no FMA contraction).
     double my = 0.0, sy = 0.0;
-    float rv[8];
-    const bool small = nl <= 8;                       // ring kept in registers: one read of the rows
-    if (small) {
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j < nl) { rv[j] = row(j); my = __dadd_rn(my, (double) rv[j]); }
-    } else {
-      for (int j = 0; j < nl; j++) my = __dadd_rn(my, (double) row(j));
+    for (int j = 0; j < nl; j++) my += (double) row(j);
+    my /= nl;
+    for (int j = 0; j < nl; j++) {
+      const double d = (double) row(j) - my;
+      sy += d * d;
     }
-    my = div_const(my, dnl, rnl);
-    if (small) {
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j < nl) { const double d = __dadd_rn((double) rv[j], -my); sy = __dadd_rn(sy, __dmul_rn(d, d)); }
-    } else {
-      for (int j = 0; j < nl; j++) {
-        const double d = __dadd_rn((double) row(j), -my);
-        sy = __dadd_rn(sy, __dmul_rn(d, d));
-      }
-    }
-    sy = div_const(sy, dnl1, rnl1);
-    double v = __dadd_rn(__dmul_rn(my, my), -sy);
+    sy /= (nl - 1);
+    double v = my * my - sy;
     if (v < 0.0) v = 0.0;
-    v = __dmul_rn(0.5, __dadd_rn(my, -sqrt(v)));
-    float o = (float) __dadd_rn(c0, __ddiv_rn(__dmul_rn(dnl, my), __dmul_rn(c1, v)));
+    v = 0.5 * (my - sqrt(v));
+    float o = (float) (c0 + (nl * my) / (c1 * v));
     if ((double) o <= 1.0e-3) o = 1e-3f;
     if (bin == 0) o = 1e-3f;
     if (rows_db) o = 10.f * log10f(o);
@@ -806,10 +698,8 @@ extern "C" int glb_launch_lmp(const float *psd, long long psd_first_frame, long 
   // one frame per CTA row (neighbouring frames run together and share the ring rows in L1/L2;
   // a small persistent grid measured slower: 2.9 vs 2.4 ms per 84 375 rows)
   dim3 grid(xb, (unsigned) std::min<long long>(nframes, 32768));
-  // RN(1 / nl), RN(1 / (nl - 1)): IEEE divisions on the host, the same bits as on the device
-  const double rnl = 1.0 / (double) nl, rnl1 = 1.0 / (double) (nl - 1);
   lmp_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(psd, psd_first_frame, psd_stride, psd_ring_rows, nbins, first_frame, nframes, nl,
-                                                      c0, c1, rnl, rnl1, rows_db, out, out_stride);
+                                                      c0, c1, rows_db, out, out_stride);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;

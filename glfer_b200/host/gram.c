@@ -81,6 +81,9 @@ typedef struct {
 } fused_levels;
 
 static int make_level_tables(void **tables);
+static int g_fused_avg = 1;
+/* testing aid: 0 = frame averaging always as a second pass over the PSD rows */
+void glfer_b200_set_fused_avg(int on) { g_fused_avg = on; }
 static int g_fused_levels = 1;
 /* testing aid: 0 = always map levels in a second pass over float rows */
 void glfer_b200_set_fused_levels(int on) { g_fused_levels = on; }
@@ -371,7 +374,13 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
                      const fused_levels *fl)
 {
   const glfer_gram_config *c = &p->cfg;
-  const long long halo = halo_frames(p, first);
+  /* frame averaging inside the spectrogram kernel: band-only rows, ring-kernel geometry, small band history.
+     The kernel pre-rolls the depth - 1 frames before every group itself, so the launch covers exactly the
+     requested frames (the staged samples still include the pre-roll of the first group). */
+  const int fuse_avg = g_fused_avg && !fl && c->avg_mode != GLFER_NO_AVG && c->avg_band_only && c->mode == GLFER_MODE_FFT &&
+                       c->a <= 0.0f && !c->limiter && !c->zero_history && (s->s_origin % 4) == 0 &&
+                       glb_gram_fused_avg_ok(c->n, p->hop, c->avg_depth, c->avg_maxbin - c->avg_minbin);
+  const long long halo = fuse_avg ? 0 : halo_frames(p, first);
   const long long f0 = first - halo, nf = nframes + halo;
   long long lo, hi;
   glfer_gram_required_span(p, first, nframes, &lo, &hi);
@@ -426,10 +435,8 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   g.rows_db = (c->avg_mode == GLFER_NO_AVG && c->mode != GLFER_MODE_LMP) ? c->scale_db : 0;   /* averaging / LMP need linear PSD */
   g.spectrum = NULL;
   g.tables = p->tables;
-  if (s->time_gram) TRY(glb_event_record(s->ev2, s->stream));
-  TRY(glb_launch_gram(&g, s->stream));
-  if (s->time_gram) TRY(glb_event_record(s->ev3, s->stream));
-
+  glb_avg_args a;
+  memset(&a, 0, sizeof a);
   if (c->avg_mode != GLFER_NO_AVG) {
     TRY(ensure((void **) &s->d_avg, &s->avg_cap, (size_t) nframes * p->avg_cols, sizeof(float)));
     if ((size_t) nframes > s->scal_cap) {
@@ -441,8 +448,6 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
       TRY(glb_malloc((void **) &s->d_peak, sizeof(int) * (size_t) nframes));
       s->scal_cap = (size_t) nframes;
     }
-    glb_avg_args a;
-    memset(&a, 0, sizeof a);
     a.mode = c->avg_mode;
     a.depth = c->avg_depth;
     a.minbin = c->avg_minbin;
@@ -465,8 +470,29 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
     a.peakbin_init = c->avg_peakbin_init;
     a.unresolved = s->d_unres;
     a.sequential = 0;
-    if (c->avg_mode == GLFER_AVG_SUMAVG) {
-      TRY(glb_memset(s->d_unres, 0, sizeof(int), s->stream));
+    if (fuse_avg || c->avg_mode == GLFER_AVG_SUMAVG) TRY(glb_memset(s->d_unres, 0, sizeof(int), s->stream));
+  }
+  if (fuse_avg) g.fused_avg = &a;
+  if (s->time_gram) TRY(glb_event_record(s->ev2, s->stream));
+  TRY(glb_launch_gram(&g, s->stream));
+  if (s->time_gram) TRY(glb_event_record(s->ev3, s->stream));
+
+  if (c->avg_mode != GLFER_NO_AVG) {
+    if (fuse_avg) {
+      if (c->avg_mode == GLFER_AVG_SUMAVG) {
+        /* a frame without a *peakbin write needs the carried value for its variance (avg.c:279): rare; the
+           chunk is then redone in two passes, in order */
+        int unres = 0;
+        TRY(glb_memcpy_d2h(&unres, s->d_unres, sizeof(int), s->stream));
+        TRY(glb_stream_sync(s->stream));
+        if (unres > 0) {
+          g_fused_avg = 0;
+          const int rc2 = exec_slot(p, s, first, nframes, cand_out, NULL);
+          g_fused_avg = 1;
+          return rc2;
+        }
+      }
+    } else if (c->avg_mode == GLFER_AVG_SUMAVG) {
       TRY(glb_launch_avg(&a, s->stream));
       int unres = 0;
       TRY(glb_memcpy_d2h(&unres, s->d_unres, sizeof(int), s->stream));

@@ -78,6 +78,9 @@ typedef struct {
   float *spectrum;             /* device out: [nframes][n/2+1] (re,im) pairs, or NULL (periodogram only) */
   const void *tables;          /* from glb_tables_create(n) */
   int groups_hint;             /* 0 = auto: resident frame-groups per launch */
+  const void *fused_avg;       /* glb_avg_args * or NULL: the sliding frame averaging of the launch's frames done by the
+                                  spectrogram kernel itself (band-only float rows; needs glb_gram_fused_avg_ok; its
+                                  first_frame / nframes must be the launch's, psd is ignored) */
   int general_only;            /* 1: general kernel whatever the geometry (plain global loads: the per-call layer hands
                                   it pinned HOST memory, which every device access reaches over PCIe) */
   /* fused display mapping (main_window_draw, g_main.c:1186-1229): 8-bit palette indices written by the
@@ -101,6 +104,9 @@ int glb_launch_gram(const glb_gram_args *a, void *stream);
  * multiple of hop (0 %, 50 %, 75 %, 87.5 %, 93.75 % overlap); other geometries use
  * glb_launch_block_means + block_means */
 int glb_gram_fused_mean_ok(int n, int hop);
+/* fused averaging is available when the launch runs on the TMA ring kernel with one frame group per CTA
+ * (n = 4096 or 8192, regular hop) and the band history [depth][maxbin - minbin] fits 2 KB of shared memory */
+int glb_gram_fused_avg_ok(int n, int hop, int depth, int band);
 /* testing aid: 1 = always use the general kernel (the TMA ring kernel is chosen automatically
  * for the regular geometries) */
 void glb_force_generic_kernel(int on);

@@ -594,3 +594,39 @@ def test_big_frame_multitaper_kernel(gpu_api):
         lo, hi = p.required_span(2, nf - 3)
         part = p.run(np.ascontiguousarray(x[max(lo, 0):hi]), origin=max(lo, 0), first_frame=2, nframes=nf - 3)["psd"]
         assert np.array_equal(part, got[2:nf - 1])
+
+
+# ------------------------------------------------------------------ averaging fused into the ring kernel
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_fused_averaging_equals_two_pass(gpu_api, mode):
+    """avg_band_only plans at N = 4096 / 8192: the ring kernel averages the frames it computes (band history in
+    shared memory, one warp per frame).  Rows, return values, peak bins and variances must EQUAL the two-pass
+    path (float PSD rows -> averaging kernel): both run avg_frame_warp()."""
+    x = synth.qrss_stream(2_000_000, fs=FS, seed=93, dot_s=0.2)
+    for n, wt, ov, depth, mn, mx in ((4096, 7, 0.75, 4, 34, 102), (4096, 0, 0.5, 7, 300, 360), (8192, 0, 0.5, 3, 68, 204),
+                                     (4096, 1, 0.875, 2, 0, 40)):
+        kw = dict(n=n, window_type=wt, overlap=ov, sub_mean=True, avg_mode=mode, avg_depth=depth, avg_minbin=mn, avg_maxbin=mx,
+                  avg_max0=1, avg_band_only=True, avg_peakbin_init=mn + 1)
+        gpu_api.set_fused_avg(True)
+        n0 = gpu_api.kernel_launches()
+        fused = gpu_api.GramPlan(**kw).run(x)
+        n_fused = gpu_api.kernel_launches() - n0
+        gpu_api.set_fused_avg(False)
+        n0 = gpu_api.kernel_launches()
+        two = gpu_api.GramPlan(**kw).run(x)
+        n_two = gpu_api.kernel_launches() - n0
+        gpu_api.set_fused_avg(True)
+        assert n_fused < n_two, (n_fused, n_two)
+        for k in ("psd", "avg", "ret", "peakbin", "variance"):
+            assert np.array_equal(fused[k], two[k], equal_nan=True), (kw, k)
+        # sub-range at an offset: the groups' pre-roll reads before the first requested frame
+        p = gpu_api.GramPlan(**kw)
+        nf = fused["psd"].shape[0]
+        first, cnt = nf // 3, nf // 2
+        lo, hi = p.required_span(first, cnt)
+        part = p.run(np.ascontiguousarray(x[max(lo, 0):hi]), origin=max(lo, 0), first_frame=first, nframes=cnt)
+        assert np.array_equal(part["avg"], fused["avg"][first:first + cnt])
+        assert np.array_equal(part["ret"], fused["ret"][first:first + cnt])
+    # against avg.c restated on the GPU's own rows
+    a, ret, pk, var = O.update_avg(mode, fused["psd"], 4096, 2, 0, 40, 1, peakbin_init=1)
+    assert np.allclose(fused["avg"], a[:, 0:40], rtol=1e-5, atol=1e-15) and np.array_equal(fused["peakbin"], pk)
