@@ -426,7 +426,7 @@ def map_levels(rows: np.ndarray, log_scale=True, max_level_db=-20.0, min_level_d
 
 
 def set_fused_avg(on: bool) -> None:
-    """testing aid: False = frame averaging always as a second pass over the PSD rows"""
+    """True = frame averaging inside the spectrogram kernel where possible (default False: measured slower)"""
     lib().glfer_b200_set_fused_avg(int(on))
 
 

@@ -7,59 +7,80 @@
 #include <cstdint>
 #include "../../include/glb_shim.h"
 
+// RN(x / d) for a small integer divisor d with r = RN(1 / d) (Markstein: q = RN(x r); e = x - q d exactly, by
+// FMA; RN(q + e r) = RN(x / d) when r is the correctly rounded reciprocal and q is faithful).  Checked by
+// brute force against IEEE division for d = 1 .. 63.  Three dependent operations instead of a division.
+__device__ __forceinline__ double avg_div_small(double x, double d, double r) {
+  const double q = __dmul_rn(x, r);
+  const double e = __fma_rn(-q, d, x);
+  return __fma_rn(e, r, q);
+}
+
 // psd_at(g, b): PSD of frame g (index since alloc_avg) at bin b.  fl: index of the frame in the launch's
-// outputs (f = a.first_frame + fl).  Pass 1 reduces max / first argmax / sum / min of the window sums over
-// the band with shuffles, pass 2 recomputes the sums and writes the normalised row.
-template <typename OutT, class PsdAt>
-__device__ __forceinline__ void avg_frame_warp(const glb_avg_args &a, long long fl, int lane, PsdAt &&psd_at) {
+// outputs (f = a.first_frame + fl).  Pass 1 forms the window sums of the band (a lane's bins lane, lane + 32,
+// ...; the first four stay in registers) and reduces max / first argmax / sum (/ min) with shuffles, pass 2
+// writes the normalised row.  MODE: avgmode_t (1 sumavg, 2 plain, 3 sumextreme), compile time so that each
+// carrier only executes what its normalisation needs.
+template <typename OutT, int MODE, class PsdAt>
+__device__ __forceinline__ void avg_frame_warp_m(const glb_avg_args &a, long long fl, int lane, PsdAt &&psd_at) {
+  constexpr int KREG = 4;                                  // window sums kept in registers per lane
   const int band = a.maxbin - a.minbin;
   OutT *out_base = (OutT *) a.avg_rows;
-  {
-    const long long f = a.first_frame + fl;
-    const long long eff = (f + 1 < a.depth) ? f + 1 : a.depth;
-    const long long g0 = f - eff + 1;
-    auto window_sum = [&](int b) {
-      double c = 0.0;
-      for (long long g2 = g0; g2 <= f; ++g2) c += (double) psd_at(g2, b);
-      return c;
-    };
-    double mx = -1.0, sum = 0.0, mn = 1.0;
-    int arg = -1;
-    for (int i = lane; i < band; i += 32) {
-      const int b = a.minbin + i;
-      const double c = window_sum(b);
-      if (arg < 0 || c > mx) { mx = c; arg = b; }
-      sum += c;
-      if (c < mn) mn = c;
-    }
+  const long long f = a.first_frame + fl;
+  const int eff = (int) ((f + 1 < a.depth) ? f + 1 : a.depth);
+  const long long g0 = f - eff + 1;
+  auto window_sum = [&](int b) {
+    double c = 0.0;
+#pragma unroll 1
+    for (int d = 0; d < eff; ++d) c += (double) psd_at(g0 + d, b);      // oldest to newest
+    return c;
+  };
+  // (loops deliberately NOT unrolled: this code runs once per frame on one warp, inlined into the spectrogram
+  // kernel; unrolled it was 3 000 instructions per mode and evicted the FFT loop from the instruction cache)
+  double creg[KREG];
+  double mx = -1.0, sum = 0.0, mn = 1.0;
+  int arg = -1;
+#pragma unroll 1
+  for (int i = lane, k = 0; i < band; i += 32, ++k) {
+    const int b = a.minbin + i;
+    const double c = window_sum(b);
+    if (k < KREG) creg[k] = c;
+    if (arg < 0 || c > mx) { mx = c; arg = b; }
+    sum += c;
+    if (MODE == 3 && c < mn) mn = c;
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
-      const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (oarg >= 0 && (arg < 0 || omx > mx || (omx == mx && oarg < arg))) { mx = omx; arg = oarg; }
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (oarg >= 0 && (arg < 0 || omx > mx || (omx == mx && oarg < arg))) { mx = omx; arg = oarg; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (MODE == 3) {
       const double omn = __shfl_xor_sync(0xffffffffu, mn, o);
       if (omn < mn) mn = omn;
     }
-    const double m0 = (double) psd_at(f, a.minbin);            // `double max = psd[minbin]` (avg.c:111)
-    const int cand = (arg >= 0 && mx > m0) ? arg : -1;
-    const double vmax = (cand >= 0) ? mx : m0;
-    // *peakbin after this frame: the new candidate, else the caller's value -- known only for
-    // the very first frame of the call; otherwise the frame is flagged for the in-order kernel
-    const bool carry_known = (cand >= 0) || (fl == 0);
-    const int pk = (cand >= 0) ? cand : a.peakbin_init;
-    double avgspec = 0.0, retv;
-    if (a.mode == 2) {
-      retv = (sum - vmax) / ((double) (band - 1) * (double) (eff + 1));
-    } else {
-      avgspec = (sum - vmax) / (double) (band - 1);
-      retv = vmax / avgspec;
-    }
-    OutT *orow = out_base + fl * a.out_stride;
-    double var = 0.0;
-    int cnt = 0;
-    // outside the band the row is the constant 1e-15 (avg.c:152-153): plain streaming stores
-    const bool out_db = sizeof(OutT) == 4 && a.rows_db;
+  }
+  const double m0 = (double) psd_at(f, a.minbin);              // `double max = psd[minbin]` (avg.c:111)
+  const int cand = (arg >= 0 && mx > m0) ? arg : -1;
+  const double vmax = (cand >= 0) ? mx : m0;
+  // *peakbin after this frame: the new candidate, else the caller's value -- known only for
+  // the very first frame of the call; otherwise the frame is flagged for the in-order kernel
+  const bool carry_known = (cand >= 0) || (fl == 0);
+  const int pk = (cand >= 0) ? cand : a.peakbin_init;
+  const double deff = (double) (eff + 1), reff = 1.0 / deff;
+  double avgspec = 0.0, retv;
+  if (MODE == 2) {
+    retv = (sum - vmax) / ((double) (band - 1) * deff);
+  } else {
+    avgspec = (sum - vmax) / (double) (band - 1);
+    retv = vmax / avgspec;
+  }
+  OutT *orow = out_base + fl * a.out_stride;
+  double var = 0.0;
+  int cnt = 0;
+  // outside the band the row is the constant 1e-15 (avg.c:152-153): plain streaming stores
+  const bool out_db = sizeof(OutT) == 4 && a.rows_db;
+  if (!a.band_only) {
     const OutT fill = (OutT) (out_db ? -150.0 : 1e-15);
     auto fill_range = [&](int lo, int hi) {
       if (sizeof(OutT) == 4) {
@@ -78,39 +99,45 @@ __device__ __forceinline__ void avg_frame_warp(const glb_avg_args &a, long long 
         for (int b = lo + lane; b < hi; b += 32) orow[b] = fill;
       }
     };
-    if (!a.band_only) {
-      fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
-      if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
+    fill_range(0, a.minbin < a.nbins ? a.minbin : a.nbins);
+    if (a.maxbin < a.nbins) fill_range(a.maxbin, a.nbins);
+  }
+  const int ob0 = a.band_only ? a.minbin : 0;
+  auto emit = [&](int b, double c) {
+    double y;
+    if (MODE == 2) {
+      y = avg_div_small(c, deff, reff);                         // c / (effdepth + 1), avg.c:150
+    } else if (MODE == 3) {
+      y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
+    } else if (c - avgspec > 0) {
+      y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
+      if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
+    } else {
+      y = 1e-15;
     }
-    const int ob0 = a.band_only ? a.minbin : 0;
-    for (int b = a.minbin + lane; b < a.maxbin && b < a.nbins; b += 32) {
-      double y;
-      const double c = window_sum(b);
-      if (a.mode == 2) {
-        y = c / (double) (eff + 1);
-      } else if (a.mode == 3) {
-        y = a.max0 ? (c - mn) / (vmax - mn) : c / avgspec;
-      } else if (c - avgspec > 0) {
-        y = a.max0 ? (c - avgspec) / (vmax - avgspec) : c / avgspec;
-        if (b != pk) { const double r = c / avgspec; var += r * r; cnt++; }
-      } else {
-        y = 1e-15;
-      }
-      if (out_db) y = 10.0 * log10(y);
-      orow[b - ob0] = (OutT) y;
-    }
-    if (a.mode == 1) {
+    if (out_db) y = 10.0 * log10(y);
+    orow[b - ob0] = (OutT) y;
+  };
+#pragma unroll 1
+  for (int b = a.minbin + lane, k = 0; b < a.maxbin && b < a.nbins; b += 32, ++k) emit(b, k < KREG ? creg[k] : window_sum(b));
+  if (MODE == 1) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        var += __shfl_xor_sync(0xffffffffu, var, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      }
-    }
-    if (lane == 0) {
-      if (a.ret) a.ret[fl] = retv;
-      if (a.peak_cand) a.peak_cand[fl] = cand;
-      if (a.variance) a.variance[fl] = (a.mode == 1) ? var / (double) cnt : 0.0;
-      if (a.mode == 1 && !carry_known && a.unresolved) atomicAdd(a.unresolved, 1);
+    for (int o = 16; o > 0; o >>= 1) {
+      var += __shfl_xor_sync(0xffffffffu, var, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
   }
+  if (lane == 0) {
+    if (a.ret) a.ret[fl] = retv;
+    if (a.peak_cand) a.peak_cand[fl] = cand;
+    if (a.variance) a.variance[fl] = (MODE == 1) ? var / (double) cnt : 0.0;
+    if (MODE == 1 && !carry_known && a.unresolved) atomicAdd(a.unresolved, 1);
+  }
+}
+
+template <typename OutT, class PsdAt>
+__device__ __forceinline__ void avg_frame_warp(const glb_avg_args &a, long long fl, int lane, PsdAt &&psd_at) {
+  if (a.mode == 2) avg_frame_warp_m<OutT, 2>(a, fl, lane, psd_at);
+  else if (a.mode == 3) avg_frame_warp_m<OutT, 3>(a, fl, lane, psd_at);
+  else avg_frame_warp_m<OutT, 1>(a, fl, lane, psd_at);
 }

@@ -127,10 +127,12 @@ struct BigLast {
 };
 template <int M> GLB_HD int big_khi(int t) { return t != 0 ? t + 16 * Big<M>::T : Big<M>::T; }
 
-template <int M> GLB_HD void big_load_last(BigLast &L, int t, const float2 *roots, const float2 *vtab) {
+template <int M> GLB_HD void big_load_last(BigLast &L, int t, const float2 *roots, const float2 *vtab, bool bases = true) {
   const int e[6] = {1, 2, 3, 4, 8, 12};
+  if (bases) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) L.w[i] = make_tw3(roots[t * e[i]]);
+    for (int i = 0; i < 6; i++) L.w[i] = make_tw3(roots[t * e[i]]);
+  }
   L.v0 = make_tw3(vtab[t]);
   L.v0hi = make_tw3(vtab[big_khi<M>(t)]);
 }
@@ -163,6 +165,30 @@ template <int M> GLB_HD void big_pass2(float2 *v, int t, const BigLast &L) {
     y[4 * a + 2] = cmulc(y[4 * a + 2], w2);
     y[4 * a + 3] = cmulc(y[4 * a + 3], w3);
   }
+  dft16<1>(y);
+#pragma unroll
+  for (int r = 0; r < 16; r++) v[16 + r] = y[(r + 1) & 15];
+}
+
+// The same pass with every power w^r = W_M^(t r), r = 1..15, read from a table [15][T] (shared memory, built
+// once per CTA from the M-th roots: each entry rounded once, and 18 complex multiplications fewer per thread
+// than rebuilding the powers from six bases); one load serves butterfly A (w^r) and butterfly B (conj w^r).
+template <int M> GLB_HD void big_pass2_tab(float2 *v, int t, const float2 *tab) {
+  constexpr int T = Big<M>::T;
+  if (t == 0) {
+#pragma unroll
+    for (int r = 1; r < 16; r++) v[16 + r] = mul_w32(v[16 + r], 32 - r);
+  }
+#pragma unroll
+  for (int r = 1; r < 16; r++) {
+    const Tw3 w = make_tw3(tab[(r - 1) * T + t]);
+    v[r] = cmul(v[r], w);
+    v[16 + r] = cmulc(v[16 + r], w);
+  }
+  dft16<1>(v);
+  float2 y[16];
+#pragma unroll
+  for (int r = 0; r < 16; r++) y[r] = v[16 + r];
   dft16<1>(y);
 #pragma unroll
   for (int r = 0; r < 16; r++) v[16 + r] = y[(r + 1) & 15];

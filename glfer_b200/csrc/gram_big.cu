@@ -20,10 +20,13 @@ template <int M> struct BigGeo {
   static constexpr int T = Big<M>::T, N = 2 * M, NW = T / 32;
   static constexpr size_t BUF_BYTES = (size_t) Big<M>::BUF * sizeof(float2);
   static constexpr size_t TW_BYTES = (size_t) Big<M>::TW1 * sizeof(float2);
+  static constexpr int MINB = (T <= 256) ? 2 : 1;
   static constexpr size_t RED_BYTES = (size_t) 4 * NW * sizeof(float);
   static constexpr size_t ACC_BYTES = (size_t) 33 * T * sizeof(float);         // multitaper: the row being summed
-  static constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0); }
-  static constexpr int MINB = (T <= 256) ? 2 : 1;
+  static constexpr size_t TW2_BYTES = (size_t) 15 * T * sizeof(float2);       // last-pass powers W_M^(t r), r = 1..15
+  // the last-pass table is used wherever it fits beside the rest (not at N = 32768 multitaper)
+  static __host__ __device__ constexpr bool tw2(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + TW2_BYTES <= (size_t) (MINB == 2 ? 113 : 227) * 1024 - 1024; }
+  static __host__ __device__ constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + (tw2(multi) ? TW2_BYTES : 0); }
 };
 
 // MULTI: Thomson multitaper (mtm_do, mtm.c:189-220): the frame goes through the transform once per taper -- its
@@ -41,10 +44,16 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   float *red = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES);
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES);
   float *acc = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16) + threadIdx.x;   // [slot][T]
+  constexpr bool TW2 = G::tw2(MULTI);
+  float2 *tw2 = reinterpret_cast<float2 *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16 + (MULTI ? G::ACC_BYTES : 0));
   const int t = threadIdx.x;
 
   // middle-pass twiddles exp(-2 pi i k r / (32 R1)) = roots[16 k r], one copy per CTA
   for (int i = t; i < Big<M>::TW1; i += T) tw1[i] = p.roots[(i & 31) * ((i >> 5) + 1) * 16];
+  if constexpr (TW2) {
+#pragma unroll
+    for (int r = 1; r < 16; r++) tw2[(r - 1) * T + t] = p.roots[t * r];       // t r < 15 M / 32
+  }
   __syncthreads();
 
   const long long fb = (long long) blockIdx.x * p.frames_per_group;
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
     big_scatter1<M>(v, t, buf);
     __syncthreads();
     BigLast L;
-    big_load_last<M>(L, t, p.roots, p.vtab);
+    big_load_last<M>(L, t, p.roots, p.vtab, !TW2);
     big_load2<M>(v, t, buf);
     __syncthreads();                   // (E) the last-pass loads are done: the buffer is free for the next frame
     {
@@ -155,7 +164,8 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
         tma_load_1d(buf, p.samples + (sn - p.origin), N * 4u, mbar);
       }
     }
-    big_pass2<M>(v, t, L);
+    if constexpr (TW2) big_pass2_tab<M>(v, t, tw2);
+    else big_pass2<M>(v, t, L);
     float yv[33];
     yv[32] = 1.f;                      // only thread 0 has a 33rd bin
     auto sink = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };

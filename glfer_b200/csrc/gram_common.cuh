@@ -352,7 +352,9 @@ template <int M, int P, bool RT> struct MidPasses {
 
 // MULTI: multitaper (K' tapers per frame, frame staged in shared memory by TMA one frame
 // ahead and re-read per taper).  PLAIN: no RA9MB / limiter code in the kernel.
-template <int M, bool MULTI, bool PLAIN>
+// LEV: 8-bit display levels beside / instead of the float rows (separate instantiations: as a run-time
+// branch the display epilogue cost the float path registers, +14 % on the odd-hop workload).
+template <int M, bool MULTI, bool PLAIN, bool LEV = false>
 __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(const KParams p) {
   using GeoM = Geo<M>;
   constexpr int T = GeoM::T, G = GeoM::G, N = GeoM::N;
@@ -466,13 +468,15 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
       MidPasses<M, 1, RT>::run(v, t, buf, tw_mid, tr, g);
       auto sink_multi = [&](int slot, float2 a, bool) { acc[slot] += norm2(a); };
       float *row = (!MULTI && active && p.rows) ? p.rows + fl * p.row_stride : nullptr;
-      unsigned char *lrow = (!MULTI && active && p.levels) ? p.levels + fl * p.lev_stride : nullptr;
+      unsigned char *lrow = (LEV && !MULTI && active) ? p.levels + fl * p.lev_stride : nullptr;
       float2 *sp = (!MULTI && active && p.spectrum) ? p.spectrum + fl * (long long) (M + 1) : nullptr;
       const bool db = p.rows_db != 0;
       const float ss = p.spec_scale;
       auto sink_single = [&](int slot, float2 a, bool cj) {
         const int bin = slot_bin<M>(t, slot);
-        if (lrow) lrow[M - bin] = map_level(norm2(a), p.lm);
+        if constexpr (LEV) {
+          if (lrow) lrow[M - bin] = map_level(norm2(a), p.lm);
+        }
         if (row) {
           float y = norm2(a);
           if (db) y = 10.f * log10f(y);
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, Geo<M>::MINB) gram_kernel(con
       }
       // no barrier here: (A) of the next transform orders these reads before its stores
     }
-    if (MULTI && active && p.levels) {
+    if (LEV && MULTI && active) {
       unsigned char *lrow = p.levels + fl * p.lev_stride;
 #pragma unroll
       for (int slot = 0; slot < 17; slot++)
@@ -807,12 +811,22 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
     }
   }
   auto av_frame = [&](int itf) {
-    // averaged row of the frame computed in iteration itf (an output frame), by the calling warp
+    // averaged row of the frame computed in iteration itf (an output frame), by the calling warp.  History
+    // row of frame gg: (gg mod depth), found from the frame's own row by a 32-bit step back (no 64-bit
+    // modulo per access: the first version spent 60 % of the kernel in them)
     const int lane = t & 31;
-    auto psd_at = [&](long long gg, int b) -> float { return hist[(int) (gg % av_depth) * av_band + (b - p.av.minbin)]; };
+    const long long gf = f_first + itf;                          // global index of the frame
+    const int sf = (int) ((unsigned long long) gf % (unsigned) av_depth);
+    auto psd_at = [&](long long gg, int b) -> float {
+      int s = sf - (int) (gf - gg);                              // 0 <= gf - gg < depth
+      if (s < 0) s += av_depth;
+      return hist[s * av_band + (b - p.av.minbin)];
+    };
     avg_frame_warp<float>(p.av, fb + (itf - pre), lane, psd_at);
   };
-  const int n_iter = p.frames_per_group + (AVG ? av_depth - 1 : 0);
+  int hslot = (AVG && group_active) ? (int) ((unsigned long long) f_first % (unsigned) av_depth) : 0;   // history row of frame `it`
+  // (fused averaging: the pre-roll, plus one idle iteration in which the last frame of a full run is averaged)
+  const int n_iter = p.frames_per_group + (AVG ? av_depth : 0);
   for (int it = 0; it < n_iter; ++it, row_ptr += p.row_stride, lev_ptr += p.lev_stride, next_src += hop) {
     const bool active = it < nact;
     const bool storing = !AVG || it >= pre;                      // pre-roll frames only feed the history
@@ -920,7 +934,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
           }
           if constexpr (AVG) {
             if (active && av_mask != 0) {
-              float *hrow = hist + (int) ((f_first + it) % av_depth) * av_band - p.av.minbin;
+              float *hrow = hist + hslot * av_band - p.av.minbin;
 #pragma unroll
               for (int slot = 0; slot < 17; slot++)
                 if (av_mask & (1u << slot)) hrow[slot_bin<M>(t, slot)] = yv[slot];
@@ -950,11 +964,7 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
       }
     }
     slot_new = slot_next;
-  }
-  if constexpr (AVG) {
-    // the last frame of a run that filled every iteration (shorter runs were served by an idle iteration)
-    group_sync<M>(g);
-    if (nact == n_iter && nact > pre && (t >> 5) == ((nact - 1) & (Geo<M>::NW - 1))) av_frame(nact - 1);
+    if constexpr (AVG) hslot = (hslot + 1 == av_depth) ? 0 : hslot + 1;
   }
 }
 
@@ -1477,12 +1487,18 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
     return GLB_EINVAL;
   }
   const int variant = multi ? 2 : (plain ? 1 : 0);
-  auto kern = multi ? gram_kernel<M, true, true> : (plain ? gram_kernel<M, false, true> : gram_kernel<M, false, false>);
+  const bool glev = kp.levels != nullptr;
+  if (glev && !plain) {
+    glb_set_error("glb_launch_gram: display levels are not available together with RA9MB / limiter");
+    return GLB_EINVAL;
+  }
+  auto kern = glev ? (multi ? gram_kernel<M, true, true, true> : gram_kernel<M, false, true, true>)
+                   : (multi ? gram_kernel<M, true, true> : (plain ? gram_kernel<M, false, true> : gram_kernel<M, false, false>));
   // the staging buffer is only carved out for the multitaper variant
   const size_t smem = GeoM::smem_bytes(multi);
   // per (device, variant): opt in to the dynamic shared memory once, cache the occupancy
-  static thread_local int occ_cache[3][64];
-  int &occ = occ_cache[variant][dev & 63];
+  static thread_local int occ_cache[6][64];
+  int &occ = occ_cache[variant + (glev ? 3 : 0)][dev & 63];
   if (occ == 0) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GeoM::THREADS, smem));

@@ -169,8 +169,9 @@ int glfer_b200_map_levels(const float *rows, long long nrows, int nbins, const g
 /* per-call interface (fft_do / mtm_do / lmp_do): 1 (default) = the frame is read from, and the results are written
  * to, pinned host memory by the kernel itself (no copy-engine round trips); 0 = staged through device buffers */
 void glfer_b200_set_zero_copy(int on);
-/* testing aid: 0 = frame averaging always as a second pass over the PSD rows; 1 (default) = fused into the spectrogram
- * kernel where it can be (avg_band_only plans, N = 4096 / 8192, regular overlap, band history <= 2 KB) */
+/* 0 (default) = frame averaging as a second pass over the PSD rows; 1 = fused into the spectrogram kernel where it
+ * can be (avg_band_only plans, N = 4096 / 8192, regular overlap, band history <= 2 KB): bit-identical rows, but
+ * measured slower on B200 (1.31 ms against 0.82 + 0.20 ms on BASELINE config C2), so it is opt-in */
 void glfer_b200_set_fused_avg(int on);
 /* testing aid: 0 = glfer_gram_run_display always maps the levels in a second pass over float rows; 1 (default) =
  * with a fixed display range and no averaging the spectrogram kernel writes the 8-bit levels itself */

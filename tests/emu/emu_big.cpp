@@ -28,7 +28,7 @@ static void fft_ref(std::vector<cld> &a) {
   }
 }
 
-template <int M> int check(unsigned seed) {
+template <int M> int check(unsigned seed, bool tab = false) {
   constexpr int N = 2 * M, T = Big<M>::T;
   std::vector<float> x(N);
   srand(seed);
@@ -53,7 +53,13 @@ template <int M> int check(unsigned seed) {
   std::vector<BigLast> L(T);
   for (int t = 0; t < T; t++) big_load_last<M>(L[t], t, roots.data(), vtab.data());
   for (int t = 0; t < T; t++) big_load2<M>(regs[t].data(), t, buf.data());
-  for (int t = 0; t < T; t++) big_pass2<M>(regs[t].data(), t, L[t]);
+  std::vector<float2> tw2(15 * T);
+  for (int r = 1; r < 16; r++)
+    for (int t = 0; t < T; t++) tw2[(r - 1) * T + t] = roots[t * r];
+  for (int t = 0; t < T; t++) {
+    if (tab) big_pass2_tab<M>(regs[t].data(), t, tw2.data());
+    else big_pass2<M>(regs[t].data(), t, L[t]);
+  }
   std::vector<double> psd(M + 1, -1.0);
   std::vector<float2> spec(M + 1);
   std::vector<int> hits(M + 1, 0);
@@ -90,5 +96,7 @@ int main() {
   rc |= check<4096>(2);
   rc |= check<8192>(3);
   rc |= check<16384>(4);
+  rc |= check<8192>(5, true);
+  rc |= check<16384>(6, true);
   return rc;
 }

@@ -615,8 +615,8 @@ def test_fused_averaging_equals_two_pass(gpu_api, mode):
         n0 = gpu_api.kernel_launches()
         two = gpu_api.GramPlan(**kw).run(x)
         n_two = gpu_api.kernel_launches() - n0
-        gpu_api.set_fused_avg(True)
         assert n_fused < n_two, (n_fused, n_two)
+        gpu_api.set_fused_avg(True)
         for k in ("psd", "avg", "ret", "peakbin", "variance"):
             assert np.array_equal(fused[k], two[k], equal_nan=True), (kw, k)
         # sub-range at an offset: the groups' pre-roll reads before the first requested frame
@@ -627,6 +627,7 @@ def test_fused_averaging_equals_two_pass(gpu_api, mode):
         part = p.run(np.ascontiguousarray(x[max(lo, 0):hi]), origin=max(lo, 0), first_frame=first, nframes=cnt)
         assert np.array_equal(part["avg"], fused["avg"][first:first + cnt])
         assert np.array_equal(part["ret"], fused["ret"][first:first + cnt])
+    gpu_api.set_fused_avg(False)
     # against avg.c restated on the GPU's own rows
     a, ret, pk, var = O.update_avg(mode, fused["psd"], 4096, 2, 0, 40, 1, peakbin_init=1)
     assert np.allclose(fused["avg"], a[:, 0:40], rtol=1e-5, atol=1e-15) and np.array_equal(fused["peakbin"], pk)
