@@ -20,12 +20,15 @@ template <int M> struct BigGeo {
   static constexpr int T = Big<M>::T, N = 2 * M, NW = T / 32;
   static constexpr size_t BUF_BYTES = (size_t) Big<M>::BUF * sizeof(float2);
   static constexpr size_t TW_BYTES = (size_t) Big<M>::TW1 * sizeof(float2);
-  static constexpr int MINB = (T <= 256) ? 2 : 1;
+  static constexpr int MINB = 512 / T;            // CTAs per SM at 128 registers per thread
   static constexpr size_t RED_BYTES = (size_t) 4 * NW * sizeof(float);
   static constexpr size_t ACC_BYTES = (size_t) 33 * T * sizeof(float);         // multitaper: the row being summed
   static constexpr size_t TW2_BYTES = (size_t) 15 * T * sizeof(float2);       // last-pass powers W_M^(t r), r = 1..15
   // the last-pass table is used wherever it fits beside the rest (not at N = 32768 multitaper)
-  static __host__ __device__ constexpr bool tw2(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + TW2_BYTES <= (size_t) (MINB == 2 ? 113 : 227) * 1024 - 1024; }
+#ifndef GLB_BIG_TW2
+#define GLB_BIG_TW2 1
+#endif
+  static __host__ __device__ constexpr bool tw2(bool multi) { return GLB_BIG_TW2 && BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + TW2_BYTES <= (size_t) 227 * 1024 / MINB - 1024; }
   static __host__ __device__ constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + (tw2(multi) ? TW2_BYTES : 0); }
 };
 
@@ -33,7 +36,8 @@ template <int M> struct BigGeo {
 // samples land again by TMA from L2 each time, the block means are formed once -- and the eigenspectra
 // (1 / lambda_k folded into the tapers) are summed in a shared-memory row [33][T], so that the register
 // budget of the periodogram kernel (two frames per SM at N = 16384) holds for the multitaper one too.
-template <int M, int NBLK, bool MULTI>
+// LEV: 8-bit display levels (levels.cuh) beside / instead of the float rows, pixel i = bin M - i.
+template <int M, int NBLK, bool MULTI, bool LEV>
 __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(const KParams p) {
   using G = BigGeo<M>;
   constexpr int T = G::T, N = G::N, NW = G::NW, QB = kBP / NBLK;     // QB registers (float2) per hop block
@@ -61,7 +65,8 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   const bool sub = p.fused_mean != 0;
   const bool db = p.rows_db != 0;
   const int ntap = MULTI ? p.ntapers : 1;
-  float *row_ptr = p.rows + fb * p.row_stride;
+  float *row_ptr = p.rows + fb * p.row_stride;                   // (never dereferenced when p.rows is null)
+  unsigned char *lev_ptr = p.levels + fb * p.lev_stride;
   long long s0 = (p.first_frame + fb) * (long long) HOP - (N - HOP);   // stream index of the frame's first sample
 
   // The exchange buffer is idle from the last-pass loads of one frame to the first-pass stores of the next:
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   }
   __syncthreads();
 
-  for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride) {
+  for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride, lev_ptr += p.lev_stride) {
    float bs[NBLK];
    for (int j = 0; j < ntap; ++j) {
     const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers + (size_t) j * N) + t;
@@ -183,13 +188,23 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
         continue;
       }
     }
+    // the row leaves the registers: slot 2 rp is bin k, slot 2 rp + 1 is bin M - k, k = t + rp 2T (thread 0:
+    // rp 2T, then T + (rp - 8) 2T); consecutive threads store consecutive bins
+    const int kh = big_khi<M>(t) - 16 * T;
+    if constexpr (LEV) {
+      unsigned char *pa = lev_ptr + (M - t), *pb = lev_ptr + t, *pah = lev_ptr + (M - kh), *pbh = lev_ptr + kh;
+#pragma unroll
+      for (int rp = 0; rp < 16; rp++) {
+        *((rp < 8 ? pa : pah) - rp * 2 * T) = map_level(yv[2 * rp], p.lm);
+        *((rp < 8 ? pb : pbh) + rp * 2 * T) = map_level(yv[2 * rp + 1], p.lm);
+      }
+      if (t == 0) lev_ptr[M - M / 2] = map_level(yv[32], p.lm);
+      if (p.rows == nullptr) continue;
+    }
     if (db) {
 #pragma unroll
       for (int s = 0; s < 33; s++) yv[s] = 10.f * log10f(yv[s]);
     }
-    // the row leaves the registers: slot 2 rp is bin k, slot 2 rp + 1 is bin M - k, k = t + rp 2T (thread 0:
-    // rp 2T, then T + (rp - 8) 2T); consecutive threads store consecutive bins
-    const int kh = big_khi<M>(t) - 16 * T;
     float *ra = row_ptr + t, *rb = row_ptr + (M - t), *rah = row_ptr + kh, *rbh = row_ptr + (M - kh);
     GLB_CHECK_ROW(p, row_ptr);
     GLB_CHECK_ROW(p, row_ptr + M);
@@ -204,13 +219,13 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   }
 }
 
-template <int M, int NBLK, bool MULTI>
+template <int M, int NBLK, bool MULTI, bool LEV>
 static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
   using G = BigGeo<M>;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  auto kern = gram_big_kernel<M, NBLK, MULTI>;
+  auto kern = gram_big_kernel<M, NBLK, MULTI, LEV>;
   constexpr size_t smem = G::smem(MULTI);
   static thread_local int occ_cache[64];
   int &occ = occ_cache[dev & 63];
@@ -233,30 +248,36 @@ static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
   return GLB_OK;
 }
 
-template <int M>
-static int launch_big_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
+template <int M, bool MULTI, bool LEV>
+static int launch_big_ml(const KParams &kp, int groups_hint, cudaStream_t st) {
   const int n = 2 * M;
-  if (multi) {
-    if (kp.hop == n) return launch_big<M, 1, true>(kp, groups_hint, st);
-    if (kp.hop == n / 2) return launch_big<M, 2, true>(kp, groups_hint, st);
-    if (kp.hop == n / 4) return launch_big<M, 4, true>(kp, groups_hint, st);
-    return -1;
-  }
-  if (kp.hop == n) return launch_big<M, 1, false>(kp, groups_hint, st);
-  if (kp.hop == n / 2) return launch_big<M, 2, false>(kp, groups_hint, st);
-  if (kp.hop == n / 4) return launch_big<M, 4, false>(kp, groups_hint, st);
+  if (kp.hop == n) return launch_big<M, 1, MULTI, LEV>(kp, groups_hint, st);
+  if (kp.hop == n / 2) return launch_big<M, 2, MULTI, LEV>(kp, groups_hint, st);
+  if (kp.hop == n / 4) return launch_big<M, 4, MULTI, LEV>(kp, groups_hint, st);
   return -1;
 }
 
-// -1: this launch is not one the big-frame kernel serves (the caller goes on to the 16-point families)
-int glb_gram_big(int m, const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
-  if (kp.rows == nullptr || kp.levels != nullptr || kp.spectrum != nullptr || kp.means != nullptr) return -1;
+template <int M, bool WITH_LEV>
+static int launch_big_m(const KParams &kp, bool multi, int groups_hint, cudaStream_t st) {
+  if (kp.levels != nullptr) {
+    if constexpr (WITH_LEV) return multi ? launch_big_ml<M, true, true>(kp, groups_hint, st) : launch_big_ml<M, false, true>(kp, groups_hint, st);
+    else return -1;
+  }
+  return multi ? launch_big_ml<M, true, false>(kp, groups_hint, st) : launch_big_ml<M, false, false>(kp, groups_hint, st);
+}
+
+// -1: this launch is not one the big-frame kernel serves (the caller goes on to the 16-point families).
+// small_too: also N = 4096 / 8192 (kernel preference 5: experiments; the 16-point ring kernel is faster there)
+int glb_gram_big(int m, const KParams &kp, bool multi, int groups_hint, cudaStream_t st, bool small_too) {
+  if ((kp.rows == nullptr && kp.levels == nullptr) || kp.spectrum != nullptr || kp.means != nullptr) return -1;
   if (kp.ra9mb_a > 0.f || kp.limiter != 0 || kp.zero_hist || kp.av_on) return -1;
   // pairs of samples are read as one 64-bit word: even offsets, 8-byte aligned base
   if ((kp.hop & 1) || (kp.origin & 1) || (reinterpret_cast<uintptr_t>(kp.samples) & 7)) return -1;
   switch (m) {
-    case 8192: return launch_big_m<8192>(kp, multi, groups_hint, st);
-    case 16384: return launch_big_m<16384>(kp, multi, groups_hint, st);
+    case 2048: return small_too ? launch_big_m<2048, false>(kp, multi, groups_hint, st) : -1;
+    case 4096: return small_too ? launch_big_m<4096, false>(kp, multi, groups_hint, st) : -1;
+    case 8192: return launch_big_m<8192, true>(kp, multi, groups_hint, st);
+    case 16384: return launch_big_m<16384, true>(kp, multi, groups_hint, st);
     default: return -1;
   }
 }

@@ -1544,4 +1544,4 @@ GLB_DECLARE_PART(1);
 GLB_DECLARE_PART(2);
 GLB_DECLARE_PART(3);
 // the 32-points-per-thread family for N = 16384 / 32768 (gram_big.cu); -1 = not served
-int glb_gram_big(int m, const KParams &k, bool multi, int groups_hint, cudaStream_t st);
+int glb_gram_big(int m, const KParams &k, bool multi, int groups_hint, cudaStream_t st, bool small_too);

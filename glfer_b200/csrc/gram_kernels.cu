@@ -292,7 +292,7 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   const int m = a->n / 2;
   int rc = -1;
   // big frames: the 32-points-per-thread kernel (family 5) unless another family is asked for
-  if ((g_kernel_pref == 0 || g_kernel_pref == 5) && !g_force_generic && !a->general_only) rc = glb_gram_big(m, k, multi, a->groups_hint, st);
+  if ((g_kernel_pref == 0 || g_kernel_pref == 5) && !g_force_generic && !a->general_only) rc = glb_gram_big(m, k, multi, a->groups_hint, st, g_kernel_pref == 5);
   if (rc != -1) return rc;
   rc = glb_gram_part_0(m, k, multi, a->groups_hint, st, allow);
   if (rc == -1) rc = glb_gram_part_1(m, k, multi, a->groups_hint, st, allow);

@@ -573,6 +573,29 @@ def test_fftw_layout_library_per_call_interface(gpu_api):
     lf.mtm_close(C.byref(m))
 
 
+def test_32_point_kernel_on_small_frames(gpu_api):
+    """kernel preference 5 runs the 32-point family at N = 4096 / 8192 too (64 / 128 threads per frame, up to eight
+    frames in flight per SM): an experiment kept selectable; the 16-point ring kernel stays the default there."""
+    x = synth.qrss_stream(4096 * 300 + 17, fs=FS, seed=85, dot_s=0.2)
+    try:
+        for n, ov, wt in ((4096, 0.5, 0), (8192, 0.75, 7), (4096, 0.0, 2)):
+            gpu_api.set_kernel_preference(5)
+            got = gpu_api.GramPlan(n=n, window_type=wt, overlap=ov, sub_mean=True).run(x)["psd"]
+            assert gpu_api.last_kernel_family().startswith("gram_big_kernel")
+            assert_psd_close(got, O.periodogram(x, n, wt, ov, True), f"32-point kernel N={n}")
+            gpu_api.set_kernel_preference(0)
+            ring = gpu_api.GramPlan(n=n, window_type=wt, overlap=ov, sub_mean=True).run(x)["psd"]
+            assert gpu_api.last_kernel_family().startswith("gram_ring_kernel")
+            assert_psd_close(got, ring, "32-point vs ring")
+        gpu_api.set_kernel_preference(5)
+        p = gpu_api.GramPlan(n=4096, mode=1, overlap=0.5, sub_mean=True, mtm_w=4.0, mtm_kmax=7)
+        got = p.run(x[:200000])["psd"]
+        tap, lam = p.tapers()
+        assert_psd_close(got, O.multitaper(x[:200000], 4096, 0.5, 4.0, 7, True, tapers=tap, lam=lam), "32-point multitaper N=4096")
+    finally:
+        gpu_api.set_kernel_preference(0)
+
+
 def test_big_frame_multitaper_kernel(gpu_api):
     """multitaper at N = 16384 / 32768 on the 32-point kernel (eigenspectra summed in shared memory, the frame
     re-landed by TMA per taper): against the oracle and the 16-point general kernel, 0 / 50 / 75 % overlap."""
