@@ -278,9 +278,11 @@ class GramPlan:
         avg = ret = pk = var = None
         if self.avg:
             avg = out.get("avg") if "avg" in out else np.empty((nframes, self.avg_cols), np.float32)
-            ret = np.empty(nframes, np.float64)
-            pk = np.empty(nframes, np.int32)
-            var = np.empty(nframes, np.float64)
+            # the per-frame scalars are small but downloaded chunk by chunk: into pageable memory each of those
+            # copies would block the host thread and stall the chunk pipeline, so they are pinned
+            ret = out.get("ret") if "ret" in out else pinned_empty((nframes,), np.float64)
+            pk = out.get("peakbin") if "peakbin" in out else pinned_empty((nframes,), np.int32)
+            var = out.get("variance") if "variance" in out else pinned_empty((nframes,), np.float64)
         return psd, avg, ret, pk, var
 
     def run(self, samples: np.ndarray, origin: int = 0, first_frame: int = 0, nframes: int | None = None,
@@ -338,8 +340,10 @@ class GramPlan:
     def run_display(self, samples: np.ndarray, log_scale=True, autoscale=True, max_level_db=-20.0, min_level_db=-80.0,
                     thr_level=0.0, colortab: np.ndarray | None = None, origin: int = 0, first_frame: int = 0,
                     nframes: int | None = None, agc_state: np.ndarray | None = None, want_rgb: bool = False,
-                    out: dict | None = None):
-        """glfer_gram_run_display: rows -> 8-bit levels (and RGB) as main_window_draw maps them."""
+                    out: dict | None = None, want_range: bool = True):
+        """glfer_gram_run_display: rows -> 8-bit levels (and RGB) as main_window_draw maps them.
+        out: optional pre-allocated (pinned) "levels" / "range" arrays -- a download into pageable memory
+        blocks the host thread and with it the chunk pipeline."""
         pcm = samples.dtype == np.int16
         assert samples.flags["C_CONTIGUOUS"] and (pcm or samples.dtype == np.float32)
         if nframes is None:
@@ -347,7 +351,9 @@ class GramPlan:
         out = out or {}
         levels = out.get("levels") if "levels" in out else np.empty((nframes, self.bins), np.uint8)
         rgb = np.empty((nframes, self.bins, 3), np.uint8) if want_rgb else None
-        rng = np.empty((nframes, 2), np.float32) if autoscale else None
+        rng = None
+        if autoscale and want_range:
+            rng = out.get("range") if "range" in out else np.empty((nframes, 2), np.float32)
         if colortab is not None:
             colortab = np.ascontiguousarray(colortab, dtype=np.uint8)
             assert colortab.size == 768

@@ -30,9 +30,20 @@ __device__ __forceinline__ void avg_frame_warp_m(const glb_avg_args &a, long lon
   const int eff = (int) ((f + 1 < a.depth) ? f + 1 : a.depth);
   const long long g0 = f - eff + 1;
   auto window_sum = [&](int b) {
+    // oldest to newest, as the reference's cum[] would hold them; four loads in flight at a time (the loads do
+    // not depend on the sum: issued one by one they cost a full memory latency each)
     double c = 0.0;
+    int d = 0;
 #pragma unroll 1
-    for (int d = 0; d < eff; ++d) c += (double) psd_at(g0 + d, b);      // oldest to newest
+    for (; d + 4 <= eff; d += 4) {
+      const float v0 = psd_at(g0 + d, b), v1 = psd_at(g0 + d + 1, b), v2 = psd_at(g0 + d + 2, b), v3 = psd_at(g0 + d + 3, b);
+      c += (double) v0;
+      c += (double) v1;
+      c += (double) v2;
+      c += (double) v3;
+    }
+#pragma unroll 1
+    for (; d < eff; ++d) c += (double) psd_at(g0 + d, b);
     return c;
   };
   // (loops deliberately NOT unrolled: this code runs once per frame on one warp, inlined into the spectrogram

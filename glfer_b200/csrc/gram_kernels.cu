@@ -1017,6 +1017,7 @@ __global__ void __launch_bounds__(256) levels_kernel(const float *__restrict__ r
 extern "C" int glb_launch_agc(const float *stats, long long nframes, long long first_frame, float overlap, int log_scale,
                               float *state, float *range, void *stream) {
   if (nframes <= 0) return GLB_OK;
+  // (asking for most of an SM's shared memory, to keep the chain's CTA alone on its SM, changed nothing end to end)
   agc_kernel<<<1, 256, 0, (cudaStream_t) stream>>>(stats, nframes, first_frame, overlap, log_scale, state, range);
   CU(cudaGetLastError());
   g_launches++;
