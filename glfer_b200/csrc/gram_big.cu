@@ -16,6 +16,8 @@
 #include "gram_common.cuh"
 #include "fft_big.cuh"
 
+int g_big_pair = 1;                  // 0: never the two-groups-per-CTA variant (experiments)
+
 template <int M> struct BigGeo {
   static constexpr int T = Big<M>::T, N = 2 * M, NW = T / 32;
   static constexpr size_t BUF_BYTES = (size_t) Big<M>::BUF * sizeof(float2);
@@ -30,6 +32,12 @@ template <int M> struct BigGeo {
 #endif
   static __host__ __device__ constexpr bool tw2(bool multi) { return GLB_BIG_TW2 && BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + TW2_BYTES <= (size_t) 227 * 1024 / MINB - 1024; }
   static __host__ __device__ constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + (tw2(multi) ? TW2_BYTES : 0); }
+  // PAIR: one CTA of 2 T threads = two frame groups (own exchange buffer, reduction scratch and mbarrier each,
+  // own named barrier) that share the twiddle tables and ONE copy of the first half of the taper in shared memory
+  static constexpr size_t GROUP_BYTES = BUF_BYTES + RED_BYTES + 16;
+  static constexpr size_t HALF_TAPER_BYTES = (size_t) (M / 2) * sizeof(float2);
+  static constexpr size_t PAIR_SMEM = 2 * GROUP_BYTES + TW_BYTES + TW2_BYTES + HALF_TAPER_BYTES;
+  static constexpr bool PAIR_FITS = GLB_BIG_TW2 && T == 256 && PAIR_SMEM <= (size_t) 227 * 1024;   // N = 16384
 };
 
 // MULTI: Thomson multitaper (mtm_do, mtm.c:189-220): the frame goes through the transform once per taper -- its
@@ -37,30 +45,52 @@ template <int M> struct BigGeo {
 // (1 / lambda_k folded into the tapers) are summed in a shared-memory row [33][T], so that the register
 // budget of the periodogram kernel (two frames per SM at N = 16384) holds for the multitaper one too.
 // LEV: 8-bit display levels (levels.cuh) beside / instead of the float rows, pixel i = bin M - i.
-template <int M, int NBLK, bool MULTI, bool LEV>
-__global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(const KParams p) {
+// PAIR (periodogram with a symmetric taper, w[i] == w[N - 1 - i] bit for bit -- every window of fft.c:37-82
+// is): two frame groups per CTA, one per half of the threads, synchronised by a named barrier each; the first
+// half of the taper lives in shared memory once per SM and both halves of a frame are read from it (the
+// second half mirrored), instead of 64 KB per frame through an L1 that 2 x 104 KB of shared memory leave too
+// small for it (11 % hit rate).
+template <int M, int NBLK, bool MULTI, bool LEV, bool PAIR>
+__global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<M>::MINB) gram_big_kernel(const KParams p) {
   using G = BigGeo<M>;
   constexpr int T = G::T, N = G::N, NW = G::NW, QB = kBP / NBLK;     // QB registers (float2) per hop block
   constexpr int HOP = N / NBLK;
+  static_assert(!PAIR || (!MULTI && G::PAIR_FITS), "pair variant: periodogram only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-  float2 *tw1 = reinterpret_cast<float2 *>(smem_raw + G::BUF_BYTES);
-  float *red = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES);
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES);
+  const int g = PAIR ? (int) threadIdx.x / T : 0;
+  const int t = PAIR ? (int) threadIdx.x % T : (int) threadIdx.x;
+  // PAIR: [group 0: buf | red | mbar][group 1: ...][tw1 | tw2 | half taper]; else buf | tw1 | red | mbar | acc | tw2
+  unsigned char *grp = smem_raw + (PAIR ? (size_t) g * G::GROUP_BYTES : 0);
+  unsigned char *shr = smem_raw + 2 * G::GROUP_BYTES;
+  float2 *buf = reinterpret_cast<float2 *>(grp);
+  float2 *tw1 = reinterpret_cast<float2 *>(PAIR ? shr : smem_raw + G::BUF_BYTES);
+  float *red = reinterpret_cast<float *>(grp + G::BUF_BYTES + (PAIR ? 0 : G::TW_BYTES));
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(grp + G::BUF_BYTES + (PAIR ? 0 : G::TW_BYTES) + G::RED_BYTES);
   float *acc = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16) + threadIdx.x;   // [slot][T]
-  constexpr bool TW2 = G::tw2(MULTI);
-  float2 *tw2 = reinterpret_cast<float2 *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16 + (MULTI ? G::ACC_BYTES : 0));
-  const int t = threadIdx.x;
+  constexpr bool TW2 = PAIR || G::tw2(MULTI);
+  float2 *tw2 = reinterpret_cast<float2 *>(PAIR ? shr + G::TW_BYTES : smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16 + (MULTI ? G::ACC_BYTES : 0));
+  const float2 *htap = reinterpret_cast<const float2 *>(shr + G::TW_BYTES + G::TW2_BYTES);
+  auto gsync = [&]() {
+    if constexpr (PAIR) asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
+    else __syncthreads();
+  };
 
   // middle-pass twiddles exp(-2 pi i k r / (32 R1)) = roots[16 k r], one copy per CTA
-  for (int i = t; i < Big<M>::TW1; i += T) tw1[i] = p.roots[(i & 31) * ((i >> 5) + 1) * 16];
+  for (int i = threadIdx.x; i < Big<M>::TW1; i += blockDim.x) tw1[i] = p.roots[(i & 31) * ((i >> 5) + 1) * 16];
   if constexpr (TW2) {
+    if (g == 0) {
 #pragma unroll
-    for (int r = 1; r < 16; r++) tw2[(r - 1) * T + t] = p.roots[t * r];       // t r < 15 M / 32
+      for (int r = 1; r < 16; r++) tw2[(r - 1) * T + t] = p.roots[t * r];       // t r < 15 M / 32
+    }
+  }
+  if constexpr (PAIR) {
+    float2 *ht = reinterpret_cast<float2 *>(shr + G::TW_BYTES + G::TW2_BYTES);
+    const float2 *src = reinterpret_cast<const float2 *>(p.tapers);
+    for (int i = threadIdx.x; i < M / 2; i += 2 * T) ht[i] = src[i];
   }
   __syncthreads();
 
-  const long long fb = (long long) blockIdx.x * p.frames_per_group;
+  const long long fb = (long long) (blockIdx.x * (PAIR ? 2 : 1) + g) * p.frames_per_group;
   const int nact = (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group);
   const bool sub = p.fused_mean != 0;
   const bool db = p.rows_db != 0;
@@ -90,7 +120,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
       tma_load_1d(buf, p.samples + (s0 - p.origin), N * 4u, mbar);
     }
   }
-  __syncthreads();
+  __syncthreads();                     // (the last CTA-wide barrier: from here on the groups run on their own)
 
   for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride, lev_ptr += p.lev_stride) {
    float bs[NBLK];
@@ -130,7 +160,7 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
         if ((t & 31) == 0) red[b * NW + (t >> 5)] = s;
       }
     }
-    __syncthreads();                   // (A) block sums visible; everyone has taken its samples out of the buffer
+    gsync();                   // (A) block sums visible; everyone has taken its samples out of the buffer
     if (sub) {
       if (j == 0) {
 #pragma unroll
@@ -144,20 +174,31 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
 #pragma unroll
       for (int q = 0; q < kBP; q++) v[q] = sub2(v[q], bc(bs[q / QB]));
     }
+    if constexpr (PAIR) {
+      // pair i of the taper for i < M / 2; pair i >= M / 2 is pair M - 1 - i with its two weights exchanged
 #pragma unroll
-    for (int q = 0; q < kBP; q++) v[q] = mul2(v[q], ld_taper(w2 + T * q));
+      for (int q = 0; q < kBP / 2; q++) v[q] = mul2(v[q], htap[t + T * q]);
+#pragma unroll
+      for (int q = kBP / 2; q < kBP; q++) {
+        const float2 w = htap[M - 1 - t - T * q];
+        v[q] = mul2(v[q], make_float2(w.y, w.x));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kBP; q++) v[q] = mul2(v[q], ld_taper(w2 + T * q));
+    }
     big_pass0(v);
     big_scatter0<M>(v, t, buf);
-    __syncthreads();
+    gsync();
     big_load1<M>(v, t, buf);
     big_pass1<M>(v, t, tw1);
-    __syncthreads();                   // every thread has read before anyone overwrites
+    gsync();                   // every thread has read before anyone overwrites
     big_scatter1<M>(v, t, buf);
-    __syncthreads();
+    gsync();
     BigLast L;
     big_load_last<M>(L, t, p.roots, p.vtab, !TW2);
     big_load2<M>(v, t, buf);
-    __syncthreads();                   // (E) the last-pass loads are done: the buffer is free for the next frame
+    gsync();                   // (E) the last-pass loads are done: the buffer is free for the next frame
     {
       // what lands next: this frame again for its next taper (from L2), else the next frame
       const bool again = j + 1 < ntap;
@@ -219,29 +260,31 @@ __global__ void __launch_bounds__(Big<M>::T, BigGeo<M>::MINB) gram_big_kernel(co
   }
 }
 
-template <int M, int NBLK, bool MULTI, bool LEV>
+template <int M, int NBLK, bool MULTI, bool LEV, bool PAIR = false>
 static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
   using G = BigGeo<M>;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  auto kern = gram_big_kernel<M, NBLK, MULTI, LEV>;
-  constexpr size_t smem = G::smem(MULTI);
+  auto kern = gram_big_kernel<M, NBLK, MULTI, LEV, PAIR>;
+  constexpr size_t smem = PAIR ? G::PAIR_SMEM : G::smem(MULTI);
+  constexpr int GPC = PAIR ? 2 : 1;               // frame groups per CTA
   static thread_local int occ_cache[64];
   int &occ = occ_cache[dev & 63];
   if (occ == 0) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::T, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G::T * GPC, smem));
     if (occ < 1) occ = 1;
   }
-  // resident grid: every CTA walks a contiguous run of frames (its older hop blocks stay in L2)
-  long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ;
+  // resident grid: every frame group walks a contiguous run of frames (its older hop blocks stay in L2)
+  long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ * GPC;
   if (groups > kp.nframes) groups = kp.nframes;
   if (groups < 1) groups = 1;
   KParams k = kp;
   k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
-  const long long ctas = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-  kern<<<(unsigned) ctas, G::T, smem, st>>>(k);
+  const long long ngroups = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
+  const long long ctas = (ngroups + GPC - 1) / GPC;
+  kern<<<(unsigned) ctas, G::T * GPC, smem, st>>>(k);
   CU(cudaGetLastError());
   g_launches++;
   g_last_family = 5;
@@ -251,6 +294,13 @@ static int launch_big(const KParams &kp, int groups_hint, cudaStream_t st) {
 template <int M, bool MULTI, bool LEV>
 static int launch_big_ml(const KParams &kp, int groups_hint, cudaStream_t st) {
   const int n = 2 * M;
+  if constexpr (!MULTI && !LEV && BigGeo<M>::PAIR_FITS) {
+    if (kp.taper_sym && g_big_pair) {
+      if (kp.hop == n) return launch_big<M, 1, false, false, true>(kp, groups_hint, st);
+      if (kp.hop == n / 2) return launch_big<M, 2, false, false, true>(kp, groups_hint, st);
+      if (kp.hop == n / 4) return launch_big<M, 4, false, false, true>(kp, groups_hint, st);
+    }
+  }
   if (kp.hop == n) return launch_big<M, 1, MULTI, LEV>(kp, groups_hint, st);
   if (kp.hop == n / 2) return launch_big<M, 2, MULTI, LEV>(kp, groups_hint, st);
   if (kp.hop == n / 4) return launch_big<M, 4, MULTI, LEV>(kp, groups_hint, st);

@@ -23,6 +23,7 @@ using namespace glb;
 
 // shared state of the library (defined in gram_kernels.cu)
 extern std::atomic<unsigned long long> g_launches;
+extern int g_big_pair;
 extern int g_kernel_pref;            // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
 extern int g_last_family;            // family of the last spectrogram kernel launched (same numbering)
 extern "C" void glb_set_error(const char *msg);
@@ -46,6 +47,7 @@ struct KParams {
   long long origin, count;
   const float *tapers;
   int ntapers;
+  int taper_sym;              // 1: periodogram taper with w[i] == w[N - 1 - i] bit for bit
   const float *means;         // pre-computed block means (general geometry), or nullptr
   long long means_first_block;
   int fused_mean;             // 1: block means are computed inside the kernel (regular geometry)

@@ -31,7 +31,11 @@ extern "C" const char *glb_last_error(void) { return g_err; }
 extern "C" void glb_set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
 extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load(); }
 extern "C" void glb_force_generic_kernel(int on) { g_force_generic = on; }
-extern "C" void glb_set_kernel_preference(int pref) { g_kernel_pref = pref; }
+extern "C" void glb_set_kernel_preference(int pref) {
+  // 6 = automatic choice, but the 32-point kernel never pairs two frame groups in one CTA (A/B measurements)
+  g_big_pair = pref != 6;
+  g_kernel_pref = pref == 6 ? 0 : pref;
+}
 extern "C" int glb_last_kernel_family(void) { return g_last_family; }
 
 // ------------------------------------------------------------------------- plumbing
@@ -217,6 +221,7 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   k.count = a->count;
   k.tapers = a->tapers;
   k.ntapers = a->ntapers;
+  k.taper_sym = a->ntapers == 1 && a->taper_symmetric;
   k.means = a->block_means;
   k.means_first_block = a->means_first_block;
   k.fused_mean = a->fused_mean;

@@ -58,6 +58,7 @@ struct glfer_gram_plan {
   double *h_tapers;     /* MTM: [ntapers][n] */
   double *h_lambda;
   float *d_tapers;
+  int taper_sym;        /* periodogram: the uploaded table is mirror-symmetric bit for bit */
   void *tables;
   slot_t slot[NSLOT];
   int *d_cand_all, *d_peak_all;   /* whole-run *peakbin candidates / carried values */
@@ -319,6 +320,13 @@ int glfer_gram_plan_create(const glfer_gram_config *cfg, glfer_gram_plan **out)
       for (int i = 0; i < n; i++) scaled[(size_t) k * n + i] = (float) (p->h_tapers[(size_t) k * n + i] * g);
     }
   }
+  p->taper_sym = 0;
+  if (p->ntapers == 1) {
+    /* every window of fft.c:37-82 comes out mirror-symmetric bit for bit; checked, not assumed */
+    p->taper_sym = 1;
+    for (int i = 0; i < n / 2; i++)
+      if (memcmp(&scaled[i], &scaled[n - 1 - i], sizeof(float)) != 0) { p->taper_sym = 0; break; }
+  }
   rc = shim(glb_malloc((void **) &p->d_tapers, sizeof(float) * (size_t) p->ntapers * n));
   if (rc == 0) rc = shim(glb_memcpy_h2d(p->d_tapers, scaled, sizeof(float) * (size_t) p->ntapers * n, NULL));
   free(scaled);
@@ -413,6 +421,7 @@ static int exec_slot(glfer_gram_plan *p, slot_t *s, long long first, long long n
   g.count = s->s_count;
   g.tapers = p->d_tapers;
   g.ntapers = p->ntapers;
+  g.taper_symmetric = p->taper_sym;
   g.block_means = d_means;
   g.means_first_block = means_first;
   g.fused_mean = fused_mean;

@@ -92,6 +92,8 @@ typedef struct {
   const unsigned char *level_lut;   /* device: level of every integer dB value (fixed display range, log scales) or NULL */
   float level_min, level_max;  /* display_min / display_max (dB in the log scales); used when level_lut == NULL */
   float level_thr;             /* opt.thr_level / 100 */
+  int taper_symmetric;         /* 1: ntapers == 1 and tapers[i] == tapers[n - 1 - i] bit for bit (checked by the host layer
+                                  on the table it uploads): lets a kernel keep half of it in shared memory */
 } glb_gram_args;
 
 /* host-computed tables of the display mapping on the current device: dB thresholds as floats and doubles
@@ -111,7 +113,8 @@ int glb_gram_fused_avg_ok(int n, int hop, int depth, int band);
  * for the regular geometries) */
 void glb_force_generic_kernel(int on);
 /* 0 = automatic choice, 1 = general kernel, 2 = TMA ring kernel, 3 = warp-per-frame kernel, 4 = two frames per
- * thread, 5 = 32-points-per-thread kernel (N = 16384 / 32768; what the automatic choice takes there)
+ * thread, 5 = 32-points-per-thread kernel (N = 16384 / 32768; what the automatic choice takes there),
+ * 6 = automatic, but the 32-point kernel never pairs two frame groups per CTA (A/B measurements)
  * (a preference: launches a family cannot serve fall through to the next one) */
 void glb_set_kernel_preference(int pref);
 

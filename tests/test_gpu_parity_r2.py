@@ -405,6 +405,41 @@ def test_big_frame_kernel_vs_oracle_and_16_point_families(gpu_api):
     assert np.array_equal(one["psd"], many["psd"])
 
 
+def test_big_frame_pair_variant_is_bit_identical(gpu_api):
+    """N = 16384 periodograms take the two-groups-per-CTA variant of gram_big_kernel (half taper in shared
+    memory, second half mirrored) by default; kernel preference 6 keeps one group per CTA with the full taper
+    from global memory.  Same arithmetic on the same bits: rows must be identical for every window type (the
+    tables are mirror-symmetric bit for bit), every overlap, frame counts below / not a multiple of the
+    resident group count, dB rows and staged sub-ranges."""
+    x = synth.qrss_stream(16384 * 23 + 4321, fs=FS, seed=83, dot_s=0.2)
+    long = synth.qrss_stream(16384 * 340 + 99, fs=FS, seed=84, dot_s=0.2)      # > 2 x 148 groups, ragged
+    try:
+        for wt in range(8):
+            for ov, sm in ((0.5, True), (0.75, False), (0.0, True)):
+                kw = dict(n=16384, window_type=wt, overlap=ov, sub_mean=sm)
+                gpu_api.set_kernel_preference(0)
+                a = gpu_api.GramPlan(**kw).run(x)["psd"]
+                assert gpu_api.last_kernel_family().startswith("gram_big_kernel")
+                gpu_api.set_kernel_preference(6)
+                b = gpu_api.GramPlan(**kw).run(x)["psd"]
+                assert gpu_api.last_kernel_family().startswith("gram_big_kernel")
+                assert np.array_equal(a, b), (wt, ov, sm, int((a != b).sum()))
+        for nfr in (1, 2, 3, 297, None):
+            for db in (False, True):
+                kw = dict(n=16384, window_type=0, overlap=0.5, sub_mean=True, scale_db=db)
+                gpu_api.set_kernel_preference(0)
+                p0 = gpu_api.GramPlan(**kw)
+                nf = p0.num_frames(len(long)) if nfr is None else nfr
+                lo, hi = p0.required_span(7, nf - 7 if nfr is None else nf)
+                cnt = nf - 7 if nfr is None else nf
+                a = p0.run(np.ascontiguousarray(long[lo:hi]), origin=lo, first_frame=7, nframes=cnt)["psd"]
+                gpu_api.set_kernel_preference(6)
+                b = gpu_api.GramPlan(**kw).run(np.ascontiguousarray(long[lo:hi]), origin=lo, first_frame=7, nframes=cnt)["psd"]
+                assert a.shape[0] == cnt and np.array_equal(a, b), (nfr, db)
+    finally:
+        gpu_api.set_kernel_preference(0)
+
+
 # ------------------------------------------------------------------ per-call interface: k blocks per call
 def test_fft_do_batch_equals_the_sequence_of_single_calls(gpu_api):
     import ctypes as C
