@@ -468,7 +468,7 @@ def main():
                                       "levels_nonconstant": bool(probe.min() < probe.max())}
             # autoscale (glfer's default): float rows stay in HBM, floor statistics -> AGC recurrence -> levels
             disp["autoscale"] = True
-            disp["want_range"] = False                  # (a per-frame range download into pageable memory would stall the pipeline)
+            # (the per-frame display range comes back too: the library stages it through pinned memory)
             au_s = timed_e2e(lambda: plan.run_display(pcm_host, origin=lo, first_frame=first, nframes=nf, **disp))
             e2e["pcm16_in_u8_out_autoscale"] = {"value": world * nf * e2e_steps / au_s, "unit": "frames/s",
                                                 "ms_per_step": 1e3 * au_s / e2e_steps,
@@ -502,7 +502,7 @@ def main():
             if with_e2e and out_pinned is not None and cx is x_host:
                 o = {"psd": out_view(cnf, p.bins, np.float32)}
                 if p.avg:
-                    o["avg"] = np.empty((cnf, p.avg_cols), np.float32)
+                    o["avg"] = api.pinned_empty((cnf, p.avg_cols), np.float32)
                 p.run(cx, origin=corigin, first_frame=cfirst, nframes=cnf, out=o)
                 barrier()
                 t0 = time.perf_counter()

@@ -278,11 +278,11 @@ class GramPlan:
         avg = ret = pk = var = None
         if self.avg:
             avg = out.get("avg") if "avg" in out else np.empty((nframes, self.avg_cols), np.float32)
-            # the per-frame scalars are small but downloaded chunk by chunk: into pageable memory each of those
-            # copies would block the host thread and stall the chunk pipeline, so they are pinned
-            ret = out.get("ret") if "ret" in out else pinned_empty((nframes,), np.float64)
-            pk = out.get("peakbin") if "peakbin" in out else pinned_empty((nframes,), np.int32)
-            var = out.get("variance") if "variance" in out else pinned_empty((nframes,), np.float64)
+            # (the library stages these small per-frame outputs through pinned memory of its own: plain arrays do
+            # not stall the chunk pipeline; allocating pinned memory per call would cost ~100 ms per array)
+            ret = out.get("ret") if "ret" in out else np.empty((nframes,), np.float64)
+            pk = out.get("peakbin") if "peakbin" in out else np.empty((nframes,), np.int32)
+            var = out.get("variance") if "variance" in out else np.empty((nframes,), np.float64)
         return psd, avg, ret, pk, var
 
     def run(self, samples: np.ndarray, origin: int = 0, first_frame: int = 0, nframes: int | None = None,
@@ -342,8 +342,8 @@ class GramPlan:
                     nframes: int | None = None, agc_state: np.ndarray | None = None, want_rgb: bool = False,
                     out: dict | None = None, want_range: bool = True):
         """glfer_gram_run_display: rows -> 8-bit levels (and RGB) as main_window_draw maps them.
-        out: optional pre-allocated (pinned) "levels" / "range" arrays -- a download into pageable memory
-        blocks the host thread and with it the chunk pipeline."""
+        out: optional pre-allocated (pinned) "levels" array -- a download of rows into pageable memory blocks the
+        host thread and with it the chunk pipeline (the small "range" output is staged by the library)."""
         pcm = samples.dtype == np.int16
         assert samples.flags["C_CONTIGUOUS"] and (pcm or samples.dtype == np.float32)
         if nframes is None:

@@ -40,6 +40,27 @@ template <int M> struct BigGeo {
   static constexpr bool PAIR_FITS = GLB_BIG_TW2 && T == 256 && PAIR_SMEM <= (size_t) 227 * 1024;   // N = 16384
 };
 
+// the per-warp partial sums of a block, added as a tree from vector loads (not a chain of dependent loads)
+template <int NW> __device__ __forceinline__ float big_sum_warps(const float *r) {
+  float a[NW];
+  if constexpr (NW % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < NW / 4; i++) {
+      const float4 x = reinterpret_cast<const float4 *>(r)[i];
+      a[4 * i] = x.x; a[4 * i + 1] = x.y; a[4 * i + 2] = x.z; a[4 * i + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NW; i++) a[i] = r[i];
+  }
+#pragma unroll
+  for (int w = NW / 2; w >= 1; w /= 2) {
+#pragma unroll
+    for (int i = 0; i < w; i++) a[i] += a[i + w];
+  }
+  return a[0];
+}
+
 // MULTI: Thomson multitaper (mtm_do, mtm.c:189-220): the frame goes through the transform once per taper -- its
 // samples land again by TMA from L2 each time, the block means are formed once -- and the eigenspectra
 // (1 / lambda_k folded into the tapers) are summed in a shared-memory row [33][T], so that the register
@@ -122,8 +143,8 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
   }
   __syncthreads();                     // (the last CTA-wide barrier: from here on the groups run on their own)
 
+  float bs[NBLK] = {};                 // block means, carried from frame to frame
   for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride, lev_ptr += p.lev_stride) {
-   float bs[NBLK];
    for (int j = 0; j < ntap; ++j) {
     const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers + (size_t) j * N) + t;
     float2 v[kBP];
@@ -149,12 +170,20 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
     if (sub && j == 0) {
       // block means (prepare_audio, fft.c:86-96): block b = registers [b QB, (b + 1) QB).  The summation tree
       // of a block does not depend on its position in the frame, so its mean is the same bits in every
-      // frame (and time shard) it appears in; zero history sums to a zero mean.
+      // frame (and time shard) it appears in; zero history sums to a zero mean.  Hence only the NEWEST block
+      // is summed after a group's first frame: the older ones are the previous frame's means, moved down.
 #pragma unroll
       for (int b = 0; b < NBLK; b++) {
-        float s = 0.f;
+        if (b < NBLK - 1 && it > 0) continue;
+        float a[QB];
 #pragma unroll
-        for (int q = b * QB; q < (b + 1) * QB; q++) s += v[q].x + v[q].y;
+        for (int q = 0; q < QB; q++) a[q] = v[b * QB + q].x + v[b * QB + q].y;
+#pragma unroll
+        for (int w = QB / 2; w >= 1; w /= 2) {
+#pragma unroll
+          for (int q = 0; q < w; q++) a[q] += a[q + w];
+        }
+        float s = a[0];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if ((t & 31) == 0) red[b * NW + (t >> 5)] = s;
@@ -165,10 +194,8 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
       if (j == 0) {
 #pragma unroll
         for (int b = 0; b < NBLK; b++) {
-          float s = 0.f;
-#pragma unroll
-          for (int w = 0; w < NW; w++) s += red[b * NW + w];
-          bs[b] = s * p.inv_hop_mean;
+          if (b < NBLK - 1 && it > 0) bs[b] = bs[b + 1];
+          else bs[b] = big_sum_warps<NW>(red + b * NW) * p.inv_hop_mean;
         }
       }
 #pragma unroll
