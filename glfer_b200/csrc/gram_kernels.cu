@@ -647,9 +647,8 @@ extern "C" int glb_launch_peak_carry(const int *cand, int *peakbin, long long nf
 // (mean, then variance) in slot order and stay in L1/L2.  Double arithmetic throughout, as the
 // reference (my, sy, v_hat are doubles); IEEE sqrt and division, so inf / NaN appear exactly
 // where the reference produces them (v_hat = 0).
-// (Tried in round 2 and dropped: Markstein's 3-operation division by the constants nl and nl - 1, the ring
-// kept in registers, non-contracted products -- bit-identical results, but 3.05 ms instead of 2.29 ms per
-// 84 375 rows: the kernel is not bound by the divisions.)
+// This general form serves the per-call ring (ring_rows > 0) and ring lengths the run kernel below is not
+// instantiated for.
 __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd, long long psd_first_frame, long long psd_stride,
                                                   int ring_rows, int nbins, long long first_frame, long long nframes, int nl,
                                                   double c0, double c1, int rows_db, float *__restrict__ out, long long out_stride) {
@@ -673,10 +672,10 @@ __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd,
     my /= nl;
     for (int j = 0; j < nl; j++) {
       const double d = (double) row(j) - my;
-      sy += d * d;
+      sy = __dadd_rn(sy, __dmul_rn(d, d));             // (no FMA contraction: the reference's doubles)
     }
     sy /= (nl - 1);
-    double v = my * my - sy;
+    double v = __dsub_rn(__dmul_rn(my, my), sy);
     if (v < 0.0) v = 0.0;
     v = 0.5 * (my - sqrt(v));
     float o = (float) (c0 + (nl * my) / (c1 * v));
@@ -689,6 +688,80 @@ __global__ void __launch_bounds__(256) lmp_kernel(const float *__restrict__ psd,
   }
 }
 
+// The batch form: one thread walks ONE bin through a run of consecutive frames with the ring in registers, in
+// slot order (runs start at multiples of NL, so the slot of every frame of the unrolled body is a compile-time
+// index).  A PSD value is loaded once per run instead of 2 nl times per frame, the frame index arithmetic is
+// paid once per run, and the divisions by the constants nl and nl - 1 take three operations (Markstein,
+// avg_frame.cuh: correctly rounded, the same bits as IEEE division).  Every product and sum is a separate
+// IEEE operation (no FMA contraction): the doubles are those of the reference built for baseline x86-64.
+// ncu on the general kernel above (profiles/r02_ncu_lmp_*): issue-bound, 416 instructions per (frame, bin) warp,
+// 28 % of the samples in the per-thread prologue.
+template <int NL>
+__global__ void __launch_bounds__(256) lmp_run_kernel(const float *__restrict__ psd, long long psd_first_frame, long long psd_stride,
+                                                      int nbins, long long first_frame, long long nframes, long long run0,
+                                                      int run_len, long long nruns, double c0, double c1, int rows_db,
+                                                      float *__restrict__ out, long long out_stride) {
+  const long long w = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nruns * nbins) return;
+  const long long run = w / nbins;
+  const int bin = (int) (w - run * nbins);
+  const long long fa = run0 + run * run_len;                 // a multiple of NL: frame fa + u lives in slot u
+  const long long fend = first_frame + nframes;
+  const long long fb = (fa + run_len < fend) ? fa + run_len : fend;
+  const float *col = psd + bin;
+  auto load = [&](long long g) -> double {                   // frames before the stream start were never written: 0
+    return (g >= 0 && g >= psd_first_frame) ? (double) __ldg(col + (g - psd_first_frame) * psd_stride) : 0.0;
+  };
+  constexpr double rn = 1.0 / NL, rn1 = 1.0 / (NL - 1);
+  constexpr bool pow2 = (NL & (NL - 1)) == 0, pow2m1 = ((NL - 1) & (NL - 2)) == 0;
+  double ring[NL];
+  ring[0] = 0.0;
+#pragma unroll
+  for (int j = 1; j < NL; j++) ring[j] = load(fa - NL + j);
+  for (long long base = fa; base < fb; base += NL) {
+    double nxt[NL];
+#pragma unroll
+    for (int u = 0; u < NL; u++) nxt[u] = (base + u < fb) ? load(base + u) : 0.0;
+#pragma unroll
+    for (int u = 0; u < NL; u++) {
+      const long long f = base + u;
+      if (f >= fb) break;
+      ring[u] = nxt[u];
+      if (f < first_frame) continue;
+      double my = 0.0;
+#pragma unroll
+      for (int j = 0; j < NL; j++) my = __dadd_rn(my, ring[j]);
+      my = pow2 ? __dmul_rn(my, rn) : avg_div_small(my, (double) NL, rn);
+      double sy = 0.0;
+#pragma unroll
+      for (int j = 0; j < NL; j++) {
+        const double d = __dsub_rn(ring[j], my);
+        sy = __dadd_rn(sy, __dmul_rn(d, d));
+      }
+      sy = pow2m1 ? __dmul_rn(sy, rn1) : avg_div_small(sy, (double) (NL - 1), rn1);
+      double v = __dsub_rn(__dmul_rn(my, my), sy);
+      if (v < 0.0) v = 0.0;
+      v = __dmul_rn(0.5, __dsub_rn(my, __dsqrt_rn(v)));
+      float o = (float) __dadd_rn(c0, __ddiv_rn(__dmul_rn((double) NL, my), __dmul_rn(c1, v)));
+      if ((double) o <= 1.0e-3) o = 1e-3f;
+      if (bin == 0) o = 1e-3f;
+      if (rows_db) o = 10.f * log10f(o);
+      out[(f - first_frame) * out_stride + bin] = o;
+    }
+  }
+}
+
+template <int NL>
+static void launch_lmp_run(const float *psd, long long psd_first_frame, long long psd_stride, int nbins, long long first_frame,
+                           long long nframes, double c0, double c1, int rows_db, float *out, long long out_stride, cudaStream_t st) {
+  const int run_len = NL * 8;
+  const long long run0 = (first_frame / NL) * NL;
+  const long long nruns = (first_frame + nframes - run0 + run_len - 1) / run_len;
+  const long long ctas = (nruns * nbins + 255) / 256;
+  lmp_run_kernel<NL><<<(unsigned) ctas, 256, 0, st>>>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, run0, run_len,
+                                                      nruns, c0, c1, rows_db, out, out_stride);
+}
+
 extern "C" int glb_launch_lmp(const float *psd, long long psd_first_frame, long long psd_stride, int psd_ring_rows, int nbins,
                               long long first_frame, long long nframes, int nl, int rows_db, float *out, long long out_stride,
                               void *stream) {
@@ -699,6 +772,21 @@ extern "C" int glb_launch_lmp(const float *psd, long long psd_first_frame, long 
   }
   // the two constants of lmp.c:154, in double on the host (IEEE sqrt: the same bits as on the device)
   const double c0 = -sqrt((double) nl / 2.0), c1 = 2.0 * sqrt(2.0 * (double) nl);
+  if (psd_ring_rows <= 0 && nl <= 8) {
+    cudaStream_t st = (cudaStream_t) stream;
+    switch (nl) {
+      case 2: launch_lmp_run<2>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+      case 3: launch_lmp_run<3>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+      case 4: launch_lmp_run<4>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+      case 5: launch_lmp_run<5>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+      case 6: launch_lmp_run<6>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+      case 7: launch_lmp_run<7>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+      default: launch_lmp_run<8>(psd, psd_first_frame, psd_stride, nbins, first_frame, nframes, c0, c1, rows_db, out, out_stride, st); break;
+    }
+    CU(cudaGetLastError());
+    g_launches++;
+    return GLB_OK;
+  }
   const int xb = (nbins + 255) / 256;
   // one frame per CTA row (neighbouring frames run together and share the ring rows in L1/L2;
   // a small persistent grid measured slower: 2.9 vs 2.4 ms per 84 375 rows)

@@ -185,6 +185,32 @@ def test_sharded_sumavg_with_unresolved_leading_frames(gpu_api):
     assert np.array_equal(pk, one["peakbin"]) and np.allclose(var, one["variance"], rtol=1e-9, equal_nan=True)
 
 
+def test_lmp_run_kernel_exact_for_every_ring_length(gpu_api):
+    """The batch LMP kernel (one thread per bin walking a run of frames, ring in registers, Markstein division by
+    nl and nl - 1) against the oracle formula on the GPU's own PSD rows: identical floats for every ring
+    length it is instantiated for (2 .. 8) and for the general kernel behind it (9 .. 12), on runs that start
+    and end off the run grid, and on a stream with a 200 dB step (sums that are not exact in double, so the
+    slot order matters)."""
+    x = synth.qrss_stream(512 * 150 + 77, fs=FS, seed=31, dot_s=0.2)
+    x[512 * 60:] *= np.float32(1e-10)                       # PSD drops by 200 dB in the middle of the run
+    x[512 * 100:] *= np.float32(1e10)
+    raw = gpu_api.GramPlan(n=1024, window_type=5, overlap=0.5, sub_mean=True).run(x)["psd"]
+    for nl in range(2, 13):
+        p = gpu_api.GramPlan(n=1024, mode=gpu_api.MODE_LMP, overlap=0.5, sub_mean=True, lmp_av=nl)
+        got = p.run(x)["psd"]
+        want = O.lmp_statistic(raw, nl)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (nl, int((got.view(np.uint32) != want.view(np.uint32)).sum()))
+        for first, cnt in ((1, 5), (nl - 1, 3 * nl + 1), (37, 70), (got.shape[0] - 3, 3)):
+            lo, hi = p.required_span(first, cnt)
+            lo = max(lo, 0)
+            sub = p.run(np.ascontiguousarray(x[lo:hi]), origin=lo, first_frame=first, nframes=cnt)["psd"]
+            assert np.array_equal(sub.view(np.uint32), want[first:first + cnt].view(np.uint32)), (nl, first, cnt)
+    db = gpu_api.GramPlan(n=1024, mode=gpu_api.MODE_LMP, overlap=0.5, sub_mean=True, lmp_av=4, scale_db=True).run(x)["psd"]
+    lin = O.lmp_statistic(raw, 4)
+    fin = np.isfinite(lin)
+    assert np.allclose(db[fin], 10.0 * np.log10(lin[fin]), atol=2e-4)
+
+
 def test_sharded_multitaper_and_lmp_bit_identical(gpu_api):
     x = synth.qrss_stream(200000, fs=FS, seed=44, dot_s=0.2)
     nd = gpu_api.device_count()
