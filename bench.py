@@ -415,7 +415,7 @@ def main():
         d2h = rows_host.nbytes + (avg_host.nbytes if avg_host is not None else 0)
         e2e = {"value": world * nf * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(x_host.nbytes),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-               "api": "glfer_gram_run (pinned host buffers, float32 in, float32 rows out, 2-slot chunked pipeline)"}
+               "api": "glfer_gram_run (pinned host buffers, float32 in, float32 rows out, 3-slot chunked pipeline)"}
         checksum = float(rows_host[:: max(1, nf // 97)].sum())
         # the copies alone, same bytes, same buffers' sizes, both directions at once on two streams: what the
         # host <-> device path of this box gives this many ranks, i.e. the ceiling of any end-to-end number

@@ -1001,12 +1001,139 @@ __global__ void __launch_bounds__(32 * kFsWarps) floor_stats_kernel(const float 
   }
 }
 
+// The same statistics with the row held in registers (rows of up to 32 NPL bins, K <= 128): one load per bin, then a
+// bit-by-bit descent from the highest bit in which the row's keys differ, counting in registers (no shared-
+// memory histogram: the first radix passes of the kernel above put a whole row into two or three counters, 32-way
+// conflicts).  The descent stops as soon as at most 128 bins remain at or below the current prefix range -- for
+// a noise-like row after some ten bits; those bins are compacted by ballots, sorted as above, and the last K of
+// them are summed.  If all 32 bits are spent first, the bins still undecided are equal to the threshold.
+// Per 4096 rows of 2049 bins: 65 us -> see profiles/ (the display path's autoscale statistics).
+template <int NPL>
+__global__ void __launch_bounds__(32 * kFsWarps) floor_stats_reg_kernel(const float *__restrict__ rows, long long stride,
+                                                                      int nbins, long long nrows, float *__restrict__ stats) {
+  constexpr int CAP = 128;
+  __shared__ float s_cand[kFsWarps][CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float *cand = s_cand[w];
+  const int K = nbins - (int) (nbins * 0.95);
+  const unsigned full = 0xffffffffu;
+  for (long long r = (long long) blockIdx.x * kFsWarps + w; r < nrows; r += (long long) gridDim.x * kFsWarps) {
+    const float *row = rows + r * stride;
+    unsigned key[NPL];
+    float best = 0.f, top = -INFINITY;
+    int best_i = 0x7fffffff;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+    for (int k = 0; k < NPL; k++) {
+      const int i = lane + 32 * k;
+      if (i < nbins) {
+        const float v = __ldg(row + i);
+        key[k] = fs_key(v);
+        if (v > best) { best = v; best_i = i; }             // a lane's bins ascend: its first maximum
+        top = fmaxf(top, v);
+        kmin = min(kmin, key[k]);
+        kmax = max(kmax, key[k]);
+      } else {
+        key[k] = 0xffffffffu;                               // padding: above every bin, never gathered
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(full, best, o);
+      const int oi = __shfl_xor_sync(full, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+      top = fmaxf(top, __shfl_xor_sync(full, top, o));
+    }
+    kmin = __reduce_min_sync(full, kmin);
+    kmax = __reduce_max_sync(full, kmax);
+    // keys agree above `bit`; P = the common prefix, the range [P, P + 2^(bit+1)) holds every bin
+    int bit = 31 - __clz(kmin ^ kmax);                      // -1: all bins equal
+    unsigned P = (bit == 31) ? 0u : ((kmin >> (bit + 1)) << (bit + 1));
+    int n_lt = 0, n_in = nbins;                             // bins below P / inside the range; n_lt < K <= n_lt + n_in
+    while (bit >= 0 && n_lt + n_in > CAP) {
+      const unsigned half = 1u << bit;
+      int c0 = 0;
+#pragma unroll
+      for (int k = 0; k < NPL; k++) c0 += (key[k] - P < half) ? 1 : 0;      // (bins below P wrap to huge values)
+      c0 = __reduce_add_sync(full, c0);
+      if (K <= n_lt + c0) {
+        n_in = c0;
+      } else {
+        n_lt += c0;
+        n_in -= c0;
+        P += half;
+      }
+      --bit;
+    }
+    // candidates: with the range narrowed to <= CAP bins, every bin up to the end of the range; otherwise (all
+    // bits spent: the n_in undecided bins equal P) the bins below P, then copies of the threshold up to K
+    const bool ties = n_lt + n_in > CAP;
+    const unsigned span1 = (bit < 0) ? 0u : (bit == 31) ? 0xffffffffu : ((2u << bit) - 1u);   // range length - 1
+    const unsigned last = ties ? P - 1u : P + span1;                         // gather keys <= last (ties: n_lt > 0 => P > 0)
+    const bool any = !(ties && n_lt == 0);
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < NPL; k++) {
+      const bool take = any && (lane + 32 * k < nbins) && key[k] <= last;
+      const unsigned m = __ballot_sync(full, take);
+      if (take) {
+        const unsigned kk = key[k];
+        cand[c + __popc(m & ((1u << lane) - 1u))] = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
+      }
+      c += __popc(m);
+    }
+    if (ties) {
+      const float tv = __uint_as_float((P & 0x80000000u) ? (P & 0x7fffffffu) : ~P);
+      for (int i = c + lane; i < K; i += 32) cand[i] = tv;
+      c = K;
+    }
+    for (int i = c + lane; i < CAP; i += 32) cand[i] = -INFINITY;            // padding sorts behind the candidates
+    __syncwarp();
+    for (int k2 = 2; k2 <= CAP; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = lane; i < CAP; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const float a = cand[i], b = cand[l];
+            const bool desc = ((i & k2) == 0);
+            if (desc ? (a < b) : (a > b)) { cand[i] = b; cand[l] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      float fsum = 0.f;
+      for (int i = c - K; i < c; i++) fsum += cand[i];      // the K smallest, descending (fft.c:271-272)
+      float fl = (float) ((double) fsum / 0.05);
+      fl = fl / (float) nbins;
+      float *o = stats + r * 4;
+      o[0] = top;
+      o[1] = fl;
+      o[2] = (best > 0.f) ? best : 0.f;
+      o[3] = (best > 0.f) ? (float) best_i : 0.f;
+    }
+    __syncwarp();
+  }
+}
+
 extern "C" int glb_launch_floor_stats(const float *rows, long long stride, int nbins, long long nrows, float *stats,
                                       void *stream) {
   if (nrows <= 0) return GLB_OK;
   if (nbins < 1 || nbins - (int) (nbins * 0.95) > kFsMaxK) { glb_set_error("floor_stats: row too wide"); return GLB_EINVAL; }
   long long ctas = (nrows + kFsWarps - 1) / kFsWarps;
   if (ctas > 148 * 16) ctas = 148 * 16;
+  const int K = nbins - (int) (nbins * 0.95);
+  if (K >= 1 && K <= 128 && nbins <= 32 * 65 && g_kernel_pref != 1) {
+    cudaStream_t st = (cudaStream_t) stream;
+    if (nbins <= 32 * 17) floor_stats_reg_kernel<17><<<(unsigned) ctas, 32 * kFsWarps, 0, st>>>(rows, stride, nbins, nrows, stats);
+    else if (nbins <= 32 * 33) floor_stats_reg_kernel<33><<<(unsigned) ctas, 32 * kFsWarps, 0, st>>>(rows, stride, nbins, nrows, stats);
+    else floor_stats_reg_kernel<65><<<(unsigned) ctas, 32 * kFsWarps, 0, st>>>(rows, stride, nbins, nrows, stats);
+    CU(cudaGetLastError());
+    g_launches++;
+    return GLB_OK;
+  }
   floor_stats_kernel<<<(unsigned) ctas, 32 * kFsWarps, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nrows, stats);
   CU(cudaGetLastError());
   g_launches++;
@@ -1077,32 +1204,60 @@ __global__ void __launch_bounds__(256) agc_kernel(const float *__restrict__ stat
   if (tid < 2) state[tid] = s_state[tid];
 }
 
-// levels_kernel: one warp per row.  Pixel i of a row shows bin n-1-i (g_main.c:1193-1201); in
-// the log scales the level first passes through the reference's `short` level buffer
-// (sig_level = levbuf[..] = 10 log10(x): integer-truncated dB, g_main.c:68,1193-1195), located
+// levels_kernel: one thread per four consecutive pixels of the [nframes][nbins] level image (one 32-bit
+// store; rows are nbins = n/2 + 1 bytes, so a group may straddle two rows).  Pixel i of a row shows bin
+// n-1-i (g_main.c:1193-1201); in the log scales the level first passes through the reference's `short`
+// level buffer (sig_level = levbuf[..] = 10 log10(x): integer-truncated dB, g_main.c:68,1193-1195), located
 // between the host-computed thresholds (levels.cuh) so that it is the host libm's value bit for bit.
+// (The first version walked a row per warp, one dependent load per iteration: 59 us per 4096 rows of 2049
+// bins, latency-bound at 0.7 TB/s.)
 __global__ void __launch_bounds__(256) levels_kernel(const float *__restrict__ rows, long long stride, int nbins,
                                                      long long nframes, const float *__restrict__ range, LevelMap lm,
                                                      const unsigned char *__restrict__ colortab,
                                                      unsigned char *__restrict__ levels, unsigned char *__restrict__ rgb) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long) gridDim.x * blockDim.x) >> 5;
-  for (long long f = warp; f < nframes; f += nwarps) {
-    if (range) {                                         // per-frame display range (autoscale)
-      lm.dmax = range[2 * f];
-      lm.dmin = range[2 * f + 1];
+  const long long total = nframes * (long long) nbins;
+  const long long p0 = 4 * ((long long) blockIdx.x * blockDim.x + threadIdx.x);
+  if (p0 >= total) return;
+  long long f = p0 / nbins;
+  int i = (int) (p0 - f * nbins);
+  const int cnt = (total - p0 < 4) ? (int) (total - p0) : 4;
+  float x[4];
+  float2 rg[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    long long fe = f;
+    int ie = i + e;
+    while (ie >= nbins) { ie -= nbins; fe++; }
+    x[e] = (e < cnt) ? __ldg(rows + fe * stride + (nbins - 1 - ie)) : 0.f;
+    rg[e] = (range && e < cnt) ? __ldg(reinterpret_cast<const float2 *>(range) + fe) : make_float2(lm.dmax, lm.dmin);
+  }
+  unsigned char v[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    LevelMap m = lm;
+    m.dmax = rg[e].x;                                      // per-frame display range (autoscale)
+    m.dmin = rg[e].y;
+    v[e] = map_level(x[e], m);
+  }
+  if (levels) {
+    if (cnt == 4) *reinterpret_cast<uchar4 *>(levels + p0) = make_uchar4(v[0], v[1], v[2], v[3]);
+    else for (int e = 0; e < cnt; e++) levels[p0 + e] = v[e];
+  }
+  if (rgb) {
+    unsigned char px[12];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      px[3 * e] = colortab[3 * v[e]];
+      px[3 * e + 1] = colortab[3 * v[e] + 1];
+      px[3 * e + 2] = colortab[3 * v[e] + 2];
     }
-    const float *row = rows + f * stride;
-    for (int i = lane; i < nbins; i += 32) {
-      const unsigned char v = map_level(row[nbins - 1 - i], lm);
-      if (levels) levels[f * nbins + i] = v;
-      if (rgb) {
-        unsigned char *px = rgb + (f * nbins + i) * 3;
-        px[0] = colortab[3 * v];
-        px[1] = colortab[3 * v + 1];
-        px[2] = colortab[3 * v + 2];
-      }
+    if (cnt == 4) {
+      uint32_t *o = reinterpret_cast<uint32_t *>(rgb + 3 * p0);      // 12 p0' bytes: 4-byte aligned
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        o[q] = (uint32_t) px[4 * q] | ((uint32_t) px[4 * q + 1] << 8) | ((uint32_t) px[4 * q + 2] << 16) | ((uint32_t) px[4 * q + 3] << 24);
+    } else {
+      for (int e = 0; e < 3 * cnt; e++) rgb[3 * p0 + e] = px[e];
     }
   }
 }
@@ -1133,9 +1288,13 @@ extern "C" int glb_launch_levels(const float *rows, long long stride, int nbins,
   lm.dmax = fixed_range ? fixed_range[0] : 0.f;
   lm.dmin = fixed_range ? fixed_range[1] : 0.f;
   lm.thr_level = thr;
-  long long ctas = (nframes * 32 + 255) / 256;
-  if (ctas > 148 * 64) ctas = 148 * 64;
-  levels_kernel<<<(int) ctas, 256, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nframes, range, lm, colortab, levels, rgb);
+  if (nbins < 1 || ((reinterpret_cast<uintptr_t>(levels) | reinterpret_cast<uintptr_t>(rgb)) & 3) ||
+      (range && (reinterpret_cast<uintptr_t>(range) & 7))) {
+    glb_set_error("glb_launch_levels: unaligned output or range");
+    return GLB_EINVAL;
+  }
+  const long long ctas = ((nframes * nbins + 3) / 4 + 255) / 256;
+  levels_kernel<<<(unsigned) ctas, 256, 0, (cudaStream_t) stream>>>(rows, stride, nbins, nframes, range, lm, colortab, levels, rgb);
   CU(cudaGetLastError());
   g_launches++;
   return GLB_OK;

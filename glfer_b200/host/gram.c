@@ -19,8 +19,11 @@
 #include <string.h>
 #include "glb_host.h"
 
+/* chunks in flight (stream + device buffers each).  Two overlap H2D / kernels / D2H of a plain run; the autoscale
+   display chain (floor statistics -> AGC recurrence -> levels, ~0.25 ms of dependent kernels per chunk between the
+   copies) needs a third to stay PCIe-bound: 8.9 -> 7.0 ms per hour of signal (four: 7.4 ms). */
 #ifndef NSLOT
-#define NSLOT 2
+#define NSLOT 3
 #endif
 
 typedef struct {
@@ -717,7 +720,7 @@ static int scal_staging(glfer_gram_plan *p, size_t bytes, void **out)
 static long long chunk_frames(const glfer_gram_plan *p)
 {
   /* ~32 MiB of new samples per chunk: large enough to run the copy engines and the
-     kernel at full rate, small enough that two slots overlap well */
+     kernel at full rate, small enough that the slots overlap well */
   long long mib = 32;
   const char *e = getenv("GLFER_B200_CHUNK_MIB");            /* experiments */
   if (e && atoi(e) > 0) mib = atoi(e);
@@ -746,7 +749,7 @@ static int run_impl(glfer_gram_plan *p, const float *samples, const short *pcm, 
   /* *peakbin is carried from frame to frame (avg.c:129-133).  SUMAVG needs the carried
      value inside the kernel (variance excludes it, avg.c:279), so its chunks hand the
      value over serially; the other modes collect per-frame candidates for the whole run
-     and resolve the carry once at the end, keeping the two slots fully overlapped. */
+     and resolve the carry once at the end, keeping the slots fully overlapped. */
   const int serial_carry = avg_on && p->cfg.avg_mode == GLFER_AVG_SUMAVG;
   const int defer_carry = avg_on && !serial_carry;
   if (defer_carry) {
@@ -842,7 +845,7 @@ int glfer_gram_run_pcm16(glfer_gram_plan *p, const short *pcm, long long origin,
 /* ---------------------------------------------------------------- display mapping
  * The tail of main_window_draw (g_main.c:1109-1229) for a whole run: per-row floor statistics
  * (compute_floor), the AGC of the display range (a recurrence over frames, walked in order on
- * the device and carried from chunk to chunk through an event chain between the two slots),
+ * the device and carried from chunk to chunk through an event chain between the slots),
  * then 8-bit levels / RGB.  Only 1 (levels) or 3 (RGB) bytes per bin go back to the host. */
 static int run_display_impl(glfer_gram_plan *p, const float *samples, const short *pcm, long long origin,
                             long long count, long long first_frame, long long nframes,

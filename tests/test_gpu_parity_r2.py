@@ -520,10 +520,13 @@ def test_compute_floor_bit_exact_and_autoscale_display_on_wide_rows(gpu_api):
     import ctypes as C
     lib = gpu_api.lib()
     rng = np.random.default_rng(12)
-    for nb in (17, 257, 513, 2049, 8193, 16385):
+    for nb in (17, 33, 257, 513, 544, 545, 1056, 1057, 2049, 2080, 2081, 8193, 16385):
         rows = [(rng.standard_normal(nb) ** 2 * 1e-6).astype(np.float32), np.full(nb, 3e-7, np.float32),
-                np.zeros(nb, np.float32), (rng.integers(0, 4, nb) * 1e-5).astype(np.float32)]
+                np.zeros(nb, np.float32), (rng.integers(0, 4, nb) * 1e-5).astype(np.float32),
+                np.full(nb, 3e-7, np.float32), (rng.standard_normal(nb) ** 2 * 10.0 ** rng.uniform(-30, 5, nb)).astype(np.float32)]
         rows[0][nb // 3] = 2e-3
+        rows[4][: nb // 50] = (rng.random(nb // 50) * 1e-7).astype(np.float32)    # a few bins below a wide tie at the threshold
+        rows[4] = rng.permutation(rows[4])
         for row in rows:
             s, f, p, b = C.c_float(), C.c_float(), C.c_float(), C.c_uint()
             r = row.copy()

@@ -28,7 +28,11 @@ def timed(label, **kw):
     p.close()
 
 
-for mib in (8, 32, 128, 512):
+if "--once" in sys.argv:                 # launch list under ncu: one autoscale run
+    p = api.GramPlan(n=4096, window_type=0, overlap=0.5, sub_mean=True)
+    p.run_display(pcm[: 40 * 2048 * 4096], out={"levels": lev[: 40 * 4096 - 1]}, log_scale=True, autoscale=True)
+    sys.exit(0)
+for mib in (32, 128):
     os.environ["GLFER_B200_CHUNK_MIB"] = str(mib)
     timed(f"autoscale, chunk {mib} MiB", log_scale=True, autoscale=True)
     timed(f"fixed range (fused), chunk {mib} MiB", log_scale=True, autoscale=False)
