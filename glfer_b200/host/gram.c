@@ -731,6 +731,9 @@ static long long chunk_frames(const glfer_gram_plan *p)
   return f;
 }
 
+/* (A ramp of chunk sizes at both ends of a run was tried and dropped: the download stream trails the upload
+   stream by one full-size chunk whatever the sizes at the ends, so fill + drain stay one chunk = 0.7 of the
+   15 ms an hour of signal takes; 32 MiB is where that balances the ~28 us each further chunk costs.) */
 static int run_impl(glfer_gram_plan *p, const float *samples, const short *pcm, long long origin, long long count,
                     long long first_frame, long long nframes, float *psd_rows, float *avg_rows, double *avg_ret,
                     int *avg_peakbin, double *avg_variance)
