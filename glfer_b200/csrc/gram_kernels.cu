@@ -746,6 +746,7 @@ __global__ void __launch_bounds__(256) lmp_run_kernel(const float *__restrict__ 
       if ((double) o <= 1.0e-3) o = 1e-3f;
       if (bin == 0) o = 1e-3f;
       if (rows_db) o = 10.f * log10f(o);
+      GLB_CHECK(f - first_frame >= 0 && f - first_frame < nframes && bin < nbins);
       out[(f - first_frame) * out_stride + bin] = o;
     }
   }
@@ -1077,6 +1078,7 @@ __global__ void __launch_bounds__(32 * kFsWarps) floor_stats_reg_kernel(const fl
       const bool take = any && (lane + 32 * k < nbins) && key[k] <= last;
       const unsigned m = __ballot_sync(full, take);
       if (take) {
+        GLB_CHECK(c + __popc(m & ((1u << lane) - 1u)) < CAP);
         const unsigned kk = key[k];
         cand[c + __popc(m & ((1u << lane) - 1u))] = __uint_as_float((kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk);
       }
@@ -1105,6 +1107,7 @@ __global__ void __launch_bounds__(32 * kFsWarps) floor_stats_reg_kernel(const fl
     }
     if (lane == 0) {
       float fsum = 0.f;
+      GLB_CHECK(c >= K && c <= CAP);
       for (int i = c - K; i < c; i++) fsum += cand[i];      // the K smallest, descending (fft.c:271-272)
       float fl = (float) ((double) fsum / 0.05);
       fl = fl / (float) nbins;
@@ -1228,6 +1231,7 @@ __global__ void __launch_bounds__(256) levels_kernel(const float *__restrict__ r
     long long fe = f;
     int ie = i + e;
     while (ie >= nbins) { ie -= nbins; fe++; }
+    GLB_CHECK(e >= cnt || (fe < nframes && ie >= 0));
     x[e] = (e < cnt) ? __ldg(rows + fe * stride + (nbins - 1 - ie)) : 0.f;
     rg[e] = (range && e < cnt) ? __ldg(reinterpret_cast<const float2 *>(range) + fe) : make_float2(lm.dmax, lm.dmin);
   }
