@@ -178,8 +178,7 @@ def kernel_launches() -> int:
 
 
 KERNEL_FAMILIES = {0: "none", 1: "gram_kernel (general)", 2: "gram_ring_kernel (TMA ring)", 3: "gram_wpf_kernel (warp per frame)",
-                   4: "gram_pair_kernel (two frames per thread)", 5: "gram_big_kernel (32 points per thread)",
-                   6: "gram_ring_kernel (TMA ring; gram_ring_ahead_kernel: block sums one frame ahead)"}
+                   4: "gram_pair_kernel (two frames per thread)", 5: "gram_big_kernel (32 points per thread)"}
 
 
 def last_kernel_family() -> str:

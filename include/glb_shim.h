@@ -114,8 +114,7 @@ int glb_gram_fused_avg_ok(int n, int hop, int depth, int band);
 void glb_force_generic_kernel(int on);
 /* 0 = automatic choice, 1 = general kernel, 2 = TMA ring kernel, 3 = warp-per-frame kernel, 4 = two frames per
  * thread, 5 = 32-points-per-thread kernel (N = 16384 / 32768; what the automatic choice takes there),
- * 6 = automatic, but the 32-point kernel never pairs two frame groups per CTA, 7 = automatic, but the ring kernel
- * never forms the block sums one frame ahead (A/B measurements)
+ * 6 = automatic, but the 32-point kernel never pairs two frame groups per CTA (A/B measurements)
  * (a preference: launches a family cannot serve fall through to the next one) */
 void glb_set_kernel_preference(int pref);
 
@@ -199,7 +198,7 @@ int glb_launch_ftest(const float *spec, long long nframes, int nbins, int n, int
 /* counters */
 unsigned long long glb_kernel_launches(void);
 /* family of the last spectrogram kernel launched: 1 general, 2 TMA ring, 3 warp-per-frame, 4 two frames per thread,
- * 5 32 points per thread, 6 TMA ring with the block sums formed one frame ahead */
+ * 5 32 points per thread */
 int glb_last_kernel_family(void);
 
 #ifdef __cplusplus

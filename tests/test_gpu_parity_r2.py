@@ -431,41 +431,6 @@ def test_big_frame_kernel_vs_oracle_and_16_point_families(gpu_api):
     assert np.array_equal(one["psd"], many["psd"])
 
 
-def test_ring_kernel_sums_one_frame_ahead_is_bit_identical(gpu_api):
-    """N = 2048 / 4096 periodograms with block means removed at 50 / 75 % overlap take gram_ring_ahead_kernel (the
-    newest block's sums formed at the end of the previous frame, four barriers per frame); kernel preference 7
-    keeps gram_ring_kernel.  Same arithmetic on the same bits: identical rows, also dB rows, ragged frame
-    counts, sub-ranges staged at an offset (zero history only at the stream start) and frame counts below the
-    number of resident groups."""
-    x = synth.qrss_stream(4096 * 700 + 1234, fs=FS, seed=85, dot_s=0.2)
-    try:
-        for n in (2048, 4096):
-            for ov in (0.5, 0.75):
-                for wt, db in ((0, False), (7, True), (5, False)):
-                    kw = dict(n=n, window_type=wt, overlap=ov, sub_mean=True, scale_db=db)
-                    gpu_api.set_kernel_preference(0)
-                    p0 = gpu_api.GramPlan(**kw)
-                    a = p0.run(x)["psd"]
-                    assert gpu_api.last_kernel_family().startswith("gram_ring_kernel")
-                    gpu_api.set_kernel_preference(7)
-                    p7 = gpu_api.GramPlan(**kw)
-                    b = p7.run(x)["psd"]
-                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n, ov, wt, int((a != b).sum()))
-                    for first, cnt in ((0, 1), (0, 5), (3, 2), (17, 333), (a.shape[0] - 9, 9)):
-                        lo, hi = p0.required_span(first, cnt)
-                        lo = max(lo, 0)
-                        seg = np.ascontiguousarray(x[lo:hi])
-                        gpu_api.set_kernel_preference(0)
-                        s0 = p0.run(seg, origin=lo, first_frame=first, nframes=cnt)["psd"]
-                        assert np.array_equal(s0.view(np.uint32), a[first:first + cnt].view(np.uint32)), (n, ov, first, cnt)
-        ref = O.periodogram(x[: 4096 * 40], 4096, 0, 0.5, True)
-        gpu_api.set_kernel_preference(0)
-        got = gpu_api.GramPlan(n=4096, window_type=0, overlap=0.5, sub_mean=True).run(x[: 4096 * 40])["psd"]
-        assert_psd_close(got, ref, "ahead kernel vs oracle")
-    finally:
-        gpu_api.set_kernel_preference(0)
-
-
 def test_big_frame_pair_variant_is_bit_identical(gpu_api):
     """N = 16384 periodograms take the two-groups-per-CTA variant of gram_big_kernel (half taper in shared
     memory, second half mirrored) by default; kernel preference 6 keeps one group per CTA with the full taper
