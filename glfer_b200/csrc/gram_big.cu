@@ -143,8 +143,38 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
   }
   __syncthreads();                     // (the last CTA-wide barrier: from here on the groups run on their own)
 
+  // PAIR: the two groups of a CTA start together and take the same time per frame; left alone they stay in step,
+  // both in their butterflies (FP32 pipe) or both in their exchanges (shared-memory pipe) at once.  A frame is
+  // FP-heavy at both ends (first pass; last pass + split) and exchange-heavy in the middle, so the groups are
+  // held half a frame apart by a handshake on two named barriers: a group starts a frame only when the OTHER one
+  // has passed the first exchange of its current frame (bar.arrive there, bar.sync here: 256 + 256 threads).
+  // Both groups run the same number of iterations (idle ones past their last frame) so that the counts match.
+  // p.stagger: 0 handshake (default), 1 none, > 1 a start delay of that many cycles for group 1 (experiments).
+  const bool shake = PAIR && p.stagger == 0;
+  auto hs_arrive = [&]() {
+    if constexpr (PAIR) {
+      if (shake) asm volatile("bar.arrive %0, %1;" ::"r"(3 + g), "n"(2 * T) : "memory");
+    }
+  };
+  auto hs_wait = [&]() {
+    if constexpr (PAIR) {
+      if (shake) asm volatile("bar.sync %0, %1;" ::"r"(3 + (1 - g)), "n"(2 * T) : "memory");
+    }
+  };
+  if constexpr (PAIR) {
+    if (g == 1 && p.stagger > 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger) { }
+    }
+  }
   float bs[NBLK] = {};                 // block means, carried from frame to frame
-  for (int it = 0; it < nact; ++it, s0 += HOP, row_ptr += p.row_stride, lev_ptr += p.lev_stride) {
+  const int n_iter = (PAIR && shake) ? p.frames_per_group : nact;
+  for (int it = 0; it < n_iter; ++it, s0 += HOP, row_ptr += p.row_stride, lev_ptr += p.lev_stride) {
+   if (g == 1 || it > 0) hs_wait();    // group 1: group 0 is past the first exchange of frame `it`; group 0: group 1 of frame `it - 1`
+   if (it >= nact) {                   // (PAIR only: an idle iteration keeps the handshake counts equal)
+     hs_arrive();
+     continue;
+   }
    for (int j = 0; j < ntap; ++j) {
     const float2 *w2 = reinterpret_cast<const float2 *>(p.tapers + (size_t) j * N) + t;
     float2 v[kBP];
@@ -217,6 +247,7 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
     big_pass0(v);
     big_scatter0<M>(v, t, buf);
     gsync();
+    hs_arrive();               // (later points of the frame measured slower: after pass 1 +1 %, after the second exchange +7 %)
     big_load1<M>(v, t, buf);
     big_pass1<M>(v, t, tw1);
     gsync();                   // every thread has read before anyone overwrites
@@ -285,6 +316,7 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
     if (t == 0) st_row(row_ptr + M / 2, yv[32]);
    }
   }
+  if (g == 0 && n_iter > 0) hs_wait();   // (PAIR: group 1's last arrival)
 }
 
 template <int M, int NBLK, bool MULTI, bool LEV, bool PAIR = false>
