@@ -91,9 +91,14 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
   constexpr bool TW2 = PAIR || G::tw2(MULTI);
   float2 *tw2 = reinterpret_cast<float2 *>(PAIR ? shr + G::TW_BYTES : smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16 + (MULTI ? G::ACC_BYTES : 0));
   const float2 *htap = reinterpret_cast<const float2 *>(shr + G::TW_BYTES + G::TW2_BYTES);
+  // (barrier numbers as immediates: with the number in a register ptxas reserves all 16 barriers)
   auto gsync = [&]() {
-    if constexpr (PAIR) asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
-    else __syncthreads();
+    if constexpr (PAIR) {
+      if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+      else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
+    } else {
+      __syncthreads();
+    }
   };
 
   // middle-pass twiddles exp(-2 pi i k r / (32 R1)) = roots[16 k r], one copy per CTA
@@ -153,12 +158,18 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
   const bool shake = PAIR && p.stagger == 0;
   auto hs_arrive = [&]() {
     if constexpr (PAIR) {
-      if (shake) asm volatile("bar.arrive %0, %1;" ::"r"(3 + g), "n"(2 * T) : "memory");
+      if (shake) {
+        if (g == 0) asm volatile("bar.arrive 3, %0;" ::"n"(2 * T) : "memory");
+        else asm volatile("bar.arrive 4, %0;" ::"n"(2 * T) : "memory");
+      }
     }
   };
   auto hs_wait = [&]() {
     if constexpr (PAIR) {
-      if (shake) asm volatile("bar.sync %0, %1;" ::"r"(3 + (1 - g)), "n"(2 * T) : "memory");
+      if (shake) {
+        if (g == 0) asm volatile("bar.sync 4, %0;" ::"n"(2 * T) : "memory");
+        else asm volatile("bar.sync 3, %0;" ::"n"(2 * T) : "memory");
+      }
     }
   };
   if constexpr (PAIR) {
