@@ -24,7 +24,6 @@ using namespace glb;
 // shared state of the library (defined in gram_kernels.cu)
 extern std::atomic<unsigned long long> g_launches;
 extern int g_big_pair;
-extern int g_ring_pair;
 extern int g_stagger_cycles;
 extern int g_kernel_pref;            // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
 extern int g_last_family;            // family of the last spectrogram kernel launched (same numbering)
@@ -998,158 +997,10 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
 // workload, 0.829 against 0.824 ms at 75 % overlap.  With six CTAs per SM the other groups fill those stalls
 // already; the kernel is bound by pipe throughput (FP32 lanes, shared-memory wavefronts, issue), not by latency.)
 
-// ------------------------------------------------------------------------- ring kernel, two groups held in anti-phase
-// The periodogram ring kernel for N = 4096 (register twiddles, three passes), 50 / 75 % overlap, block means
-// removed, float rows: the same arithmetic and bits as gram_ring_kernel, with two differences in time.
-//  (1) The partial sums of the NEXT frame's newest block are formed at the end of a frame (the block landed by
-//      TMA during the mid pass), and ONE barrier (E) at the end of the frame both publishes them and frees the
-//      exchange buffer: four group barriers per frame instead of five, no sum / shuffle chain in front of the
-//      transform.  (On its own this changed nothing: commit 5cac14a.)
-//  (2) A CTA is TWO frame groups of 128 threads, each on its own named barrier, held half a frame apart by a
-//      handshake on two more named barriers (a group starts a frame only when the other one is past the first
-//      exchange of its current frame).  A frame is FP-heavy at both ends and exchange-heavy in the middle; groups
-//      that start together stay in step -- all in their butterflies or all in their exchanges at once -- and the
-//      FP32 and shared-memory pipes are used alternately instead of together.  On the 32-point kernel (N =
-//      16384, two groups per SM) the same handshake gave 14 %.
-template <int M> struct Ring2Geo {
-  static constexpr int T = Geo<M>::T, G = 2, THREADS = G * T;
-  static constexpr int MINB_ = 65536 / (THREADS * GLB_REG_TARGET);
-  static constexpr int MINB = MINB_ < 1 ? 1 : MINB_;
-};
-template <int M, int QSC>
-__global__ void __launch_bounds__(Ring2Geo<M>::THREADS, (Ring2Geo<M>::MINB)) gram_ring2_kernel(const KParams p) {
-  using GeoM = Geo<M>;
-  constexpr int T = GeoM::T, G = Ring2Geo<M>::G, N = GeoM::N, NW = GeoM::NW;
-  static_assert(GeoM::RT && Plan<M>::NP == 3 && T == 128 && GeoM::G == 1 && QSC >= 0 && GLB_RING_EXTRA == 0, "two-group ring kernel: N = 4096");
-  // group barrier (bar.sync g+1) and the handshake between the two groups (bar.arrive / bar.sync 3+g, 2 T threads)
-  // (barrier numbers as immediates: with the number in a register ptxas reserves all 16 barriers and the
-  // generic form of the instruction is slower)
-  auto gsync = [&](int gg) {
-    if (gg == 0) asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
-    else asm volatile("bar.sync 2, %0;" ::"n"(T) : "memory");
-  };
-  const bool shake = p.stagger == 0;     // (1: free-running groups, for A/B measurements)
-  constexpr int hop = (2 * T) << QSC, nb = kPoints >> QSC, slots = nb;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int g = threadIdx.x / T;
-  const int t = threadIdx.x % T;
-  const RingLayout L = ring_layout<M>(hop, nb, 0);
-  unsigned char *gbase = smem_raw + (size_t) g * L.group_bytes;
-  float2 *buf = reinterpret_cast<float2 *>(gbase);
-  float *ring = reinterpret_cast<float *>(gbase + L.ring_off);
-  float *red = reinterpret_cast<float *>(gbase + L.red_off);
-  float *mu = reinterpret_cast<float *>(gbase + L.mu_off);
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(gbase + L.mbar_off);
-  const long long gid = (long long) blockIdx.x * G + g;
-  const long long fb = gid * p.frames_per_group;
-  const bool group_active = fb < p.nframes;
-  const long long f_first = p.first_frame + fb;
-  const long long b0 = f_first - (nb - 1);                       // oldest block of the first frame
-  constexpr unsigned blk_bytes = (unsigned) hop * 4u;
-  unsigned phase_bits = 0;                                       // one parity bit per ring slot
-
-  TwRegs tr;
-  load_tw_regs<M>(tr, t, p.tw, p.vtab);
-  if (t == 0) {
-    for (int sl = 0; sl < slots; sl++) mbar_init(&mbar[sl], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // prologue: the nb blocks of the first frame (zeros before the stream start, fft.c:103-108) and their means
-  for (int lb = 0; lb < nb; lb++) {
-    const long long blk = b0 + lb;
-    if (group_active) {
-      if (blk < 0) {
-        float2 *z = reinterpret_cast<float2 *>(ring + (size_t) lb * hop);
-        for (int i = 0; i < (1 << QSC); i++) z[t + T * i] = make_float2(0.f, 0.f);
-      } else if (t == 0) {
-        GLB_CHECK_SRC(p, p.samples + (blk * hop - p.origin), hop);
-        mbar_expect_tx(&mbar[lb], blk_bytes);
-        tma_load_1d(ring + (size_t) lb * hop, p.samples + (blk * hop - p.origin), blk_bytes, &mbar[lb]);
-      }
-    }
-  }
-  float mu_new = 0.f;
-  for (int lb = 0; lb < nb; lb++) {
-    const long long blk = b0 + lb;
-    if (group_active && blk >= 0) {
-      mbar_wait(&mbar[lb], 0);
-      phase_bits ^= 1u << lb;
-    }
-    __syncthreads();                                             // zero fill visible to all
-    const float m = ring_block_mean<M>(ring + (size_t) lb * hop, QSC, t, red + lb * NW, p.inv_hop_mean, g);
-    mu_new = (blk < 0) ? 0.f : m;
-    if (t == 0) mu[lb] = mu_new;
-  }
-  __syncthreads();                                               // mu[] visible; stands in for barrier (E) before frame 0
-
-  int slot_new = nb - 1;
-  const int nact = group_active ? (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group) : 0;
-  float *row_ptr = p.rows + fb * p.row_stride;
-  const float *next_src = p.samples + ((f_first + 1) * (long long) hop - p.origin);
-  const bool db = p.rows_db != 0;
-  for (int it = 0; it < p.frames_per_group; ++it, row_ptr += p.row_stride, next_src += hop) {
-    const bool active = it < nact;
-    const bool next_there = it + 1 < nact;
-    const int slot_next = (slot_new + 1 == slots) ? 0 : slot_new + 1;      // tight ring: the oldest block's slot
-    // group 1: group 0 is past the first exchange of frame `it`; group 0: group 1 is past that of frame `it - 1`
-    if (shake) {
-      if (g == 1) asm volatile("bar.sync 3, %0;" ::"n"(2 * T) : "memory");
-      else if (it > 0) asm volatile("bar.sync 4, %0;" ::"n"(2 * T) : "memory");
-    }
-    // the newest block landed, and its warp sums were left in `red`, at the end of the previous iteration
-    if (it > 0) {
-      mu_new = ring_block_total<M>(0.f, red + slot_new * NW, p.inv_hop_mean);
-      if (t == 0) mu[slot_new] = mu_new;
-    }
-    float2 x[kPoints];
-    ring_fetch<M, QSC>(x, t, ring, hop, slot_next, slots, mu, mu_new, true, false, red, p.inv_hop_mean, g);
-    float2 v[kPoints];
-    apply_taper<M, true>(v, x, t, p, p.tapers);
-    pass_compute_rt<M, 0>(v, tr);
-    pass_scatter<M, 0>(v, t, buf);                                // (the buffer was freed by barrier (E))
-    gsync(g);
-    if (shake) {
-      if (g == 0) asm volatile("bar.arrive 3, %0;" ::"n"(2 * T) : "memory");
-      else asm volatile("bar.arrive 4, %0;" ::"n"(2 * T) : "memory");
-    }
-    if (next_there && t == 0) {
-      // every thread of the group has its samples in registers: the oldest block's slot takes the next block
-      GLB_CHECK_SRC(p, next_src, hop);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&mbar[slot_next], blk_bytes);
-      tma_load_1d(ring + (size_t) slot_next * hop, next_src, blk_bytes, &mbar[slot_next]);
-    }
-    pass_load<M>(v, t, buf);
-    pass_compute_rt<M, 1>(v, tr);
-    gsync(g);                                             // every thread has read before anyone overwrites
-    pass_scatter<M, 1>(v, t, buf);
-    gsync(g);
-    float yv[17];
-    yv[16] = 1.f;                                                 // only thread 0 has a 17th bin
-    auto sink = [&](int slot, float2 a, bool) { yv[slot] = norm2(a); };
-    last_pass_rt<M>(v, t, buf, p.tw, tr);
-    if (t < 32) emit_bins_rt<M, true>(v, t, tr, sink);            // warp-uniform: only warp 0 pays for thread 0's re-ordering
-    else emit_bins_rt<M, false>(v, t, tr, sink);
-    if (db) {
-#pragma unroll
-      for (int slot = 0; slot < 17; slot++) yv[slot] = 10.f * log10f(yv[slot]);
-    }
-    if (active) {
-      GLB_CHECK_ROW(p, row_ptr);
-      GLB_CHECK_ROW(p, row_ptr + M);
-      store_row<M>(row_ptr, t, yv);
-    }
-    if (next_there) {
-      mbar_wait(&mbar[slot_next], (phase_bits >> slot_next) & 1u);
-      ring_block_partial<M>(ring + (size_t) slot_next * hop, QSC, t, red + slot_next * NW);
-    }
-    phase_bits ^= (next_there ? 1u : 0u) << slot_next;
-    gsync(g);                                             // (E) last-pass loads done, partial sums visible
-    slot_new = slot_next;
-  }
-  if (shake && g == 0 && p.frames_per_group > 0) asm volatile("bar.sync 4, %0;" ::"n"(2 * T) : "memory");   // group 1's last arrival
-}
+// (Also tried and removed, commit e1c816e: the same kernel as TWO frame groups of 128 threads per CTA, each on its own named
+// barrier, held half a frame apart by the handshake that gave the 32-point kernel 14 % at N = 16384 (gram_big.cu).
+// Bit-identical rows; 0.479 ms with the handshake, 0.488 ms free-running, against 0.423 ms for six independent
+// 128-thread CTAs per SM: six groups drift apart on their own, and named 128-thread barriers cost more than they win.)
 
 // mid passes of the pair kernel (both frames through each pass, float4 exchange)
 template <int M, int P> struct PairMidPasses {
@@ -1635,35 +1486,6 @@ inline int launch_gram_m(const KParams &kp, bool multi, int groups_hint, cudaStr
                                      : (lev ? gram_ring_kernel<M, false, 2, true> : gram_ring_kernel<M, false, 2, false>);
         else rk = multi ? (lev ? gram_ring_kernel<M, true, -1, true> : gram_ring_kernel<M, true, -1, false>)
                         : (lev ? gram_ring_kernel<M, false, -1, true> : gram_ring_kernel<M, false, -1, false>);
-        if constexpr (M == 2048 && GLB_RING_EXTRA == 0) {
-          // N = 4096 periodogram, block means removed, float rows: two groups per CTA held in anti-phase
-          if (g_ring_pair && !multi && !lev && kp.fused_mean && (qs == 2 || qs == 3)) {
-            void (*r2)(const KParams) = qs == 3 ? gram_ring2_kernel<M, 3> : gram_ring2_kernel<M, 2>;
-            const size_t smem2 = (size_t) Ring2Geo<M>::G * L.group_bytes;
-            static thread_local int occ2_cache[5][64];
-            int &occ2 = occ2_cache[qs][dev & 63];
-            if (occ2 == 0) {
-              CU(cudaFuncSetAttribute(r2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-              CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, r2, Ring2Geo<M>::THREADS, smem2));
-              if (occ2 < 1) occ2 = -1;
-            }
-            if (occ2 >= 1) {
-              long long groups = groups_hint > 0 ? groups_hint : (long long) sms * occ2 * Ring2Geo<M>::G;
-              if (groups > kp.nframes) groups = kp.nframes;
-              if (groups < 1) groups = 1;
-              KParams k = kp;
-              k.qs = qs;
-              k.frames_per_group = (int) ((kp.nframes + groups - 1) / groups);
-              const long long used = (kp.nframes + k.frames_per_group - 1) / k.frames_per_group;
-              const int ctas = (int) ((used + Ring2Geo<M>::G - 1) / Ring2Geo<M>::G);
-              r2<<<ctas, Ring2Geo<M>::THREADS, smem2, st>>>(k);
-              CU(cudaGetLastError());
-              g_launches++;
-              g_last_family = 2;
-              return GLB_OK;
-            }
-          }
-        }
         static thread_local int occ_ring[2][2][5][64];
         int &occ = occ_ring[lev ? 1 : 0][multi ? 1 : 0][qs][dev & 63];
         if (occ == 0) {

@@ -23,7 +23,6 @@
 // ------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-int g_ring_pair = 1;                 // 0: never gram_ring2_kernel (experiments)
 int g_stagger_cycles = 0;             // experiments: start offset between frame groups sharing an SM
 int g_kernel_pref = 0;               // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
 int g_last_family = 0;
@@ -35,11 +34,9 @@ extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load
 extern "C" void glb_force_generic_kernel(int on) { g_force_generic = on; }
 extern "C" void glb_set_stagger_cycles(int cycles) { g_stagger_cycles = cycles; }
 extern "C" void glb_set_kernel_preference(int pref) {
-  // 6 / 7 = automatic choice, but the 32-point kernel / the ring kernel never pairs two frame groups in one CTA (A/B
-  // measurements)
+  // 6 = automatic choice, but the 32-point kernel never pairs two frame groups in one CTA (A/B measurements)
   g_big_pair = pref != 6;
-  g_ring_pair = pref != 7;
-  g_kernel_pref = (pref == 6 || pref == 7) ? 0 : pref;
+  g_kernel_pref = pref == 6 ? 0 : pref;
 }
 extern "C" int glb_last_kernel_family(void) { return g_last_family; }
 

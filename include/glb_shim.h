@@ -114,8 +114,7 @@ int glb_gram_fused_avg_ok(int n, int hop, int depth, int band);
 void glb_force_generic_kernel(int on);
 /* 0 = automatic choice, 1 = general kernel, 2 = TMA ring kernel, 3 = warp-per-frame kernel, 4 = two frames per
  * thread, 5 = 32-points-per-thread kernel (N = 16384 / 32768; what the automatic choice takes there),
- * 6 / 7 = automatic, but the 32-point kernel / the ring kernel never pairs two frame groups per CTA (A/B
- * measurements)
+ * 6 = automatic, but the 32-point kernel never pairs two frame groups per CTA (A/B measurements)
  * (a preference: launches a family cannot serve fall through to the next one) */
 void glb_set_kernel_preference(int pref);
 /* experiments: start offset (SM clock cycles) between the frame groups that share an SM; 0 = none */

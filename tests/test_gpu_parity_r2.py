@@ -431,42 +431,6 @@ def test_big_frame_kernel_vs_oracle_and_16_point_families(gpu_api):
     assert np.array_equal(one["psd"], many["psd"])
 
 
-def test_ring_kernel_two_groups_in_antiphase_is_bit_identical(gpu_api):
-    """N = 4096 periodograms with block means removed at 50 / 75 % overlap take gram_ring2_kernel (two frame groups per
-    CTA held half a frame apart by a named-barrier handshake, the newest block's sums formed at the end of the
-    previous frame); kernel preference 7 keeps gram_ring_kernel.  Same arithmetic on the same bits: identical rows,
-    also dB rows, ragged frame counts, frame counts below the number of resident groups (idle groups still shake
-    hands), sub-ranges staged at an offset (zero history only at the stream start) and the free-running variant."""
-    x = synth.qrss_stream(4096 * 700 + 1234, fs=FS, seed=85, dot_s=0.2)
-    try:
-        for ov in (0.5, 0.75):
-            for wt, db in ((0, False), (7, True), (5, False)):
-                kw = dict(n=4096, window_type=wt, overlap=ov, sub_mean=True, scale_db=db)
-                gpu_api.set_kernel_preference(0)
-                p0 = gpu_api.GramPlan(**kw)
-                a = p0.run(x)["psd"]
-                assert gpu_api.last_kernel_family().startswith("gram_ring_kernel")
-                gpu_api.set_kernel_preference(7)
-                b = gpu_api.GramPlan(**kw).run(x)["psd"]
-                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (ov, wt, int((a != b).sum()))
-                gpu_api.set_kernel_preference(0)
-                gpu_api.set_stagger_cycles(1)
-                c = gpu_api.GramPlan(**kw).run(x)["psd"]
-                gpu_api.set_stagger_cycles(0)
-                assert np.array_equal(a.view(np.uint32), c.view(np.uint32)), (ov, wt)
-                for first, cnt in ((0, 1), (0, 2), (0, 5), (3, 2), (17, 333), (a.shape[0] - 9, 9), (1, 1000)):
-                    lo, hi = p0.required_span(first, cnt)
-                    lo = max(lo, 0)
-                    seg = np.ascontiguousarray(x[lo:hi])
-                    s0 = p0.run(seg, origin=lo, first_frame=first, nframes=cnt)["psd"]
-                    assert np.array_equal(s0.view(np.uint32), a[first:first + cnt].view(np.uint32)), (ov, first, cnt)
-        got = gpu_api.GramPlan(n=4096, window_type=0, overlap=0.5, sub_mean=True).run(x[: 4096 * 40])["psd"]
-        assert_psd_close(got, O.periodogram(x[: 4096 * 40], 4096, 0, 0.5, True), "two-group ring kernel vs oracle")
-    finally:
-        gpu_api.set_kernel_preference(0)
-        gpu_api.set_stagger_cycles(0)
-
-
 def test_big_frame_pair_variant_is_bit_identical(gpu_api):
     """N = 16384 periodograms take the two-groups-per-CTA variant of gram_big_kernel (half taper in shared
     memory, second half mirrored) by default; kernel preference 6 keeps one group per CTA with the full taper
