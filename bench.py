@@ -259,7 +259,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configurations)")
     ap.add_argument("--seconds", type=int, default=0, help="override the seconds of signal per rank")
-    ap.add_argument("--stagger", type=int, default=0, help="experiment: start offset in cycles between frame groups sharing an SM")
     ap.add_argument("--kernel-pref", type=int, default=0, help="experiment: 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread")
     ap.add_argument("--no-submean", action="store_true", help="experiment: opt.autoscale = 0 (no block-mean removal)")
     args = ap.parse_args()
@@ -350,8 +349,6 @@ def main():
     x_host[:] = synth.tiled_stream(nsamp, fs=FS, block_s=20.0, seed=0x5EED + rank)
     if args.kernel_pref:
         api.set_kernel_preference(args.kernel_pref)
-    if args.stagger:
-        api.set_stagger_cycles(args.stagger)
     plan = api.GramPlan(device=local_rank, **kw)
     plan.stage(x_host, origin=lo)
     plan.sync()

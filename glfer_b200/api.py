@@ -156,8 +156,6 @@ def lib() -> C.CDLL:
         l.glb_force_generic_kernel.restype = None
         l.glb_set_kernel_preference.argtypes = [C.c_int]
         l.glb_set_kernel_preference.restype = None
-        l.glb_set_stagger_cycles.argtypes = [C.c_int]
-        l.glb_set_stagger_cycles.restype = None
         _lib = l
     return _lib
 
@@ -453,11 +451,6 @@ def palette(p: int) -> np.ndarray:
 def force_generic_kernel(on: bool) -> None:
     """testing aid: run the general kernel where the TMA ring kernel would be chosen"""
     lib().glb_force_generic_kernel(int(on))
-
-
-def set_stagger_cycles(cycles: int) -> None:
-    """Experiments: start offset between the frame groups that share an SM."""
-    lib().glb_set_stagger_cycles(cycles)
 
 
 def set_kernel_preference(pref: int) -> None:

@@ -24,7 +24,6 @@ using namespace glb;
 // shared state of the library (defined in gram_kernels.cu)
 extern std::atomic<unsigned long long> g_launches;
 extern int g_big_pair;
-extern int g_stagger_cycles;
 extern int g_kernel_pref;            // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
 extern int g_last_family;            // family of the last spectrogram kernel launched (same numbering)
 extern "C" void glb_set_error(const char *msg);
@@ -49,7 +48,6 @@ struct KParams {
   const float *tapers;
   int ntapers;
   int taper_sym;              // 1: periodogram taper with w[i] == w[N - 1 - i] bit for bit
-  int stagger;                // cycles between the start of the frame groups that share an SM (0: none)
   const float *means;         // pre-computed block means (general geometry), or nullptr
   long long means_first_block;
   int fused_mean;             // 1: block means are computed inside the kernel (regular geometry)
@@ -719,21 +717,6 @@ template <int M, bool MULTI> struct RingGeo {
 // one each frame -- forms the averaged band row, the return value, the *peakbin candidate and the variance
 // of the frame before, right after barrier (A) has made that frame's history entries visible.  The
 // arithmetic is avg_frame_warp() of the stand-alone kernel: identical bits.  Band-only output rows.
-// arrival rank of this CTA on its SM (a counter per SM that only ever grows), times `cycles` of delay.
-// `scratch`: one word of the CTA's dynamic shared memory (the kernel asks for all 227 KB: no static allocation).
-__device__ int g_sm_arrivals[1024];
-__device__ __forceinline__ void stagger_start(int cycles, int *scratch) {
-  if (threadIdx.x == 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    *scratch = atomicAdd(&g_sm_arrivals[smid & 1023], 1);
-  }
-  __syncthreads();
-  const long long wait = (long long) (*scratch % (cycles >> 20 ? cycles >> 20 : 8)) * (cycles & 0xfffff);   // (experiments: modulus in bits 20+)
-  __syncthreads();
-  const long long t0 = clock64();
-  while (clock64() - t0 < wait) { }
-}
 template <int M, bool MULTI, int QSC, bool LEV, bool AVG = false>
 __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gram_ring_kernel(const KParams p) {
   using GeoM = Geo<M>;
@@ -813,9 +796,8 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   }
   group_sync<M>(g);                                               // zero fill and mu[] visible
 
-  // CTAs that share an SM start together and, taking the same time per frame, stay in step: all in their
-  // butterflies or all in their exchanges at once.  A start offset per arrival rank on the SM spreads them.
-  if (p.stagger > 0) stagger_start(p.stagger, reinterpret_cast<int *>(smem_raw + L.mu_off) + 17);   // (group 0's mu[17]: never a ring slot)
+  // (CTAs that share an SM start together; a start offset per arrival rank on the SM -- rank x 400 ... 4 371 cycles,
+  // or two / three clusters half / a third of a frame apart -- changed nothing here: 0.424 ... 0.430 ms.)
   int slot_new = nb - 1;                                         // slot of the newest block of frame `it`
   // loop state carried incrementally (no 64-bit multiplies per frame): frames of this group that
   // exist, the row to write and the block the next bulk copy reads

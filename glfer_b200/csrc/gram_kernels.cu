@@ -23,7 +23,6 @@
 // ------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-int g_stagger_cycles = 0;             // experiments: start offset between frame groups sharing an SM
 int g_kernel_pref = 0;               // 0 auto, 1 general, 2 ring, 3 warp-per-frame, 4 two frames per thread
 int g_last_family = 0;
 static int g_force_generic = 0;     // tests: run the general kernel where the ring kernel would be chosen
@@ -32,7 +31,6 @@ extern "C" const char *glb_last_error(void) { return g_err; }
 extern "C" void glb_set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
 extern "C" unsigned long long glb_kernel_launches(void) { return g_launches.load(); }
 extern "C" void glb_force_generic_kernel(int on) { g_force_generic = on; }
-extern "C" void glb_set_stagger_cycles(int cycles) { g_stagger_cycles = cycles; }
 extern "C" void glb_set_kernel_preference(int pref) {
   // 6 = automatic choice, but the 32-point kernel never pairs two frame groups in one CTA (A/B measurements)
   g_big_pair = pref != 6;
@@ -224,7 +222,6 @@ extern "C" int glb_launch_gram(const glb_gram_args *a, void *stream) {
   k.tapers = a->tapers;
   k.ntapers = a->ntapers;
   k.taper_sym = a->ntapers == 1 && a->taper_symmetric;
-  k.stagger = g_stagger_cycles;
   k.means = a->block_means;
   k.means_first_block = a->means_first_block;
   k.fused_mean = a->fused_mean;

@@ -117,8 +117,6 @@ void glb_force_generic_kernel(int on);
  * 6 = automatic, but the 32-point kernel never pairs two frame groups per CTA (A/B measurements)
  * (a preference: launches a family cannot serve fall through to the next one) */
 void glb_set_kernel_preference(int pref);
-/* experiments: start offset (SM clock cycles) between the frame groups that share an SM; 0 = none */
-void glb_set_stagger_cycles(int cycles);
 
 /* mean of every complete hop block: means[b - first_block] = mean(stream[b*hop, (b+1)*hop)) */
 int glb_launch_block_means(const float *samples, long long origin, long long count, int hop,
