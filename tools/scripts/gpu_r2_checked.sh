@@ -1,5 +1,5 @@
 set -x
-O=gpurun_out/r2_checked2
+O=gpurun_out/r2_checked
 mkdir -p $O
 export GLFER_B200_LIB=$PWD/glfer_b200/libglfer_b200_checked.so
 timeout 600 python tools/sanitize_driver.py > $O/checked_driver.log 2>&1; echo "checked driver rc=$?" >> $O/checked_driver.log
