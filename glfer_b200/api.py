@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
         l.glfer_gram_shard_range.restype = None
         l.glfer_wav_load.argtypes = [C.c_char_p, C.POINTER(Wav)]
         l.glfer_wav_free.argtypes = [C.POINTER(Wav)]
+        l.glfer_wav_select_channel.argtypes = [C.POINTER(Wav), C.c_int]
         l.glfer_wav_num_frames.argtypes = [C.c_void_p, C.POINTER(Wav)]
         l.glfer_wav_num_frames.restype = C.c_longlong
         l.glfer_gram_run_wav.argtypes = [C.c_void_p, C.POINTER(Wav)] + [C.c_void_p] * 5
@@ -365,10 +366,14 @@ class GramPlan:
                   _ptr(levels), _ptr(rgb), _ptr(rng)))
         return dict(levels=levels, rgb=rgb, range=rng, agc_state=state)
 
-    def run_wav(self, path: str, want_psd: bool = True):
+    def run_wav(self, path: str, want_psd: bool = True, channel: int | None = None):
+        """glfer_gram_run_wav; channel: keep one channel of a multi-channel file (an extension -- the reference, and
+        the default here, feed the interleaved samples to the estimator as they are)."""
         wav = Wav()
         _check(lib().glfer_wav_load(path.encode(), C.byref(wav)))
         try:
+            if channel is not None:
+                _check(lib().glfer_wav_select_channel(C.byref(wav), channel))
             nframes = int(lib().glfer_wav_num_frames(self._h, C.byref(wav)))
             psd, avg, ret, pk, var = self._outs(nframes, want_psd)
             _check(lib().glfer_gram_run_wav(self._h, C.byref(wav), _ptr(psd), _ptr(avg), _ptr(ret), _ptr(pk), _ptr(var)))

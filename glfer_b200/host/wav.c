@@ -47,6 +47,27 @@ int glfer_wav_load(const char *path, glfer_wav *wav)
   return 0;
 }
 
+/* An extension the reference lacks (it feeds the interleaved samples of a stereo file to the estimator as if they
+   were one channel): keep ONE channel of the loaded file, in place.  channel in [0, channels); a trailing partial
+   sample frame is dropped.  Afterwards the file looks mono to glfer_gram_run_wav(). */
+int glfer_wav_select_channel(glfer_wav *wav, int channel)
+{
+  if (!wav || !wav->data) return wfail("no WAV data");
+  if (wav->channels < 1 || channel < 0 || channel >= wav->channels) return wfail("no such channel in the WAV file");
+  if (wav->channels == 1) return 0;
+  const long long nfr = wav->nsamples / wav->channels;
+  if (wav->bits == 16) {
+    short *b = wav->data;
+    for (long long i = 0; i < nfr; i++) b[i] = b[i * wav->channels + channel];
+  } else {
+    unsigned char *b = wav->data;
+    for (long long i = 0; i < nfr; i++) b[i] = b[i * wav->channels + channel];
+  }
+  wav->nsamples = nfr;
+  wav->channels = 1;
+  return 0;
+}
+
 void glfer_wav_free(glfer_wav *wav)
 {
   free(wav->data);

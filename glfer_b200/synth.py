@@ -75,12 +75,13 @@ def tiled_stream(nsamples: int, fs: int = 48000, block_s: float = 60.0, seed: in
     return np.tile(blk, reps)[:nsamples]
 
 
-def write_wav16(path: str, pcm: np.ndarray, fs: int) -> None:
-    """Canonical 44-byte-header mono 16-bit PCM WAV (the layout wav_fmt.h:34-52 describes)."""
+def write_wav16(path: str, pcm: np.ndarray, fs: int, channels: int = 1) -> None:
+    """Canonical 44-byte-header 16-bit PCM WAV (the layout wav_fmt.h:34-52 describes); pcm is the interleaved
+    sample stream ([frames][channels] flattened)."""
     import struct
     data = pcm.astype("<i2").tobytes()
     with open(path, "wb") as fh:
         fh.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE")
-        fh.write(b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, fs, fs * 2, 2, 16))
+        fh.write(b"fmt " + struct.pack("<IHHIIHH", 16, 1, channels, fs, fs * 2 * channels, 2 * channels, 16))
         fh.write(b"data" + struct.pack("<I", len(data)))
         fh.write(data)

@@ -199,6 +199,8 @@ typedef struct {
   void *data;           /* raw PCM as read */
 } glfer_wav;
 int glfer_wav_load(const char *path, glfer_wav *wav);
+/* extension (the reference treats a stereo file's interleaved samples as one channel): keep one channel, in place */
+int glfer_wav_select_channel(glfer_wav *wav, int channel);
 void glfer_wav_free(glfer_wav *wav);
 /* spectrogram of a WAV exactly as `glfer -f file` would see it block by block, including
  * the stale tail of a short final read (wav_fmt.c:102-119).  Returns frames via *nframes;

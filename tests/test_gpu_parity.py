@@ -504,6 +504,17 @@ def test_wav_source_with_stale_tail(gpu_api, tmp_path):
     p0 = gpu_api.GramPlan(n=1024, window_type=0, overlap=0.5, sub_mean=False)
     strm0, _, _ = O.read_wav_blocks(path, 512)
     assert_psd_close(p0.run_wav(path)["psd"], O.periodogram(strm0, 1024, 0, 0.5, False), "WAV no mean")
+    # a stereo file: as the reference (interleaved samples taken as one stream), and one channel of it (extension)
+    left = pcm[: len(pcm) // 2 * 2 // 2]
+    right = np.roll(left, 137)
+    st = np.stack([left, right], axis=1).reshape(-1)
+    spath = str(tmp_path / "stereo.wav")
+    synth.write_wav16(spath, st, 8000, channels=2)
+    strm_i, _, _ = O.read_wav_blocks(spath, 512)
+    assert_psd_close(p0.run_wav(spath)["psd"], O.periodogram(strm_i, 1024, 0, 0.5, False), "stereo WAV, interleaved as the reference")
+    mono_r = str(tmp_path / "right.wav")
+    synth.write_wav16(mono_r, right, 8000)
+    assert np.array_equal(p0.run_wav(spath, channel=1)["psd"], p0.run_wav(mono_r)["psd"])
 
 
 def test_headless_harness_per_call_and_batch(gpu_api, tmp_path):

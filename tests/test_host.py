@@ -174,3 +174,30 @@ def test_db_threshold_tables_reproduce_host_libm(api):
     xd = np.exp(rng.uniform(-103, 88, 20000))
     got = np.searchsorted(td, xd, side="right") - 1 - 450
     assert np.array_equal(got, np.trunc(10.0 * np.log10(xd)).astype(np.int64))
+
+
+def test_wav_channel_selection(api, tmp_path):
+    """glfer_wav_select_channel (an extension: the reference feeds a stereo file's interleaved samples to the
+    estimator as one channel): the kept channel, the sample count, a partial trailing frame dropped, errors."""
+    import ctypes as C
+    from glfer_b200 import synth
+    lib = api.lib()
+    rng = np.random.default_rng(5)
+    for channels, nfr, extra in ((2, 1000, 0), (3, 777, 2), (1, 500, 0)):
+        pcm = rng.integers(-30000, 30000, nfr * channels + extra).astype(np.int16)
+        path = str(tmp_path / f"c{channels}.wav")
+        synth.write_wav16(path, pcm, 8000, channels=channels)
+        for ch in range(channels):
+            wav = api.Wav()
+            assert lib.glfer_wav_load(path.encode(), C.byref(wav)) == 0
+            assert wav.channels == channels and wav.nsamples == len(pcm)
+            assert lib.glfer_wav_select_channel(C.byref(wav), ch) == 0
+            assert wav.channels == 1 and wav.nsamples == nfr
+            got = np.ctypeslib.as_array(C.cast(wav.data, C.POINTER(C.c_short)), shape=(nfr,)).copy()
+            assert np.array_equal(got, pcm[: nfr * channels].reshape(nfr, channels)[:, ch])
+            lib.glfer_wav_free(C.byref(wav))
+        wav = api.Wav()
+        assert lib.glfer_wav_load(path.encode(), C.byref(wav)) == 0
+        assert lib.glfer_wav_select_channel(C.byref(wav), channels) != 0
+        assert lib.glfer_wav_select_channel(C.byref(wav), -1) != 0
+        lib.glfer_wav_free(C.byref(wav))
