@@ -643,10 +643,41 @@ def per_call_leg(api):
         if R.available("f32"):
             dt, nfr = R.time_periodogram(blocks.reshape(-1), n, 0, 0.5, True)
             entry["reference_cpu_us_per_call_one_core"] = dt / nfr * 1e6
+        # the k-block entry of the same interface: 64 hop blocks per call, same sequence semantics
+        p = api.FftParams()
+        p.n, p.window_type, p.overlap, p.a, p.limiter = n, 0, 0.5, 0.0, 0
+        lib.glfer_b200_set_first_buffer(1)
+        lib.fft_init(C.byref(p))
+        k = 64
+        rows = np.empty((k, n // 2 + 1), dtype=np.float32)
+        chunk = np.empty((k, hop), dtype=np.float32)
+        for i in range(4):
+            if i == 1:
+                t0 = time.perf_counter()
+            chunk[:] = blocks[i * k:(i + 1) * k]
+            lib.fft_do_batch(chunk.ctypes.data, k, rows.ctypes.data, C.byref(p))
+            lib.glfer_b200_set_first_buffer(0)
+        entry["gpu_us_per_block_fft_do_batch_64"] = (time.perf_counter() - t0) / (3 * k) * 1e6
+        lib.fft_close(C.byref(p))
+        # mtm_do, K' = 8 tapers (NW = 4): one call per hop block
+        m = api.MtmParams()
+        m.fft.n, m.fft.window_type, m.fft.overlap = n, 5, 0.5
+        m.w, m.kmax = 4.0, 7
+        lib.glfer_b200_set_first_buffer(1)
+        lib.mtm_init(C.byref(m))
+        for i in range(150):
+            if i == 50:
+                t0 = time.perf_counter()
+            blk[:] = blocks[i]
+            lib.mtm_do(blk.ctypes.data, psd.ctypes.data, None, C.byref(m))
+            lib.glfer_b200_set_first_buffer(0)
+        entry["gpu_us_per_mtm_do_8_tapers"] = (time.perf_counter() - t0) / 100 * 1e6
+        lib.mtm_close(C.byref(m))
+        if R.available("f32"):
+            dt, nfr = R.time_mtm(blocks[:60].reshape(-1), n, 0.5, 4.0, 7, True)
+            entry["reference_cpu_us_per_mtm_do_one_core"] = dt / nfr * 1e6
         res[f"n{n}"] = entry
-    # batch-of-k streaming entry (fft_do_batch): the same sequence semantics, k hop blocks per call
-    if hasattr(lib, "fft_do_batch"):
-        res["note"] = "fft_do_batch available: see INTEGRATION.md"
+    res["note"] = "one frame per call is launch-latency bound; fft_do_batch / mtm_do_batch take k hop blocks per call (INTEGRATION.md)"
     return res
 
 
