@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
   const bool sub = p.fused_mean != 0;
   const bool db = p.rows_db != 0;
   const int ntap = MULTI ? p.ntapers : 1;
+  // (Carrying only a frame counter and forming these 64-bit values where they are used removes most of the PAIR
+  // variant's spills -- 16 -> 4 bytes -- and measured 0.8 % slower.)
   float *row_ptr = p.rows + fb * p.row_stride;                   // (never dereferenced when p.rows is null)
   unsigned char *lev_ptr = p.levels + fb * p.lev_stride;
   long long s0 = (p.first_frame + fb) * (long long) HOP - (N - HOP);   // stream index of the frame's first sample

@@ -1,9 +1,10 @@
 set -x
 O=gpurun_out/r2_misc
 mkdir -p $O
-timeout 600 python -m pytest tests -m gpu -q -k "wav or headless" > $O/pytest.log 2>&1; tail -3 $O/pytest.log
-python bench.py --no-configs --no-e2e --steps 50 > $O/b.json 2> $O/b.err; tail -3 $O/b.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2_misc/b.json')); print(json.dumps(d['per_call'], indent=1))
+for lib in "" _old "" _old "" _old; do
+  GLFER_B200_LIB=$PWD/glfer_b200/libglfer_b200$lib.so python bench.py --workload c4 --steps 40 --warmup 5 --no-configs --no-e2e > $O/c4$lib.json 2> $O/c4$lib.err
+  python - $O/c4$lib.json "c4 lib$lib" <<'PY'
+import json,sys
+d=json.load(open(sys.argv[1])); r=d["roofline"]; print("AB", sys.argv[2], r["kernel_ms"], r["frac"])
 PY
+done
