@@ -30,8 +30,18 @@ template <int M> struct BigGeo {
 #ifndef GLB_BIG_TW2
 #define GLB_BIG_TW2 1
 #endif
-  static __host__ __device__ constexpr bool tw2(bool multi) { return GLB_BIG_TW2 && BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + TW2_BYTES <= (size_t) 227 * 1024 / MINB - 1024; }
-  static __host__ __device__ constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + (multi ? ACC_BYTES : 0) + (tw2(multi) ? TW2_BYTES : 0); }
+  // N = 32768 multitaper (one 512-thread CTA per SM): the row being summed lives in TENSOR MEMORY, not in shared
+  // memory -- 33 words per thread written and read back with tcgen05.st / tcgen05.ld (32x32b: a thread owns a
+  // lane, its words are columns) -- which takes 66 accesses per thread and taper off the shared-memory pipe and
+  // frees the 68 KB that the last-pass table (61 KB) needs
+#ifndef GLB_BIG_TMEM_ACC
+#define GLB_BIG_TMEM_ACC 1
+#endif
+  static constexpr bool TACC = GLB_BIG_TMEM_ACC && (T == 512);
+  static constexpr int TACC_COLS = 256;           // 4 column groups (warp / 4) of 40 columns, a power of two allocated
+  static __host__ __device__ constexpr size_t acc_bytes(bool multi) { return (multi && !TACC) ? ACC_BYTES : 0; }
+  static __host__ __device__ constexpr bool tw2(bool multi) { return GLB_BIG_TW2 && BUF_BYTES + TW_BYTES + RED_BYTES + 16 + acc_bytes(multi) + TW2_BYTES <= (size_t) 227 * 1024 / MINB - 1024; }
+  static __host__ __device__ constexpr size_t smem(bool multi) { return BUF_BYTES + TW_BYTES + RED_BYTES + 16 + acc_bytes(multi) + (tw2(multi) ? TW2_BYTES : 0); }
   // PAIR: one CTA of 2 T threads = two frame groups (own exchange buffer, reduction scratch and mbarrier each,
   // own named barrier) that share the twiddle tables and ONE copy of the first half of the taper in shared memory
   static constexpr size_t GROUP_BYTES = BUF_BYTES + RED_BYTES + 16;
@@ -59,6 +69,29 @@ template <int NW> __device__ __forceinline__ float big_sum_warps(const float *r)
     for (int i = 0; i < w; i++) a[i] += a[i + w];
   }
   return a[0];
+}
+
+// tensor memory as per-thread scratch: 16 words of this thread's lane from / to consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const float *v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+                 "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float *v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                 "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t addr, float v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t addr) {
+  float v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 // MULTI: Thomson multitaper (mtm_do, mtm.c:189-220): the frame goes through the transform once per taper -- its
@@ -89,7 +122,8 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(grp + G::BUF_BYTES + (PAIR ? 0 : G::TW_BYTES) + G::RED_BYTES);
   float *acc = reinterpret_cast<float *>(smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16) + threadIdx.x;   // [slot][T]
   constexpr bool TW2 = PAIR || G::tw2(MULTI);
-  float2 *tw2 = reinterpret_cast<float2 *>(PAIR ? shr + G::TW_BYTES : smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16 + (MULTI ? G::ACC_BYTES : 0));
+  float2 *tw2 = reinterpret_cast<float2 *>(PAIR ? shr + G::TW_BYTES : smem_raw + G::BUF_BYTES + G::TW_BYTES + G::RED_BYTES + 16 + G::acc_bytes(MULTI));
+  constexpr bool TACC = MULTI && G::TACC;           // the row being summed over the tapers lives in tensor memory
   const float2 *htap = reinterpret_cast<const float2 *>(shr + G::TW_BYTES + G::TW2_BYTES);
   // (barrier numbers as immediates: with the number in a register ptxas reserves all 16 barriers)
   auto gsync = [&]() {
@@ -114,7 +148,22 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
     const float2 *src = reinterpret_cast<const float2 *>(p.tapers);
     for (int i = threadIdx.x; i < M / 2; i += 2 * T) ht[i] = src[i];
   }
+  uint32_t tacc = 0;                                // this thread's first word in tensor memory: (lane << 16) | column
+  uint32_t *tslot = reinterpret_cast<uint32_t *>(mbar + 1);          // (the second half of the mbarrier's 16 bytes)
+  if constexpr (TACC) {
+    if (threadIdx.x < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t) __cvta_generic_to_shared(tslot)), "n"(G::TACC_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  if constexpr (TACC) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // warp w reaches lanes 32 (w mod 4) .. + 31 (32x32b shape); the four warps that share a lane quarter take 40 columns each
+    const int w = threadIdx.x >> 5;
+    tacc = *tslot + ((uint32_t) ((w & 3) * 32) << 16) + (uint32_t) ((w >> 2) * 40);
+  }
 
   const long long fb = (long long) (blockIdx.x * (PAIR ? 2 : 1) + g) * p.frames_per_group;
   const int nact = (int) ((p.nframes - fb < p.frames_per_group) ? p.nframes - fb : p.frames_per_group);
@@ -278,14 +327,33 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
     else big_emit<M, false>(v, t, L, sink);
     if constexpr (MULTI) {
       // sum over the tapers in this thread's column of the shared-memory row (own entries only: no hazard)
-      if (j > 0) {
+      if constexpr (TACC) {
+        if (j > 0) {
+          float a[33];
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");     // the previous taper's stores
+          tmem_ld16(tacc, a);
+          tmem_ld16(tacc + 16, a + 16);
+          a[32] = tmem_ld1(tacc + 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int sl = 0; sl < 33; sl++) yv[sl] += acc[sl * T];
-      }
-      if (j + 1 < ntap) {
+          for (int sl = 0; sl < 33; sl++) yv[sl] += a[sl];
+        }
+        if (j + 1 < ntap) {
+          tmem_st16(tacc, yv);
+          tmem_st16(tacc + 16, yv + 16);
+          tmem_st1(tacc + 32, yv[32]);
+          continue;
+        }
+      } else {
+        if (j > 0) {
 #pragma unroll
-        for (int sl = 0; sl < 33; sl++) acc[sl * T] = yv[sl];
-        continue;
+          for (int sl = 0; sl < 33; sl++) yv[sl] += acc[sl * T];
+        }
+        if (j + 1 < ntap) {
+#pragma unroll
+          for (int sl = 0; sl < 33; sl++) acc[sl * T] = yv[sl];
+          continue;
+        }
       }
     }
     // the row leaves the registers: slot 2 rp is bin k, slot 2 rp + 1 is bin M - k, k = t + rp 2T (thread 0:
@@ -318,6 +386,12 @@ __global__ void __launch_bounds__(Big<M>::T * (PAIR ? 2 : 1), PAIR ? 1 : BigGeo<
    }
   }
   if (g == 0 && (PAIR ? p.frames_per_group : nact) > 0) hs_wait();   // (PAIR: group 1's last arrival)
+  if constexpr (TACC) {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tslot), "n"(G::TACC_COLS) : "memory");
+  }
 }
 
 template <int M, int NBLK, bool MULTI, bool LEV, bool PAIR = false>
