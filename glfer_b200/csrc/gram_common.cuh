@@ -972,6 +972,12 @@ __global__ void __launch_bounds__(Geo<M>::THREADS, (RingGeo<M, MULTI>::MINB)) gr
   }
 }
 
+// (Tried and removed: the periodogram's taper values in TENSOR MEMORY -- 32 words per thread written once with
+// tcgen05.st and read back every frame with tcgen05.ld, to take 16 of a frame's 96 L1 / shared-memory accesses per
+// thread off the busiest pipe.  0.5435 against 0.4229 ms on the metric workload, 0.489 against 0.387 ms at N = 1024:
+// 16 KB per frame through tcgen05.ld cost ~400 cycles per frame and SM, i.e. tensor memory delivers ~40 bytes per
+// clock to the register file in the 32x32b shape, a third of shared memory.  It pays where the volume is small and
+// the shared memory it frees is worth more: the multitaper row of gram_big.cu.)
 // (Tried in round 2 and removed again, commit 5cac14a: a ring kernel that forms the sums of the NEXT frame's newest
 // block at the end of a frame, behind the row stores, so that one barrier at the end of the frame both publishes
 // them and frees the exchange buffer -- four block barriers per frame instead of five and no sum / shuffle chain

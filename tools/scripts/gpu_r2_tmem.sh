@@ -1,11 +1,13 @@
 set -x
 O=gpurun_out/r2_tmem
 mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -q -x -k "big or multitaper or mtm or c5 or golden or fuzz or random or shard" > $O/pytest.log 2>&1; tail -5 $O/pytest.log
-for i in 1 2; do
-  python bench.py --workload c5 --steps 20 --warmup 3 --no-configs --no-e2e > $O/c5.json 2> $O/c5.err
-  python - $O/c5.json <<'PY'
+timeout 900 python -m pytest tests -m gpu -q -x -k "golden or strict or subrange or windows or fuzz or random or shard or smoke" > $O/pytest.log 2>&1; tail -5 $O/pytest.log
+for lib in "" _tt0 _tt8 "" _tt0 _tt8; do
+  for w in metric c1 c2; do
+  GLFER_B200_LIB=$PWD/glfer_b200/libglfer_b200$lib.so python bench.py --workload $w --steps 100 --warmup 5 --no-configs --no-e2e > $O/$w$lib.json 2> $O/$w$lib.err
+  python - $O/$w$lib.json "$w lib$lib" <<'PY'
 import json,sys
-d=json.load(open(sys.argv[1])); r=d["roofline"]; print("AB c5", r["kernel_ms"], r.get("fp32_tflops_5nlogn"))
+d=json.load(open(sys.argv[1])); r=d["roofline"]; print("AB", sys.argv[2], r["kernel_ms"], r["frac"])
 PY
+  done
 done
